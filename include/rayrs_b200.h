@@ -1,0 +1,249 @@
+/* rayrs_b200.h — C ABI of the B200 path-tracing backend for rayrs.
+ *
+ * This is the drop-in boundary.  The reference (Frojdholm/rayrs) has no FFI of its own; the
+ * seam this library replaces is the body of the rayon closure in rayrs/src/main.rs:61-94
+ * (pixel x spp loop calling Camera::generate_primary_ray lib.rs:202-210 and radiance
+ * lib.rs:521-560).  A Rust shim `rayrs_lib::gpu::render_gpu(&Camera, &Scene, spp,
+ * max_bounces) -> Image` binds exactly these symbols (INTEGRATION.md shows the stub); the
+ * C++ host mirror in rayrs_b200/host binds them the same way.
+ *
+ * Conventions
+ *  - plain C types only; every pointer is borrowed for the duration of the call;
+ *  - every entry point returns RRS_OK (0) or a negative RrsStatus and never unwinds;
+ *    rrs_last_error() returns the message of the calling thread's last failure;
+ *  - the reference panics on bad construction (assert!, e.g. geometry.rs:97,205-212;
+ *    lib.rs:234-235): the same conditions return RRS_ERR_INVALID here and the shim turns
+ *    a non-zero status into a panic;
+ *  - there is NO CPU fallback: with no usable CUDA device every call that needs one
+ *    fails with RRS_ERR_NO_DEVICE.
+ */
+#ifndef RAYRS_B200_H
+#define RAYRS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RRS_ABI_VERSION 1
+
+typedef enum RrsStatus {
+    RRS_OK = 0,
+    RRS_ERR_INVALID = -1,   /* bad argument / scene description (reference: assert! panic)   */
+    RRS_ERR_NO_DEVICE = -2, /* no CUDA device, or not an sm_100 part                          */
+    RRS_ERR_CUDA = -3,      /* CUDA runtime failure (message carries cudaGetErrorString)      */
+    RRS_ERR_TOO_DEEP = -4,  /* BVH deeper than the traversal stack (RRS_MAX_STACK)            */
+    RRS_ERR_NOMEM = -5
+} RrsStatus;
+
+/* Primitive kinds: the three Hittable impls reachable from the scene API
+ * (geometry.rs:72-157 Sphere, :159-304 Plane, :306-392 Triangle). */
+typedef enum RrsPrimType { RRS_SPHERE = 0, RRS_PLANE = 1, RRS_TRIANGLE = 2 } RrsPrimType;
+
+/* enum Axis, geometry.rs:159-167 (declaration order). */
+typedef enum RrsAxis { RRS_AXIS_X = 0, RRS_AXIS_XREV = 1, RRS_AXIS_Y = 2, RRS_AXIS_YREV = 3, RRS_AXIS_Z = 4, RRS_AXIS_ZREV = 5 } RrsAxis;
+
+/* enum Material, material.rs:57-68 (declaration order). */
+typedef enum RrsMaterialTag {
+    RRS_MAT_LAMBERTIAN = 0,
+    RRS_MAT_REFLECT = 1,
+    RRS_MAT_REFRACT = 2,
+    RRS_MAT_GLASS = 3,
+    RRS_MAT_COOK_TORRANCE = 4,
+    RRS_MAT_COOK_TORRANCE_REFRACT = 5,
+    RRS_MAT_COOK_TORRANCE_GLASS = 6,
+    RRS_MAT_PLASTIC = 7,
+    RRS_MAT_NO_REFLECT = 8
+} RrsMaterialTag;
+
+/* enum Fresnel, material.rs:124-129. */
+typedef enum RrsFresnelKind { RRS_FRESNEL_DIELECTRIC = 0, RRS_FRESNEL_METALLIC = 1 } RrsFresnelKind;
+
+/* One primitive, in the DFS leaf order of the reference tree (bvh.rs:391-415 visits
+ * children left to right, so this order is the tie-break priority among equal t).
+ * Geometry is carried in f64 exactly as the reference stores it; the library derives its
+ * own fp32 records.
+ *   sphere  : v[0]=radius^2 (Sphere stores radius2, geometry.rs:98-101), v[1..3]=centre
+ *   plane   : v[0]=axis (RrsAxis), v[1]=umin v[2]=umax v[3]=vmin v[4]=vmax v[5]=pos
+ *   triangle: v[0..2]=p1, v[3..5]=p2, v[6..8]=p3 */
+typedef struct RrsPrim {
+    uint32_t type;     /* RrsPrimType */
+    uint32_t obj_id;   /* index of the object in the Vec<Object> given to Scene::new (lib.rs:227) */
+    uint32_t material; /* index into RrsSceneDesc.materials */
+    int32_t emission;  /* index into RrsSceneDesc.emissions, -1 = Emission::Dark */
+    double v[9];
+} RrsPrim;
+
+/* Material parameters as the constructors take them (material.rs:595-716). */
+typedef struct RrsMaterial {
+    uint32_t tag;          /* RrsMaterialTag */
+    uint32_t fresnel_kind; /* RrsFresnelKind; CookTorrance only (others are dielectric(ior)) */
+    double color[3];
+    double spec_color[3];  /* Plastic: spec_color; CookTorrance metallic: r0 */
+    double alpha;          /* roughness alpha (the library squares it like CookTorrance::new) */
+    double ior;
+} RrsMaterial;
+
+/* Emission::Emissive(strength, color), material.rs:1048-1084. */
+typedef struct RrsEmission {
+    double strength;
+    double color[3];
+} RrsEmission;
+
+/* Child reference of a BVH node.  bit31 set: leaf run of primitives —
+ * bits 0..27 = first primitive (index into prims), bits 28..30 = count-1 (1..4 prims,
+ * bvh.rs:221-224,304-315: leaf groups hold <= 4 objects).  bit31 clear: index of another
+ * RrsNode.  RRS_REF_EMPTY: no child (dead subtree, see `nodes`). */
+#define RRS_REF_LEAF 0x80000000u
+#define RRS_REF_EMPTY 0xFFFFFFFFu
+#define RRS_MAKE_LEAF(first, count) (RRS_REF_LEAF | (((uint32_t)(count)-1u) << 28) | (uint32_t)(first))
+
+/* 64-byte BVH node: one binary `BvhTree::Node` of the reference tree (bvh.rs:216-224) with
+ * the boxes of BOTH children stored in the parent, so that one 2x256-bit fetch decides both
+ * descents.  lo/hi are fp32, rounded outward from the f64 boxes of the reference.
+ *  - child that is a `Node`          : box = that node's own bbox (geometry.rs:544-550);
+ *  - child that is a bare `LeafNode` : the reference tests it whenever the parent is entered
+ *    (it has no box); box = the primitive's bbox, or the parent's box if that is degenerate;
+ *  - a `Node` whose own f64 box has zero extent on an axis can never be entered by the
+ *    reference slab test (geometry.rs:474,491,508: tmax <= tmin) — it is stored as
+ *    RRS_REF_EMPTY with an inverted box;
+ *  - node 0 is a virtual root: child0 = the reference root (with its bbox), child1 empty.
+ * NaN-free by construction. */
+typedef struct RrsNode {
+    float lo0[3], hi0[3];
+    float lo1[3], hi1[3];
+    uint32_t ref0, ref1;
+    uint32_t flags; /* bit0: child0 has no box of its own in the reference (bare LeafNode); bit1: same for child1 */
+    uint32_t pad;
+} RrsNode;
+
+/* f64 twin of RrsNode holding the reference's exact boxes; used only by the fp64
+ * verification traversal (precision=64 in rrs_intersect). 128 bytes. */
+typedef struct RrsNodeF64 {
+    double lo0[3], hi0[3];
+    double lo1[3], hi1[3];
+    uint32_t ref0, ref1;
+    uint32_t flags;
+    uint32_t pad[5];
+} RrsNodeF64;
+
+typedef struct RrsSceneDesc {
+    uint32_t abi_version; /* RRS_ABI_VERSION */
+    uint32_t n_prims;
+    const RrsPrim* prims;
+    uint32_t n_nodes;
+    const RrsNode* nodes;
+    const RrsNodeF64* nodes_f64; /* may be NULL: precision=64 queries then fail with RRS_ERR_INVALID */
+    uint32_t max_depth;          /* deepest node-stack the tree can need (host computes it) */
+    uint32_t n_materials;
+    const RrsMaterial* materials;
+    uint32_t n_emissions;
+    const RrsEmission* emissions;
+    /* equirectangular environment, row-major RGB f32, already clipped by the caller as
+     * rayrs/src/main.rs:43 does (Scene::background, lib.rs:254-285) */
+    uint32_t hdri_width, hdri_height;
+    const float* hdri_rgb;
+    /* Scene::new z_near / z_far (lib.rs:227-245; main.rs:52 passes 1e-6, 1e6) */
+    double t_min, t_max;
+} RrsSceneDesc;
+
+/* Derived camera fields exactly as Camera::new computes them (lib.rs:113-132), so that the
+ * FOV quirk (z scaled by width/tan(fov/2)) stays on the host. */
+typedef struct RrsCamera {
+    double origin[3];
+    double e_x[3];
+    double e_y[3];
+    double z_scaled[3];
+    double width, height; /* film size in cm */
+    uint32_t ppc;         /* pixels per cm */
+    uint32_t x_pixels, y_pixels;
+} RrsCamera;
+
+typedef struct RrsRenderParams {
+    uint32_t width, height;   /* must equal camera x_pixels / y_pixels */
+    uint32_t spp;             /* samples per pixel rendered by THIS call */
+    uint32_t sample_offset;   /* global index of the first sample (multi-GPU sample split) */
+    uint32_t spp_total;       /* divisor for the mean written by rrs_render (0 => spp) */
+    uint32_t max_bounces;     /* rayrs/src/main.rs:77 passes 50 */
+    uint64_t seed;            /* key of the counter-based RNG */
+    uint32_t queue_capacity;  /* rays in flight; 0 = library default */
+    uint32_t flags;           /* reserved, 0 */
+} RrsRenderParams;
+
+typedef struct RrsRay {
+    double origin[3];
+    double direction[3]; /* not normalised, like lib.rs:25-32 */
+} RrsRay;
+
+typedef struct RrsStats {
+    uint64_t rays;            /* BVH queries (primary + every bounce) of the last render */
+    uint64_t paths;           /* primary rays of the last render */
+    uint64_t kernel_launches; /* kernels launched by the last render */
+    uint64_t iterations;      /* wavefront iterations of the last render */
+    uint64_t nan_pixels;      /* pixels with a NaN component (main.rs:81-83) */
+    uint64_t negative_pixels; /* pixels with a negative component (main.rs:85-87) */
+    double device_ms;         /* CUDA-event time of the last render (all kernels) */
+    double extend_ms;         /* ... of its extend (traversal) launches, when profiling is on */
+    double shade_ms;
+    double generate_ms;
+    uint64_t nodes_visited;   /* only with RRS_FLAG_COUNT_TRAVERSAL */
+    uint64_t prims_tested;
+} RrsStats;
+
+#define RRS_FLAG_COUNT_TRAVERSAL 1u /* count nodes/primitives touched (slower; for the bytes/ray model) */
+#define RRS_FLAG_TIME_PHASES 2u     /* CUDA-event time every phase separately (adds syncs-free events) */
+
+typedef struct RrsScene RrsScene;
+
+/* Scene::new (lib.rs:227-245) device half: validates, converts and uploads. */
+int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out);
+void rrs_scene_destroy(RrsScene* scene);
+
+/* The render call (replaces rayrs/src/main.rs:61-94).  out_rgb: HOST buffer of
+ * height*width*3 floats, row-major, row 0 = top (image.rs:140-165 layout); receives the
+ * per-pixel MEAN radiance over spp_total samples (main.rs:89).  Synchronous. */
+int rrs_render(RrsScene* scene, const RrsCamera* camera, const RrsRenderParams* params, float* out_rgb);
+
+/* Same, but ACCUMULATES the per-pixel radiance SUM of this call's samples into a DEVICE
+ * buffer of height*width float4 (rgb + sample count in .w), enqueued on `cuda_stream`
+ * (a cudaStream_t; NULL = default stream) and not synchronised.  Used for the multi-GPU
+ * sample split: each GPU accumulates its slice, one reduce merges the buffers. */
+int rrs_render_accumulate(RrsScene* scene, const RrsCamera* camera, const RrsRenderParams* params,
+                          void* d_sum_rgba, void* cuda_stream);
+
+/* d_sum_rgba (device, float4 per pixel) -> out (device or host per `out_is_device`) mean
+ * RGB f32, dividing by spp_total, and counting NaN / negative pixels into the stats. */
+int rrs_resolve(RrsScene* scene, const void* d_sum_rgba, uint32_t width, uint32_t height, uint32_t spp_total,
+                float* out_rgb, int out_is_device, void* cuda_stream);
+
+/* Closest hit for a batch of rays — Bvh::intersect (bvh.rs:212-214) with the scene's
+ * (t_min, t_max).  obj_id[i] = RrsPrim.obj_id of the hit or -1; t[i] = distance or +inf.
+ * precision 32: the production fp32 traversal (ordered, t-pruned).
+ * precision 64: fp64 literal traversal (reference visiting order, no pruning, no FMA)
+ *               for verification. */
+int rrs_intersect(RrsScene* scene, const RrsRay* rays, size_t n, int32_t* obj_id, double* t, int precision);
+
+/* Material::evaluate (material.rs:91-109, pdf=None) for a batch: normal_view = n x 6 doubles
+ * (unit normal, unit view), u = n x 3 uniforms in call order; out = n x 7 floats
+ * [scatter flag, color rgb, direction xyz].  Parity probe for the shading kernels. */
+int rrs_material_evaluate(RrsScene* scene, uint32_t material, const double* normal_view, const double* u,
+                          size_t n, float* out);
+
+/* Scene::background (lib.rs:254-285) for a batch of directions (n x 3 doubles) -> n x 3 floats. */
+int rrs_background(RrsScene* scene, const double* dirs, size_t n, float* out);
+
+/* The uniforms the device RNG hands to (pixel, sample, slot): 4 floats. */
+int rrs_rng_uniforms(RrsScene* scene, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, float* out4);
+
+int rrs_stats(RrsScene* scene, RrsStats* out);
+const char* rrs_last_error(void);
+int rrs_abi_version(void);
+/* number of usable sm_100 devices (0 => every device call fails with RRS_ERR_NO_DEVICE) */
+int rrs_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAYRS_B200_H */

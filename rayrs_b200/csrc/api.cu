@@ -1,0 +1,319 @@
+// C ABI of the backend (include/rayrs_b200.h): scene validation, fp32 conversion, upload,
+// and the thin entry points over wavefront.cu / verify_f64.cu.
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "wavefront.cuh"
+
+using namespace rrs;
+
+struct RrsScene {
+    SceneImpl impl;
+};
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+static bool in01(const double* c) {
+    for (int k = 0; k < 3; ++k)
+        if (!(c[k] >= 0. && c[k] <= 1.)) return false;
+    return true;
+}
+
+static int usable_devices() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ok++;
+    }
+    return ok;
+}
+
+template <typename T>
+static int upload(T** dst, const T* src, size_t n, std::string& err) {
+    RRS_CUDA_CHECK(cudaMalloc(dst, sizeof(T) * std::max<size_t>(n, 1)), err);
+    if (n) RRS_CUDA_CHECK(cudaMemcpy(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice), err);
+    return RRS_OK;
+}
+
+extern "C" {
+
+int rrs_abi_version(void) { return RRS_ABI_VERSION; }
+const char* rrs_last_error(void) { return g_last_error.c_str(); }
+int rrs_device_count(void) { return usable_devices(); }
+
+int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
+    if (!desc || !out) return fail(RRS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (desc->abi_version != RRS_ABI_VERSION) return fail(RRS_ERR_INVALID, "ABI version mismatch");
+    // --- validation: the reference's construction-time assert!s -------------------------
+    if (desc->n_prims == 0 || !desc->prims) return fail(RRS_ERR_INVALID, "a BVH for 0 objects does not make sense (bvh.rs:229)");
+    if (desc->n_prims >= (1u << 28)) return fail(RRS_ERR_INVALID, "too many primitives (max 2^28-1)");
+    if (desc->n_nodes == 0 || !desc->nodes) return fail(RRS_ERR_INVALID, "no BVH nodes");
+    if (!(desc->t_min >= 0.)) return fail(RRS_ERR_INVALID, "z_near must be >= 0 (lib.rs:234)");
+    if (!(desc->t_max > desc->t_min)) return fail(RRS_ERR_INVALID, "z_far must be > z_near (lib.rs:235)");
+    if (desc->n_materials == 0 || !desc->materials) return fail(RRS_ERR_INVALID, "no materials");
+    if (desc->hdri_width < 2 || desc->hdri_height < 2 || !desc->hdri_rgb) return fail(RRS_ERR_INVALID, "HDRI must be at least 2x2");
+    for (uint32_t i = 0; i < desc->n_materials; ++i) {
+        const RrsMaterial& m = desc->materials[i];
+        if (m.tag > RRS_MAT_NO_REFLECT) return fail(RRS_ERR_INVALID, "unknown material tag");
+        if (m.tag == RRS_MAT_NO_REFLECT) continue;
+        if (!in01(m.color)) return fail(RRS_ERR_INVALID, "material color must be within [0,1] (material.rs:597)");
+        bool rough = m.tag == RRS_MAT_COOK_TORRANCE || m.tag == RRS_MAT_COOK_TORRANCE_REFRACT ||
+                     m.tag == RRS_MAT_COOK_TORRANCE_GLASS || m.tag == RRS_MAT_PLASTIC;
+        bool has_ior = m.tag == RRS_MAT_REFRACT || m.tag == RRS_MAT_GLASS || m.tag == RRS_MAT_COOK_TORRANCE_REFRACT ||
+                       m.tag == RRS_MAT_COOK_TORRANCE_GLASS || m.tag == RRS_MAT_PLASTIC ||
+                       (m.tag == RRS_MAT_COOK_TORRANCE && m.fresnel_kind == RRS_FRESNEL_DIELECTRIC);
+        if (rough && !(m.alpha > 0. && std::isfinite(m.alpha))) return fail(RRS_ERR_INVALID, "alpha must be positive and finite (material.rs:706-707)");
+        if (has_ior && !(m.ior > 0. && std::isfinite(m.ior))) return fail(RRS_ERR_INVALID, "ior must be positive and finite (material.rs:629-630)");
+        if (m.tag == RRS_MAT_PLASTIC && !in01(m.spec_color)) return fail(RRS_ERR_INVALID, "spec_color must be within [0,1] (material.rs:882)");
+        if (m.fresnel_kind > RRS_FRESNEL_METALLIC) return fail(RRS_ERR_INVALID, "unknown Fresnel kind");
+    }
+    for (uint32_t i = 0; i < desc->n_emissions; ++i) {
+        if (!(desc->emissions[i].strength >= 0.)) return fail(RRS_ERR_INVALID, "emission strength must be >= 0 (material.rs:1064)");
+        if (!in01(desc->emissions[i].color)) return fail(RRS_ERR_INVALID, "RGB values need to be between 0 and 1 (material.rs:1065-1068)");
+    }
+    for (uint32_t i = 0; i < desc->n_prims; ++i) {
+        const RrsPrim& p = desc->prims[i];
+        if (p.type > RRS_TRIANGLE) return fail(RRS_ERR_INVALID, "unknown primitive type");
+        if (p.material >= desc->n_materials) return fail(RRS_ERR_INVALID, "primitive material index out of range");
+        if (p.emission >= (int32_t)desc->n_emissions) return fail(RRS_ERR_INVALID, "primitive emission index out of range");
+        if (p.type == RRS_SPHERE && !(p.v[0] > 0.)) return fail(RRS_ERR_INVALID, "Radius has to be positive (geometry.rs:97)");
+        if (p.type == RRS_PLANE) {
+            if (!(p.v[0] >= 0. && p.v[0] <= 5.)) return fail(RRS_ERR_INVALID, "unknown plane axis");
+            if (!(p.v[1] < p.v[2] && p.v[3] < p.v[4])) return fail(RRS_ERR_INVALID, "Plane cannot be constructed with umin >= umax or vmin >= vmax (geometry.rs:205-212)");
+        }
+        for (int k = 0; k < 9; ++k)
+            if (std::isnan(p.v[k])) return fail(RRS_ERR_INVALID, "NaN in primitive (bvh.rs:104 partial_cmp().unwrap() panics)");
+    }
+    for (uint32_t i = 0; i < desc->n_nodes; ++i) {
+        const RrsNode& nd = desc->nodes[i];
+        const uint32_t refs[2] = {nd.ref0, nd.ref1};
+        for (uint32_t r : refs) {
+            if (r == RRS_REF_EMPTY) continue;
+            if (r & RRS_REF_LEAF) {
+                uint32_t first = r & 0x0FFFFFFFu, count = ((r >> 28) & 7u) + 1u;
+                if (count > 4 || first + count > desc->n_prims) return fail(RRS_ERR_INVALID, "leaf run out of range");
+            } else if (r >= desc->n_nodes || r == 0) {
+                return fail(RRS_ERR_INVALID, "node reference out of range");
+            }
+        }
+    }
+    if (desc->max_depth + 2 > 120) return fail(RRS_ERR_TOO_DEEP, "BVH deeper than the 118-entry shared-memory traversal stack");
+
+    // --- device ---------------------------------------------------------------------------
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(RRS_ERR_NO_DEVICE, "no CUDA device: rayrs_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(RRS_ERR_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    std::string err;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(RRS_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10) return fail(RRS_ERR_NO_DEVICE, std::string("device is not sm_100 (") + prop.name + "): kernels are built for sm_100a only");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(RRS_ERR_CUDA, "cudaSetDevice failed");
+
+    auto* sc = new RrsScene();
+    SceneImpl& s = sc->impl;
+    s.device = device;
+    s.num_sms = prop.multiProcessorCount;
+    s.n_prims = desc->n_prims;
+    s.n_nodes = desc->n_nodes;
+    s.max_depth = desc->max_depth;
+    s.tmin = desc->t_min;
+    s.tmax = desc->t_max;
+
+    // --- fp32 records ---------------------------------------------------------------------
+    std::vector<DPrim> hp(desc->n_prims);
+    for (uint32_t i = 0; i < desc->n_prims; ++i) {
+        const RrsPrim& p = desc->prims[i];
+        DPrim q;
+        uint32_t meta = p.type | (p.material << 2);
+        float fmeta, fobj, femi;
+        int32_t emi = p.emission;
+        std::memcpy(&fmeta, &meta, 4);
+        std::memcpy(&fobj, &p.obj_id, 4);
+        std::memcpy(&femi, &emi, 4);
+        if (p.type == RRS_TRIANGLE) {
+            // Triangle::new geometry.rs:341-355: edges derived in f64, then rounded
+            q.a = make_float4((float)p.v[0], (float)p.v[1], (float)p.v[2], fmeta);
+            q.b = make_float4((float)(p.v[3] - p.v[0]), (float)(p.v[4] - p.v[1]), (float)(p.v[5] - p.v[2]), fobj);
+            q.c = make_float4((float)(p.v[6] - p.v[0]), (float)(p.v[7] - p.v[1]), (float)(p.v[8] - p.v[2]), femi);
+        } else if (p.type == RRS_SPHERE) {
+            q.a = make_float4((float)p.v[1], (float)p.v[2], (float)p.v[3], fmeta);
+            q.b = make_float4((float)p.v[0], 0.f, 0.f, fobj);
+            q.c = make_float4(0.f, 0.f, 0.f, femi);
+        } else {
+            uint32_t axis = (uint32_t)p.v[0];
+            float faxis;
+            std::memcpy(&faxis, &axis, 4);
+            q.a = make_float4((float)p.v[5], (float)p.v[1], (float)p.v[2], fmeta);
+            q.b = make_float4((float)p.v[3], (float)p.v[4], faxis, fobj);
+            q.c = make_float4(0.f, 0.f, 0.f, femi);
+        }
+        hp[i] = q;
+    }
+    std::vector<DMat> hm(desc->n_materials);
+    for (uint32_t i = 0; i < desc->n_materials; ++i) {
+        const RrsMaterial& m = desc->materials[i];
+        float ftag, fkind;
+        uint32_t kind = m.fresnel_kind;
+        if (m.tag != RRS_MAT_COOK_TORRANCE) kind = RRS_FRESNEL_DIELECTRIC;
+        std::memcpy(&ftag, &m.tag, 4);
+        std::memcpy(&fkind, &kind, 4);
+        double r0 = (1. - m.ior) / (1. + m.ior);  // schlick_scalar r0, material.rs:1476-1477 (symmetric in the two iors)
+        r0 = r0 * r0;
+        DMat d;
+        d.m0 = make_float4((float)m.color[0], (float)m.color[1], (float)m.color[2], ftag);
+        d.m1 = make_float4((float)m.spec_color[0], (float)m.spec_color[1], (float)m.spec_color[2], (float)(m.alpha * m.alpha));
+        d.m2 = make_float4((float)m.ior, fkind, (float)r0, 0.f);
+        hm[i] = d;
+    }
+    std::vector<float4> he(std::max<uint32_t>(desc->n_emissions, 1));
+    for (uint32_t i = 0; i < desc->n_emissions; ++i) {
+        const RrsEmission& e = desc->emissions[i];
+        he[i] = make_float4((float)(e.strength * e.color[0]), (float)(e.strength * e.color[1]), (float)(e.strength * e.color[2]), 0.f);
+    }
+    size_t ntex = (size_t)desc->hdri_width * desc->hdri_height;
+    std::vector<float4> hh(ntex);
+    for (size_t i = 0; i < ntex; ++i)
+        hh[i] = make_float4(desc->hdri_rgb[3 * i], desc->hdri_rgb[3 * i + 1], desc->hdri_rgb[3 * i + 2], 0.f);
+
+    int rc = RRS_OK;
+    static_assert(sizeof(RrsNode) == 64, "RrsNode must be 64 bytes");
+    static_assert(sizeof(RrsNodeF64) == 128, "RrsNodeF64 must be 128 bytes");
+    if (rc == RRS_OK) rc = upload(&s.prims, hp.data(), hp.size(), err);
+    if (rc == RRS_OK) rc = upload(reinterpret_cast<RrsNode**>(&s.nodes), desc->nodes, desc->n_nodes, err);
+    if (rc == RRS_OK) rc = upload(&s.mats, hm.data(), hm.size(), err);
+    if (rc == RRS_OK) rc = upload(&s.emis, he.data(), he.size(), err);
+    if (rc == RRS_OK) rc = upload(&s.hdri, hh.data(), hh.size(), err);
+    if (rc == RRS_OK && desc->nodes_f64) {
+        rc = upload(&s.nodes_f64, desc->nodes_f64, desc->n_nodes, err);
+        if (rc == RRS_OK) rc = upload(&s.prims_f64, desc->prims, desc->n_prims, err);
+    }
+    if (rc != RRS_OK) {
+        rrs_scene_destroy(sc);
+        return fail(rc, err);
+    }
+    s.d.prims = s.prims;
+    s.d.nodes = s.nodes;
+    s.d.mats = s.mats;
+    s.d.emis = s.emis;
+    s.d.hdri = s.hdri;
+    s.d.n_prims = desc->n_prims;
+    s.d.n_nodes = desc->n_nodes;
+    s.d.n_mats = desc->n_materials;
+    s.d.hdri_w = desc->hdri_width;
+    s.d.hdri_h = desc->hdri_height;
+    s.d.tmin = (float)desc->t_min;
+    s.d.tmax = (float)desc->t_max;
+    s.d.stack_entries = std::max<uint32_t>(desc->max_depth + 2, 4);
+    s.d.smem_nodes = 0;
+    *out = sc;
+    return RRS_OK;
+}
+
+void rrs_scene_destroy(RrsScene* scene) {
+    if (!scene) return;
+    SceneImpl& s = scene->impl;
+    cudaSetDevice(s.device);
+    wf_free(&s);
+    cudaFree(s.prims); cudaFree(s.nodes); cudaFree(s.mats); cudaFree(s.emis); cudaFree(s.hdri);
+    cudaFree(s.prims_f64); cudaFree(s.nodes_f64); cudaFree(s.accum); cudaFree(s.census);
+    delete scene;
+}
+
+int rrs_render_accumulate(RrsScene* scene, const RrsCamera* camera, const RrsRenderParams* params, void* d_sum_rgba,
+                          void* cuda_stream) {
+    if (!scene) return fail(RRS_ERR_INVALID, "null scene");
+    std::string err;
+    int rc = wf_render_accumulate(&scene->impl, camera, params, static_cast<float4*>(d_sum_rgba),
+                                  static_cast<cudaStream_t>(cuda_stream), err);
+    return rc == RRS_OK ? rc : fail(rc, err);
+}
+
+int rrs_resolve(RrsScene* scene, const void* d_sum_rgba, uint32_t width, uint32_t height, uint32_t spp_total, float* out_rgb,
+                int out_is_device, void* cuda_stream) {
+    if (!scene) return fail(RRS_ERR_INVALID, "null scene");
+    std::string err;
+    int rc = wf_resolve(&scene->impl, static_cast<const float4*>(d_sum_rgba), width, height, spp_total, out_rgb,
+                        out_is_device != 0, static_cast<cudaStream_t>(cuda_stream), err);
+    return rc == RRS_OK ? rc : fail(rc, err);
+}
+
+int rrs_render(RrsScene* scene, const RrsCamera* camera, const RrsRenderParams* params, float* out_rgb) {
+    if (!scene || !camera || !params || !out_rgb) return fail(RRS_ERR_INVALID, "null argument");
+    SceneImpl& s = scene->impl;
+    std::string err;
+    if (cudaSetDevice(s.device) != cudaSuccess) return fail(RRS_ERR_CUDA, "cudaSetDevice failed");
+    size_t npix = (size_t)params->width * params->height;
+    if (npix == 0) return fail(RRS_ERR_INVALID, "empty image");
+    if (s.accum_pixels != npix) {
+        cudaFree(s.accum);
+        s.accum = nullptr;
+        if (cudaMalloc(&s.accum, sizeof(float4) * npix) != cudaSuccess) return fail(RRS_ERR_NOMEM, "cudaMalloc(accumulator) failed");
+        s.accum_pixels = npix;
+    }
+    if (cudaMemsetAsync(s.accum, 0, sizeof(float4) * npix, nullptr) != cudaSuccess) return fail(RRS_ERR_CUDA, "cudaMemsetAsync failed");
+    int rc = wf_render_accumulate(&s, camera, params, s.accum, nullptr, err);
+    if (rc != RRS_OK) return fail(rc, err);
+    uint64_t launches = s.stats.kernel_launches;
+    uint32_t div = params->spp_total ? params->spp_total : params->spp;
+    if (div == 0) div = 1;
+    rc = wf_resolve(&s, s.accum, params->width, params->height, div, out_rgb, false, nullptr, err);
+    if (rc != RRS_OK) return fail(rc, err);
+    s.stats.kernel_launches = launches + 1;
+    return RRS_OK;
+}
+
+int rrs_intersect(RrsScene* scene, const RrsRay* rays, size_t n, int32_t* obj_id, double* t, int precision) {
+    if (!scene || (n && (!rays || !obj_id || !t))) return fail(RRS_ERR_INVALID, "null argument");
+    std::string err;
+    int rc;
+    if (precision == 32) rc = wf_intersect32(&scene->impl, rays, n, obj_id, t, err);
+    else if (precision == 64) rc = vf_intersect64(&scene->impl, rays, n, obj_id, t, err);
+    else return fail(RRS_ERR_INVALID, "precision must be 32 or 64");
+    return rc == RRS_OK ? rc : fail(rc, err);
+}
+
+int rrs_material_evaluate(RrsScene* scene, uint32_t material, const double* normal_view, const double* u, size_t n,
+                          float* out) {
+    if (!scene || (n && (!normal_view || !u || !out))) return fail(RRS_ERR_INVALID, "null argument");
+    std::string err;
+    int rc = wf_material_evaluate(&scene->impl, material, normal_view, u, n, out, err);
+    return rc == RRS_OK ? rc : fail(rc, err);
+}
+
+int rrs_background(RrsScene* scene, const double* dirs, size_t n, float* out) {
+    if (!scene || (n && (!dirs || !out))) return fail(RRS_ERR_INVALID, "null argument");
+    std::string err;
+    int rc = wf_background(&scene->impl, dirs, n, out, err);
+    return rc == RRS_OK ? rc : fail(rc, err);
+}
+
+int rrs_rng_uniforms(RrsScene* scene, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, float* out4) {
+    if (!scene || !out4) return fail(RRS_ERR_INVALID, "null argument");
+    std::string err;
+    int rc = wf_rng_uniforms(&scene->impl, seed, pixel, sample, slot, out4, err);
+    return rc == RRS_OK ? rc : fail(rc, err);
+}
+
+int rrs_stats(RrsScene* scene, RrsStats* out) {
+    if (!scene || !out) return fail(RRS_ERR_INVALID, "null argument");
+    *out = scene->impl.stats;
+    return RRS_OK;
+}
+
+}  // extern "C"

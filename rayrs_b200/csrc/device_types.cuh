@@ -1,0 +1,117 @@
+// Device-side records and small math helpers shared by every kernel of the backend.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rayrs_b200.h"
+
+namespace rrs {
+
+// ---------------------------------------------------------------------------------------
+// HBM layout
+// ---------------------------------------------------------------------------------------
+// Primitive record, 48 B, three float4 so that it is fetched with 128-bit loads.
+//   meta = type | material << 2          (a.w)
+//   triangle : a = (p1, meta)  b = (e1, obj_id)  c = (e2, emission)
+//   sphere   : a = (centre, meta) b = (r^2, -, -, obj_id) c = (-, -, -, emission)
+//   plane    : a = (pos, umin, umax, meta) b = (vmin, vmax, axis, obj_id) c = (-, -, -, emission)
+struct DPrim {
+    float4 a, b, c;
+};
+static_assert(sizeof(DPrim) == 48, "DPrim must be 48 bytes");
+
+// Material record, 48 B.
+//   m0 = (color rgb, tag)
+//   m1 = (spec / r0 rgb, alpha^2)
+//   m2 = (ior, fresnel kind, r0 of the dielectric ((1-ior)/(1+ior))^2, -)
+struct DMat {
+    float4 m0, m1, m2;
+};
+
+// 64-byte node as two 32-byte halves (each fetched by one 256-bit load):
+//   h0 = lo0.xyz hi0.xyz lo1.xy          h1 = lo1.z hi1.xyz ref0 ref1 flags pad
+// which is exactly the memory image of RrsNode.
+struct __align__(32) DNodeHalf {
+    float f[8];
+};
+
+#define RRS_NO_PRIM 0xFFFFFFFFu
+
+// ---------------------------------------------------------------------------------------
+// float3 helpers (no operator overloading on CUDA's builtin float3 to keep call sites explicit
+// about rounding order)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 add3(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 sub3(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 mul3(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 scale3(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ float3 cross3(float3 a, float3 b) {
+    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float3 normalize3(float3 a) { return scale3(a, rsqrtf(dot3(a, a))); }
+__device__ __forceinline__ float3 neg3(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float3 madd3(float3 a, float s, float3 b) {  // a*s + b
+    return f3(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z));
+}
+__device__ __forceinline__ float3 xyz(float4 v) { return f3(v.x, v.y, v.z); }
+
+// ---------------------------------------------------------------------------------------
+// Counter-based RNG: Philox4x32-10 (Salmon et al. 2011).  counter = (pixel, sample, slot, 0),
+// key = seed.  slot 0 = camera jitter, slot b+1 = bounce b (words 0..2 material draws in the
+// reference's call order, word 3 = Russian roulette).  Keyed by the GLOBAL sample index, so
+// the set of paths is independent of how samples are split across GPUs.
+// ---------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                       uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+        uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+#else
+        uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// uniform in [0,1) with 24 bits: the same value the oracle uses in its sample-matched mode
+__host__ __device__ __forceinline__ float u01(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }
+
+__device__ __forceinline__ float4 rng_uniforms(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t slot) {
+    uint32_t w[4];
+    philox4x32_10(pixel, sample, slot, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+    return make_float4(u01(w[0]), u01(w[1]), u01(w[2]), u01(w[3]));
+}
+
+// ---------------------------------------------------------------------------------------
+// Scene as the kernels see it
+// ---------------------------------------------------------------------------------------
+struct DScene {
+    const DPrim* prims;
+    const DNodeHalf* nodes;  // 2 halves per node
+    const DMat* mats;
+    const float4* emis;      // (strength*color, -)
+    const float4* hdri;      // RGBA f32 texels
+    uint32_t n_prims, n_nodes, n_mats;
+    uint32_t hdri_w, hdri_h;
+    float tmin, tmax;
+    uint32_t stack_entries;  // per-thread traversal stack size (entries)
+    uint32_t smem_nodes;     // top-of-tree nodes staged in shared memory (0 = none)
+};
+
+struct DCamera {
+    float3 origin, e_x, e_y, z;
+    float inv_ppc, half_w, half_h;
+    uint32_t W, H;
+};
+
+}  // namespace rrs

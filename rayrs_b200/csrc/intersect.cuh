@@ -1,0 +1,202 @@
+// fp32 primitive tests and the ordered, t-pruned stack traversal of the flattened reference
+// BVH (production path).  Semantics follow rayrs-lib:
+//   Sphere::intersect   geometry.rs:106-132     Plane::intersect  geometry.rs:229-271
+//   Triangle::intersect geometry.rs:359-375     leaf filter t>tmin && t<tmax  bvh.rs:404-413
+//   closest hit = smallest t, ties -> first leaf in DFS order (bvh.rs:50-72,395-399)
+#pragma once
+#include "device_types.cuh"
+
+namespace rrs {
+
+// 256-bit read-only load (LDG.E.ENL2.256.CONSTANT on sm_100a): one instruction per node half.
+__device__ __forceinline__ void ldg256(const DNodeHalf* p, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+
+__device__ __forceinline__ uint32_t prim_type(float4 a) { return __float_as_uint(a.w) & 3u; }
+__device__ __forceinline__ uint32_t prim_material(float4 a) { return __float_as_uint(a.w) >> 2; }
+
+// Sphere, cancellation-safe form (Haines et al., "Precision improvements for ray/sphere
+// intersection").  Same decisions as the reference: needs desc > 0, returns the near root if
+// it is >= 0, else the far root if that is >= 0.
+//
+// self == true: the ray was spawned ON this sphere.  In the f64 reference the near root is
+// then +-1e-16 and its SIGN (rounding noise of the hit position) decides the outcome: near
+// root >= 0 is returned and rejected by the leaf's t > tmin, so the far hit is lost; < 0
+// falls through to the far root.  fp32 cannot reproduce that ray by ray;
+// it reproduces it in distribution with the same mechanism: the sign of c = |o-centre|^2 - r^2
+// evaluated on the fp32 hit position.
+__device__ __forceinline__ bool hit_sphere(float4 a, float4 b, float3 o, float3 d, bool self, float& t) {
+    float3 f = sub3(o, xyz(a));
+    float r2 = b.x;
+    float aa = dot3(d, d);
+    float bp = -dot3(f, d);
+    float c = dot3(f, f) - r2;
+    if (self) {
+        if (bp <= 0.f) return false;  // leaving the surface: both roots <= ~0 -> rejected by tmin
+        if (c >= 0.f) return false;   // near root >= 0 -> returned -> rejected by tmin (F7)
+    }
+    float inv_a = 1.0f / aa;
+    float3 l = madd3(d, bp * inv_a, f);  // f + (b'/a) d : closest approach to the centre
+    float disc = r2 - dot3(l, l);        // == (b'^2 - a c) / a, without the cancellation
+    if (!(disc > 0.f)) return false;
+    float sq = sqrtf(aa * disc);
+    float q = bp + copysignf(sq, bp);
+    float t_a = q * inv_a;  // root of larger magnitude
+    float t_b = c / q;      // the other root
+    float t1 = fminf(t_a, t_b), t2 = fmaxf(t_a, t_b);
+    if (self) {
+        t = t2;
+        return true;
+    }
+    if (t1 < 0.f) {
+        if (t2 < 0.f) return false;
+        t = t2;
+        return true;
+    }
+    t = t1;
+    return true;
+}
+
+// Plane: a = (pos, umin, umax, meta), b = (vmin, vmax, axis, obj).  Half-open ranges, any
+// sign of t is returned (the leaf filter removes t <= tmin).
+__device__ __forceinline__ bool hit_plane(float4 a, float4 b, float3 o, float3 d, float& t) {
+    uint32_t axis = __float_as_uint(b.z) >> 1;  // 0:x 1:y 2:z
+    float ok = axis == 0 ? o.x : (axis == 1 ? o.y : o.z);
+    float dk = axis == 0 ? d.x : (axis == 1 ? d.y : d.z);
+    if (dk == 0.f) return false;
+    float tt = (a.x - ok) / dk;
+    float3 p = madd3(d, tt, o);
+    float u = axis == 0 ? p.y : p.x;
+    float v = axis == 2 ? p.y : p.z;
+    if (u >= a.y && u < a.z && v >= b.x && v < b.y) {
+        t = tt;
+        return true;
+    }
+    return false;
+}
+
+// Triangle: Moeller-Trumbore exactly as coded (no determinant epsilon, two-sided).  NaN/inf
+// quotients fall out at the caller's t > tmin && t < tbest.
+__device__ __forceinline__ bool hit_triangle(float4 a, float4 b, float4 c, float3 o, float3 d, float& t) {
+    float3 e1 = xyz(b), e2 = xyz(c);
+    float3 T = sub3(o, xyz(a));
+    float3 P = cross3(d, e2);
+    float3 Q = cross3(T, e1);
+    float den = dot3(P, e1);
+    float inv = 1.0f / den;
+    float dist = dot3(Q, e2) * inv;
+    float u = dot3(P, T) * inv;
+    float v = dot3(Q, d) * inv;
+    if (dist < 0.f || u < 0.f || v < 0.f || u + v > 1.f) return false;
+    t = dist;
+    return true;
+}
+
+struct TravCounters {
+    uint32_t nodes, prims;
+};
+
+// Ordered traversal.  `stack` points at this thread's column of a [entries][blockDim.x]
+// shared-memory array (stride = blockDim.x -> conflict-free).  smem_nodes: first nodes of the
+// array (the top of the tree, breadth-first) staged in shared memory.
+template <bool COUNT>
+__device__ __forceinline__ void closest_hit(const DScene& sc, const DNodeHalf* __restrict__ smem_nodes, float3 o, float3 d,
+                                            uint32_t origin_prim, uint32_t* stack, int stride, float& tbest,
+                                            uint32_t& best, TravCounters& cnt) {
+    const float tmin = sc.tmin;
+    tbest = sc.tmax;
+    best = RRS_NO_PRIM;
+    float3 idir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    int sp = 0;
+    uint32_t cur = 0;  // virtual root
+    const uint32_t DONE = 0x7FFFFFFFu;
+    while (cur != DONE) {
+        // ---- inner nodes ----
+        while (!(cur & RRS_REF_LEAF) && cur != DONE) {
+            float h0[8], h1[8];
+            if (cur < sc.smem_nodes) {
+                const float4* s = reinterpret_cast<const float4*>(smem_nodes + 2 * cur);
+                float4 q0 = s[0], q1 = s[1], q2 = s[2], q3 = s[3];
+                h0[0] = q0.x; h0[1] = q0.y; h0[2] = q0.z; h0[3] = q0.w; h0[4] = q1.x; h0[5] = q1.y; h0[6] = q1.z; h0[7] = q1.w;
+                h1[0] = q2.x; h1[1] = q2.y; h1[2] = q2.z; h1[3] = q2.w; h1[4] = q3.x; h1[5] = q3.y; h1[6] = q3.z; h1[7] = q3.w;
+            } else {
+                ldg256(sc.nodes + 2 * cur, h0);
+                ldg256(sc.nodes + 2 * cur + 1, h1);
+            }
+            if (COUNT) cnt.nodes++;
+            uint32_t ref0 = __float_as_uint(h1[4]), ref1 = __float_as_uint(h1[5]);
+            // child 0: lo = h0[0..2], hi = h0[3..5]; child 1: lo = h0[6],h0[7],h1[0], hi = h1[1..3]
+            float ax0 = (h0[0] - o.x) * idir.x, ax1 = (h0[3] - o.x) * idir.x;
+            float ay0 = (h0[1] - o.y) * idir.y, ay1 = (h0[4] - o.y) * idir.y;
+            float az0 = (h0[2] - o.z) * idir.z, az1 = (h0[5] - o.z) * idir.z;
+            float n0 = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), tmin));
+            float f0 = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), tbest));
+            float bx0 = (h0[6] - o.x) * idir.x, bx1 = (h1[1] - o.x) * idir.x;
+            float by0 = (h0[7] - o.y) * idir.y, by1 = (h1[2] - o.y) * idir.y;
+            float bz0 = (h1[0] - o.z) * idir.z, bz1 = (h1[3] - o.z) * idir.z;
+            float n1 = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), tmin));
+            float f1 = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), tbest));
+            // conservative acceptance: fp32 slab arithmetic is good to a few ulp, boxes are
+            // rounded outward, so anything the f64 test accepts is accepted here
+            bool go0 = (ref0 != RRS_REF_EMPTY) && (n0 <= f0 * 1.000001f);
+            bool go1 = (ref1 != RRS_REF_EMPTY) && (n1 <= f1 * 1.000001f);
+            if (go0 && go1) {
+                bool swap = n1 < n0;
+                uint32_t nearr = swap ? ref1 : ref0, farr = swap ? ref0 : ref1;
+                stack[sp * stride] = farr;
+                ++sp;
+                cur = nearr;
+            } else if (go0) {
+                cur = ref0;
+            } else if (go1) {
+                cur = ref1;
+            } else if (sp > 0) {
+                --sp;
+                cur = stack[sp * stride];
+            } else {
+                cur = DONE;
+            }
+        }
+        // ---- leaf run (1..4 primitives, DFS order) ----
+        if (cur != DONE) {
+            uint32_t first = cur & 0x0FFFFFFFu;
+            uint32_t count = ((cur >> 28) & 7u) + 1u;
+            for (uint32_t k = 0; k < count; ++k) {
+                uint32_t pi = first + k;
+                const float4* pp = reinterpret_cast<const float4*>(sc.prims + pi);
+                float4 a = __ldg(pp), b = __ldg(pp + 1);
+                uint32_t type = prim_type(a);
+                float t;
+                bool hit;
+                if (COUNT) cnt.prims++;
+                if (type == RRS_TRIANGLE) {
+                    if (pi == origin_prim) continue;  // planar primitive cannot re-hit itself
+                    float4 c = __ldg(pp + 2);
+                    hit = hit_triangle(a, b, c, o, d, t);
+                } else if (type == RRS_SPHERE) {
+                    hit = hit_sphere(a, b, o, d, pi == origin_prim, t);
+                } else {
+                    if (pi == origin_prim) continue;
+                    hit = hit_plane(a, b, o, d, t);
+                }
+                // leaf filter + RayIntersection::update: strictly smaller t wins; equal t keeps
+                // the lower DFS index (ordered traversal may meet them in either order)
+                if (hit && t > tmin && (t < tbest || (t == tbest && best != RRS_NO_PRIM && pi < best))) {
+                    tbest = t;
+                    best = pi;
+                }
+            }
+            if (sp > 0) {
+                --sp;
+                cur = stack[sp * stride];
+            } else {
+                cur = DONE;
+            }
+        }
+    }
+}
+
+}  // namespace rrs

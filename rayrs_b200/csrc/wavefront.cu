@@ -1,0 +1,590 @@
+// Wavefront path tracer for sm_100a: persistent generate / extend / shade kernels over ray and
+// hit queues in HBM.  Replaces the pixel x spp x bounce loops of rayrs/src/main.rs:61-94 and
+// rayrs-lib/src/lib.rs:521-560.
+//
+// One iteration = plan -> generate -> extend -> shade:
+//   plan     (1 thread)  sizes the iteration on the device: how many survivors, how many new
+//                        paths fit into the queue (path regeneration keeps the queue full);
+//   generate             Camera::generate_primary_ray (lib.rs:202-210) for new paths, appended
+//                        behind the survivors with a warp-aggregated atomic;
+//   extend               closest hit per ray (intersect.cuh), persistent warps fetch 32-ray
+//                        batches from a global cursor;
+//   shade                Material::evaluate + Russian roulette + background; survivors are
+//                        compacted into the other queue (__ballot_sync/__popc + one atomicAdd
+//                        per warp); terminated paths add their radiance to the fp32 accumulator
+//                        with one 128-bit reduction.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+
+#include "intersect.cuh"
+#include "shading.cuh"
+#include "wavefront.cuh"
+
+namespace rrs {
+
+static constexpr int kBlock = 128;  // threads per block of the persistent kernels
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// ---------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------
+__global__ void k_plan(DCounters* c, uint32_t capacity) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // n_cur still holds what the previous iteration extended
+    c->rays += c->n_cur;
+    uint32_t live = c->n_next;
+    unsigned long long left = c->total_paths - c->next_path;
+    uint32_t room = capacity - live;
+    uint32_t gen = (uint32_t)(left < (unsigned long long)room ? left : (unsigned long long)room);
+    c->gen_first = c->next_path;
+    c->gen_count = gen;
+    c->next_path += gen;
+    c->n_cur = live;  // generate appends behind the survivors
+    c->n_next = 0;
+    c->work_extend = 0;
+    c->work_shade = 0;
+    c->done = (live == 0 && gen == 0) ? 1u : 0u;
+    if (!c->done) c->iterations++;
+}
+
+// ---------------------------------------------------------------------------------------
+// generate
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_generate(RenderConst rc, DCounters* __restrict__ c, float4* __restrict__ ray_o,
+                                                      float4* __restrict__ ray_d, float4* __restrict__ state) {
+    const uint32_t gen = c->gen_count;
+    const unsigned long long first = c->gen_first;
+    const uint32_t lane = lane_id();
+    // padded to whole warps so that every lane takes part in the ballot
+    const uint32_t gen_pad = (gen + 31u) & ~31u;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < gen_pad; k += gridDim.x * blockDim.x) {
+        bool valid = k < gen;
+        uint32_t row = 0, col = 0, s_local = 0;
+        if (valid) {
+            unsigned long long p = first + k;
+            s_local = (uint32_t)(p / rc.npix_pad);
+            uint32_t q = (uint32_t)(p - (unsigned long long)s_local * rc.npix_pad);
+            uint32_t tile = q >> 5, l = q & 31u;
+            uint32_t ty = tile / rc.tiles_x, tx = tile - ty * rc.tiles_x;
+            col = tx * 8u + (l & 7u);
+            row = ty * 4u + (l >> 3);
+            valid = col < rc.cam.W && row < rc.cam.H;
+        }
+        uint32_t ballot = __ballot_sync(0xFFFFFFFFu, valid);
+        if (ballot == 0) continue;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&c->n_cur, __popc(ballot));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (!valid) continue;
+        uint32_t slot = base + __popc(ballot & ((1u << lane) - 1u));
+        uint32_t pixel = row * rc.cam.W + col;
+        uint32_t sample = rc.sample_offset + s_local;
+        float4 u = rng_uniforms(rc.seed, pixel, sample, 0u);
+        // rayrs/src/main.rs:71-76: camera indices are (H - row, W - col)   
+        float fi = (float)(rc.cam.H - row), fj = (float)(rc.cam.W - col);
+        float x = (fj + u.x) * rc.cam.inv_ppc - rc.cam.half_w;
+        float y = (fi + u.y) * rc.cam.inv_ppc - rc.cam.half_h;
+        float3 d = add3(add3(rc.cam.z, scale3(rc.cam.e_x, x)), scale3(rc.cam.e_y, y));
+        ray_o[slot] = make_float4(rc.cam.origin.x, rc.cam.origin.y, rc.cam.origin.z, __uint_as_float(RRS_NO_PRIM));
+        ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
+        state[slot] = make_float4(1.f, 1.f, 1.f, __uint_as_float(sample << 8));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// extend
+// ---------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DCounters* __restrict__ c, const float4* __restrict__ ray_o,
+                                                    const float4* __restrict__ ray_d, float2* __restrict__ hits) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    // [smem_nodes * 64 B top-of-tree nodes][stack_entries * blockDim.x * 4 B traversal stacks]
+    DNodeHalf* s_nodes = reinterpret_cast<DNodeHalf*>(smem_raw);
+    uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem_raw + (size_t)sc.smem_nodes * 64u);
+    if (sc.smem_nodes) {
+        const float4* src = reinterpret_cast<const float4*>(sc.nodes);
+        float4* dst = reinterpret_cast<float4*>(s_nodes);
+        for (uint32_t i = threadIdx.x; i < sc.smem_nodes * 4u; i += blockDim.x) dst[i] = __ldg(src + i);
+        __syncthreads();
+    }
+    const uint32_t n = c->n_cur;
+    const uint32_t lane = lane_id();
+    TravCounters cnt{0, 0};
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&c->work_extend, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        uint32_t i = base + lane;
+        if (i < n) {
+            float4 o4 = __ldg(ray_o + i), d4 = __ldg(ray_d + i);
+            float t;
+            uint32_t prim;
+            closest_hit<COUNT>(sc, s_nodes, xyz(o4), xyz(d4), __float_as_uint(o4.w), s_stack + threadIdx.x, blockDim.x, t,
+                               prim, cnt);
+            hits[i] = make_float2(t, __uint_as_float(prim));
+        }
+        __syncwarp();
+    }
+    if (COUNT) {
+        uint32_t a = cnt.nodes, b = cnt.prims;
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+            b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&c->nodes_visited, (unsigned long long)a);
+            atomicAdd(&c->prims_tested, (unsigned long long)b);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// shade
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_shade(DScene sc, RenderConst rc, DCounters* __restrict__ c,
+                                                   const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+                                                   const float4* __restrict__ state, const float2* __restrict__ hits,
+                                                   float4* __restrict__ out_o, float4* __restrict__ out_d,
+                                                   float4* __restrict__ out_state, float4* __restrict__ accum) {
+    const uint32_t n = c->n_cur;
+    const uint32_t lane = lane_id();
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&c->work_shade, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        uint32_t i = base + lane;
+        bool alive = false;
+        float4 no, nd, ns;
+        if (i < n) {
+            float2 h = hits[i];
+            float4 o4 = ray_o[i], d4 = ray_d[i], st = state[i];
+            uint32_t prim = __float_as_uint(h.y);
+            uint32_t pixel = __float_as_uint(d4.w);
+            uint32_t sb = __float_as_uint(st.w);
+            uint32_t bounce = sb & 0xFFu, sample = sb >> 8;
+            float3 thr = xyz(st);
+            float3 o = xyz(o4), d = xyz(d4);
+            if (prim == RRS_NO_PRIM) {
+                // lib.rs:552-556: light + throughput * background(direction)
+                float3 bg = background(sc, d);
+                atomicAdd(accum + pixel, make_float4(thr.x * bg.x, thr.y * bg.y, thr.z * bg.z, 1.f));
+            } else {
+                const float4* pp = reinterpret_cast<const float4*>(sc.prims + prim);
+                float4 a = __ldg(pp);
+                float3 pos = madd3(d, h.x, o);  // Ray::point lib.rs:41-43
+                float3 nrm = prim_normal(sc.prims, prim, a, pos);
+                float3 view = normalize3(neg3(d));
+                float4 u = rng_uniforms(rc.seed, pixel, sample, bounce + 1u);
+                const float4* mp = reinterpret_cast<const float4*>(sc.mats + prim_material(a));
+                DMat m;
+                m.m0 = __ldg(mp);
+                m.m1 = __ldg(mp + 1);
+                m.m2 = __ldg(mp + 2);
+                ScatterOut so = material_evaluate(m, nrm, view, u.x, u.y, u.z);
+                bool finished = true;
+                if (so.scatter) {
+                    // lib.rs:533-547
+                    int emi = __float_as_int(__ldg(pp + 2).w);
+                    if (emi >= 0) {
+                        float4 e = __ldg(sc.emis + emi);
+                        atomicAdd(accum + pixel, make_float4(thr.x * e.x, thr.y * e.y, thr.z * e.z, 0.f));
+                    }
+                    thr = mul3(thr, so.color);
+                    float p = fmaxf(fmaxf(thr.x, thr.y), thr.z);
+                    if (!(u.w > p) && bounce + 1u < rc.max_bounces) {
+                        thr = f3(thr.x / p, thr.y / p, thr.z / p);
+                        finished = false;
+                        alive = true;
+                        no = make_float4(pos.x, pos.y, pos.z, __uint_as_float(prim));
+                        nd = make_float4(so.dir.x, so.dir.y, so.dir.z, d4.w);
+                        ns = make_float4(thr.x, thr.y, thr.z, __uint_as_float((sample << 8) | (bounce + 1u)));
+                    }
+                }
+                if (finished) atomicAdd(accum + pixel, make_float4(0.f, 0.f, 0.f, 1.f));
+            }
+        }
+        // queue compaction: survivors of this warp take consecutive slots
+        uint32_t ballot = __ballot_sync(0xFFFFFFFFu, alive);
+        if (ballot) {
+            uint32_t obase = 0;
+            if (lane == 0) obase = atomicAdd(&c->n_next, __popc(ballot));
+            obase = __shfl_sync(0xFFFFFFFFu, obase, 0);
+            if (alive) {
+                uint32_t slot = obase + __popc(ballot & ((1u << lane) - 1u));
+                out_o[slot] = no;
+                out_d[slot] = nd;
+                out_state[slot] = ns;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// resolve: sum -> mean, NaN / negative census (rayrs/src/main.rs:81-89)
+// ---------------------------------------------------------------------------------------
+__global__ void k_resolve(const float4* __restrict__ accum, float* __restrict__ out, uint32_t npix, float inv_spp,
+                          unsigned long long* __restrict__ census) {
+    uint32_t nan_cnt = 0, neg_cnt = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        float4 a = accum[i];
+        if (isnan(a.x) || isnan(a.y) || isnan(a.z)) nan_cnt++;
+        if (a.x < 0.f || a.y < 0.f || a.z < 0.f) neg_cnt++;
+        out[3 * (size_t)i + 0] = a.x * inv_spp;
+        out[3 * (size_t)i + 1] = a.y * inv_spp;
+        out[3 * (size_t)i + 2] = a.z * inv_spp;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        nan_cnt += __shfl_xor_sync(0xFFFFFFFFu, nan_cnt, o);
+        neg_cnt += __shfl_xor_sync(0xFFFFFFFFu, neg_cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0 && (nan_cnt | neg_cnt)) {
+        atomicAdd(census + 0, (unsigned long long)nan_cnt);
+        atomicAdd(census + 1, (unsigned long long)neg_cnt);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// probes (parity entry points)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_intersect32(DScene sc, const float4* __restrict__ ray_o,
+                                                         const float4* __restrict__ ray_d, uint32_t n,
+                                                         int32_t* __restrict__ obj_id, float* __restrict__ t_out) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    DNodeHalf* s_nodes = reinterpret_cast<DNodeHalf*>(smem_raw);
+    uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem_raw + (size_t)sc.smem_nodes * 64u);
+    if (sc.smem_nodes) {
+        const float4* src = reinterpret_cast<const float4*>(sc.nodes);
+        float4* dst = reinterpret_cast<float4*>(s_nodes);
+        for (uint32_t i = threadIdx.x; i < sc.smem_nodes * 4u; i += blockDim.x) dst[i] = __ldg(src + i);
+        __syncthreads();
+    }
+    TravCounters cnt{0, 0};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 o4 = ray_o[i], d4 = ray_d[i];
+        float t;
+        uint32_t prim;
+        closest_hit<false>(sc, s_nodes, xyz(o4), xyz(d4), RRS_NO_PRIM, s_stack + threadIdx.x, blockDim.x, t, prim, cnt);
+        if (prim == RRS_NO_PRIM) {
+            obj_id[i] = -1;
+            t_out[i] = INFINITY;
+        } else {
+            obj_id[i] = (int32_t)__float_as_uint(__ldg(reinterpret_cast<const float4*>(sc.prims + prim) + 1).w);
+            t_out[i] = t;
+        }
+    }
+}
+
+__global__ void k_material_probe(DMat m, const float* __restrict__ nv, const float* __restrict__ u, uint32_t n,
+                                 float* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float3 nrm = f3(nv[6 * i], nv[6 * i + 1], nv[6 * i + 2]);
+    float3 view = f3(nv[6 * i + 3], nv[6 * i + 4], nv[6 * i + 5]);
+    ScatterOut so = material_evaluate(m, nrm, view, u[3 * i], u[3 * i + 1], u[3 * i + 2]);
+    float* o = out + 7 * (size_t)i;
+    o[0] = so.scatter ? 1.f : 0.f;
+    o[1] = so.color.x; o[2] = so.color.y; o[3] = so.color.z;
+    o[4] = so.dir.x; o[5] = so.dir.y; o[6] = so.dir.z;
+}
+
+__global__ void k_background_probe(DScene sc, const float* __restrict__ dirs, uint32_t n, float* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float3 c = background(sc, f3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]));
+    out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
+}
+
+__global__ void k_rng_probe(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, float* out) {
+    float4 u = rng_uniforms(seed, pixel, sample, slot);
+    out[0] = u.x; out[1] = u.y; out[2] = u.z; out[3] = u.w;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static size_t extend_smem_bytes(const DScene& d) {
+    return (size_t)d.smem_nodes * 64u + (size_t)d.stack_entries * kBlock * sizeof(uint32_t);
+}
+
+static int ensure_wavefront(SceneImpl* s, uint32_t capacity, std::string& err) {
+    Wavefront& w = s->wf;
+    if (w.capacity == capacity && w.counters) return RRS_OK;
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(w.ray_o[k]); cudaFree(w.ray_d[k]); cudaFree(w.state[k]);
+        w.ray_o[k] = w.ray_d[k] = w.state[k] = nullptr;
+    }
+    cudaFree(w.hits);
+    w.hits = nullptr;
+    for (int k = 0; k < 2; ++k) {
+        RRS_CUDA_CHECK(cudaMalloc(&w.ray_o[k], sizeof(float4) * (size_t)capacity), err);
+        RRS_CUDA_CHECK(cudaMalloc(&w.ray_d[k], sizeof(float4) * (size_t)capacity), err);
+        RRS_CUDA_CHECK(cudaMalloc(&w.state[k], sizeof(float4) * (size_t)capacity), err);
+    }
+    RRS_CUDA_CHECK(cudaMalloc(&w.hits, sizeof(float2) * (size_t)capacity), err);
+    if (!w.counters) RRS_CUDA_CHECK(cudaMalloc(&w.counters, sizeof(DCounters)), err);
+    if (!w.h_counters) RRS_CUDA_CHECK(cudaMallocHost(&w.h_counters, sizeof(DCounters)), err);
+    w.capacity = capacity;
+    return RRS_OK;
+}
+
+void wf_free(SceneImpl* s) {
+    Wavefront& w = s->wf;
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(w.ray_o[k]); cudaFree(w.ray_d[k]); cudaFree(w.state[k]);
+    }
+    cudaFree(w.hits);
+    cudaFree(w.counters);
+    if (w.h_counters) cudaFreeHost(w.h_counters);
+    for (auto e : s->ev_pool) cudaEventDestroy(e);
+    s->ev_pool.clear();
+    w = Wavefront{};
+}
+
+static DCamera make_camera(const RrsCamera* c, uint32_t W, uint32_t H) {
+    DCamera d;
+    d.origin = make_float3((float)c->origin[0], (float)c->origin[1], (float)c->origin[2]);
+    d.e_x = make_float3((float)c->e_x[0], (float)c->e_x[1], (float)c->e_x[2]);
+    d.e_y = make_float3((float)c->e_y[0], (float)c->e_y[1], (float)c->e_y[2]);
+    d.z = make_float3((float)c->z_scaled[0], (float)c->z_scaled[1], (float)c->z_scaled[2]);
+    d.inv_ppc = (float)(1.0 / (double)c->ppc);
+    d.half_w = (float)(c->width / 2.);
+    d.half_h = (float)(c->height / 2.);
+    d.W = W;
+    d.H = H;
+    return d;
+}
+
+int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderParams* p, float4* d_accum,
+                         cudaStream_t stream, std::string& err) {
+    if (!cam || !p || !d_accum) { err = "null argument"; return RRS_ERR_INVALID; }
+    if (p->width == 0 || p->height == 0) { err = "empty image"; return RRS_ERR_INVALID; }
+    if (p->width != cam->x_pixels || p->height != cam->y_pixels) {
+        err = "render size does not match Camera::x_pixels/y_pixels";
+        return RRS_ERR_INVALID;
+    }
+    if (p->max_bounces > 255) { err = "max_bounces > 255 not supported"; return RRS_ERR_INVALID; }
+    if ((unsigned long long)p->sample_offset + p->spp > (1ull << 24)) { err = "sample index exceeds 2^24"; return RRS_ERR_INVALID; }
+    if ((unsigned long long)p->width * p->height > 0xFFFFFFFFull) { err = "image too large"; return RRS_ERR_INVALID; }
+    RRS_CUDA_CHECK(cudaSetDevice(s->device), err);
+    uint32_t capacity = p->queue_capacity ? p->queue_capacity : (1u << 22);
+    capacity = std::max(capacity, 1024u) & ~31u;
+    int rc_ = ensure_wavefront(s, capacity, err);
+    if (rc_ != RRS_OK) return rc_;
+    Wavefront& w = s->wf;
+
+    RenderConst rc;
+    rc.cam = make_camera(cam, p->width, p->height);
+    rc.tiles_x = (p->width + 7u) / 8u;
+    rc.tiles_y = (p->height + 3u) / 4u;
+    rc.npix_pad = (unsigned long long)rc.tiles_x * rc.tiles_y * 32ull;
+    rc.spp = p->spp;
+    rc.sample_offset = p->sample_offset;
+    rc.max_bounces = p->max_bounces;
+    rc.seed = p->seed;
+
+    DCounters init{};
+    init.total_paths = rc.npix_pad * (unsigned long long)p->spp;
+    if (p->max_bounces == 0) init.total_paths = 0;  // radiance() with 0 bounces returns black
+    *w.h_counters = init;
+    RRS_CUDA_CHECK(cudaMemcpyAsync(w.counters, w.h_counters, sizeof(DCounters), cudaMemcpyHostToDevice, stream), err);
+
+    const bool count = (p->flags & RRS_FLAG_COUNT_TRAVERSAL) != 0;
+    const bool phases = (p->flags & RRS_FLAG_TIME_PHASES) != 0;
+    size_t smem = extend_smem_bytes(s->d);
+    auto extend_fn = count ? k_extend<true> : k_extend<false>;
+    RRS_CUDA_CHECK(cudaFuncSetAttribute(extend_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err);
+    int occ_ext = 0, occ_shade = 0, occ_gen = 0;
+    RRS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ext, extend_fn, kBlock, smem), err);
+    RRS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_shade, k_shade, kBlock, 0), err);
+    RRS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gen, k_generate, kBlock, 0), err);
+    if (occ_ext < 1) { err = "extend kernel does not fit on an SM (traversal stack too deep)"; return RRS_ERR_TOO_DEEP; }
+    const int grid_ext = s->num_sms * occ_ext, grid_shade = s->num_sms * std::max(1, occ_shade),
+              grid_gen = s->num_sms * std::max(1, occ_gen);
+
+    // event pool: [0]=start [1]=stop, then 5 per iteration when phase timing is on
+    auto get_event = [&](size_t idx) -> cudaEvent_t {
+        while (s->ev_pool.size() <= idx) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            s->ev_pool.push_back(e);
+        }
+        return s->ev_pool[idx];
+    };
+    cudaEvent_t ev_start = get_event(0), ev_stop = get_event(1);
+    RRS_CUDA_CHECK(cudaEventRecord(ev_start, stream), err);
+
+    uint64_t launches = 0, iters = 0;
+    int cur = 0;
+    const uint32_t chunk = 8;
+    size_t ev_next = 2;
+    std::vector<size_t> phase_ev;  // indices of per-iteration event groups
+    bool done = false;
+    while (!done) {
+        for (uint32_t k = 0; k < chunk; ++k) {
+            int nxt = cur ^ 1;
+            size_t e0 = 0;
+            if (phases) {
+                e0 = ev_next;
+                ev_next += 5;
+                get_event(e0 + 4);
+                phase_ev.push_back(e0);
+                cudaEventRecord(s->ev_pool[e0], stream);
+            }
+            k_plan<<<1, 32, 0, stream>>>(w.counters, capacity);
+            if (phases) cudaEventRecord(s->ev_pool[e0 + 1], stream);
+            k_generate<<<grid_gen, kBlock, 0, stream>>>(rc, w.counters, w.ray_o[cur], w.ray_d[cur], w.state[cur]);
+            if (phases) cudaEventRecord(s->ev_pool[e0 + 2], stream);
+            extend_fn<<<grid_ext, kBlock, smem, stream>>>(s->d, w.counters, w.ray_o[cur], w.ray_d[cur], w.hits);
+            if (phases) cudaEventRecord(s->ev_pool[e0 + 3], stream);
+            k_shade<<<grid_shade, kBlock, 0, stream>>>(s->d, rc, w.counters, w.ray_o[cur], w.ray_d[cur], w.state[cur], w.hits,
+                                                        w.ray_o[nxt], w.ray_d[nxt], w.state[nxt], d_accum);
+            if (phases) cudaEventRecord(s->ev_pool[e0 + 4], stream);
+            launches += 4;
+            cur = nxt;
+        }
+        RRS_CUDA_CHECK(cudaMemcpyAsync(w.h_counters, w.counters, sizeof(DCounters), cudaMemcpyDeviceToHost, stream), err);
+        RRS_CUDA_CHECK(cudaStreamSynchronize(stream), err);
+        RRS_CUDA_CHECK(cudaGetLastError(), err);
+        done = w.h_counters->done != 0;
+    }
+    RRS_CUDA_CHECK(cudaEventRecord(ev_stop, stream), err);
+    RRS_CUDA_CHECK(cudaEventSynchronize(ev_stop), err);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev_start, ev_stop);
+    iters = w.h_counters->iterations;
+    RrsStats& st = s->stats;
+    st.rays = w.h_counters->rays;
+    st.paths = (uint64_t)p->width * p->height * p->spp;
+    st.kernel_launches = launches;
+    st.iterations = iters;
+    st.device_ms = ms;
+    st.nodes_visited = w.h_counters->nodes_visited;
+    st.prims_tested = w.h_counters->prims_tested;
+    st.generate_ms = st.extend_ms = st.shade_ms = 0.;
+    if (phases) {
+        double g = 0, e = 0, sh = 0;
+        for (size_t e0 : phase_ev) {
+            float a = 0, b = 0, c2 = 0;
+            cudaEventElapsedTime(&a, s->ev_pool[e0 + 1], s->ev_pool[e0 + 2]);
+            cudaEventElapsedTime(&b, s->ev_pool[e0 + 2], s->ev_pool[e0 + 3]);
+            cudaEventElapsedTime(&c2, s->ev_pool[e0 + 3], s->ev_pool[e0 + 4]);
+            g += a; e += b; sh += c2;
+        }
+        st.generate_ms = g;
+        st.extend_ms = e;
+        st.shade_ms = sh;
+    }
+    return RRS_OK;
+}
+
+int wf_resolve(SceneImpl* s, const float4* d_accum, uint32_t w, uint32_t h, uint32_t spp_total, float* out,
+               bool out_is_device, cudaStream_t stream, std::string& err) {
+    if (!d_accum || !out || spp_total == 0) { err = "bad resolve argument"; return RRS_ERR_INVALID; }
+    RRS_CUDA_CHECK(cudaSetDevice(s->device), err);
+    uint32_t npix = w * h;
+    if (!s->census) RRS_CUDA_CHECK(cudaMalloc(&s->census, 2 * sizeof(unsigned long long)), err);
+    RRS_CUDA_CHECK(cudaMemsetAsync(s->census, 0, 2 * sizeof(unsigned long long), stream), err);
+    float* d_out = out;
+    if (!out_is_device) RRS_CUDA_CHECK(cudaMalloc(&d_out, sizeof(float) * 3 * (size_t)npix), err);
+    int grid = std::min<uint32_t>((npix + 255) / 256, (uint32_t)s->num_sms * 8u);
+    k_resolve<<<grid, 256, 0, stream>>>(d_accum, d_out, npix, 1.0f / (float)spp_total, s->census);
+    unsigned long long cs[2] = {0, 0};
+    if (!out_is_device) {
+        RRS_CUDA_CHECK(cudaMemcpyAsync(out, d_out, sizeof(float) * 3 * (size_t)npix, cudaMemcpyDeviceToHost, stream), err);
+    }
+    RRS_CUDA_CHECK(cudaMemcpyAsync(cs, s->census, sizeof(cs), cudaMemcpyDeviceToHost, stream), err);
+    RRS_CUDA_CHECK(cudaStreamSynchronize(stream), err);
+    if (!out_is_device) cudaFree(d_out);
+    s->stats.nan_pixels = cs[0];
+    s->stats.negative_pixels = cs[1];
+    s->stats.kernel_launches += 1;
+    return RRS_OK;
+}
+
+int wf_intersect32(SceneImpl* s, const RrsRay* rays, size_t n, int32_t* obj_id, double* t, std::string& err) {
+    RRS_CUDA_CHECK(cudaSetDevice(s->device), err);
+    if (n == 0) return RRS_OK;
+    if (n > 0x7FFFFFFFull) { err = "too many rays"; return RRS_ERR_INVALID; }
+    std::vector<float4> ho(n), hd(n);
+    for (size_t i = 0; i < n; ++i) {
+        ho[i] = make_float4((float)rays[i].origin[0], (float)rays[i].origin[1], (float)rays[i].origin[2], 0.f);
+        hd[i] = make_float4((float)rays[i].direction[0], (float)rays[i].direction[1], (float)rays[i].direction[2], 0.f);
+    }
+    float4 *d_o = nullptr, *d_d = nullptr;
+    int32_t* d_id = nullptr;
+    float* d_t = nullptr;
+    RRS_CUDA_CHECK(cudaMalloc(&d_o, sizeof(float4) * n), err);
+    RRS_CUDA_CHECK(cudaMalloc(&d_d, sizeof(float4) * n), err);
+    RRS_CUDA_CHECK(cudaMalloc(&d_id, sizeof(int32_t) * n), err);
+    RRS_CUDA_CHECK(cudaMalloc(&d_t, sizeof(float) * n), err);
+    RRS_CUDA_CHECK(cudaMemcpy(d_o, ho.data(), sizeof(float4) * n, cudaMemcpyHostToDevice), err);
+    RRS_CUDA_CHECK(cudaMemcpy(d_d, hd.data(), sizeof(float4) * n, cudaMemcpyHostToDevice), err);
+    size_t smem = extend_smem_bytes(s->d);
+    RRS_CUDA_CHECK(cudaFuncSetAttribute(k_intersect32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err);
+    int grid = (int)std::min<size_t>((n + kBlock - 1) / kBlock, (size_t)s->num_sms * 8);
+    k_intersect32<<<grid, kBlock, smem>>>(s->d, d_o, d_d, (uint32_t)n, d_id, d_t);
+    RRS_CUDA_CHECK(cudaGetLastError(), err);
+    std::vector<float> ht(n);
+    RRS_CUDA_CHECK(cudaMemcpy(obj_id, d_id, sizeof(int32_t) * n, cudaMemcpyDeviceToHost), err);
+    RRS_CUDA_CHECK(cudaMemcpy(ht.data(), d_t, sizeof(float) * n, cudaMemcpyDeviceToHost), err);
+    for (size_t i = 0; i < n; ++i) t[i] = (double)ht[i];
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_id); cudaFree(d_t);
+    return RRS_OK;
+}
+
+int wf_material_evaluate(SceneImpl* s, uint32_t material, const double* nv, const double* u, size_t n, float* out,
+                         std::string& err) {
+    RRS_CUDA_CHECK(cudaSetDevice(s->device), err);
+    if (material >= s->d.n_mats) { err = "material index out of range"; return RRS_ERR_INVALID; }
+    if (n == 0) return RRS_OK;
+    DMat m;
+    RRS_CUDA_CHECK(cudaMemcpy(&m, s->mats + material, sizeof(DMat), cudaMemcpyDeviceToHost), err);
+    std::vector<float> hnv(6 * n), hu(3 * n);
+    for (size_t i = 0; i < 6 * n; ++i) hnv[i] = (float)nv[i];
+    for (size_t i = 0; i < 3 * n; ++i) hu[i] = (float)u[i];
+    float *d_nv = nullptr, *d_u = nullptr, *d_out = nullptr;
+    RRS_CUDA_CHECK(cudaMalloc(&d_nv, sizeof(float) * 6 * n), err);
+    RRS_CUDA_CHECK(cudaMalloc(&d_u, sizeof(float) * 3 * n), err);
+    RRS_CUDA_CHECK(cudaMalloc(&d_out, sizeof(float) * 7 * n), err);
+    RRS_CUDA_CHECK(cudaMemcpy(d_nv, hnv.data(), sizeof(float) * 6 * n, cudaMemcpyHostToDevice), err);
+    RRS_CUDA_CHECK(cudaMemcpy(d_u, hu.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice), err);
+    k_material_probe<<<(unsigned)((n + 127) / 128), 128>>>(m, d_nv, d_u, (uint32_t)n, d_out);
+    RRS_CUDA_CHECK(cudaGetLastError(), err);
+    RRS_CUDA_CHECK(cudaMemcpy(out, d_out, sizeof(float) * 7 * n, cudaMemcpyDeviceToHost), err);
+    cudaFree(d_nv); cudaFree(d_u); cudaFree(d_out);
+    return RRS_OK;
+}
+
+int wf_background(SceneImpl* s, const double* dirs, size_t n, float* out, std::string& err) {
+    RRS_CUDA_CHECK(cudaSetDevice(s->device), err);
+    if (n == 0) return RRS_OK;
+    std::vector<float> hd(3 * n);
+    for (size_t i = 0; i < 3 * n; ++i) hd[i] = (float)dirs[i];
+    float *d_d = nullptr, *d_out = nullptr;
+    RRS_CUDA_CHECK(cudaMalloc(&d_d, sizeof(float) * 3 * n), err);
+    RRS_CUDA_CHECK(cudaMalloc(&d_out, sizeof(float) * 3 * n), err);
+    RRS_CUDA_CHECK(cudaMemcpy(d_d, hd.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice), err);
+    k_background_probe<<<(unsigned)((n + 127) / 128), 128>>>(s->d, d_d, (uint32_t)n, d_out);
+    RRS_CUDA_CHECK(cudaGetLastError(), err);
+    RRS_CUDA_CHECK(cudaMemcpy(out, d_out, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost), err);
+    cudaFree(d_d); cudaFree(d_out);
+    return RRS_OK;
+}
+
+int wf_rng_uniforms(SceneImpl* s, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, float* out4,
+                    std::string& err) {
+    RRS_CUDA_CHECK(cudaSetDevice(s->device), err);
+    float* d = nullptr;
+    RRS_CUDA_CHECK(cudaMalloc(&d, 4 * sizeof(float)), err);
+    k_rng_probe<<<1, 1>>>(seed, pixel, sample, slot, d);
+    RRS_CUDA_CHECK(cudaGetLastError(), err);
+    RRS_CUDA_CHECK(cudaMemcpy(out4, d, 4 * sizeof(float), cudaMemcpyDeviceToHost), err);
+    cudaFree(d);
+    return RRS_OK;
+}
+
+}  // namespace rrs

@@ -1,0 +1,96 @@
+// Wavefront path-tracing state shared between wavefront.cu (kernels + render loop) and
+// api.cu (scene handle).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "device_types.cuh"
+
+namespace rrs {
+
+// Device-resident loop state.  Everything the persistent kernels need to size their work is
+// read from here, so an iteration needs no host round trip.
+struct DCounters {
+    uint32_t n_cur;       // rays in the current queue (extend + shade work size)
+    uint32_t n_next;      // survivors appended to the other queue by shade
+    uint32_t gen_count;   // padded path indices to generate this iteration
+    uint32_t done;        // 1 when no live ray and no path left
+    unsigned long long gen_first;    // first padded path index of this iteration
+    unsigned long long next_path;    // next padded path index not yet generated
+    unsigned long long total_paths;  // padded total
+    unsigned long long rays;         // BVH queries so far
+    unsigned long long paths;        // primary rays generated so far
+    unsigned long long nodes_visited, prims_tested;
+    unsigned long long iterations;
+    uint32_t work_extend, work_shade;  // dynamic work cursors of the persistent kernels
+    uint32_t pad[2];
+};
+
+struct RenderConst {
+    DCamera cam;
+    uint32_t tiles_x, tiles_y;
+    unsigned long long npix_pad;  // tiles_x * tiles_y * 32
+    uint32_t spp, sample_offset, max_bounces;
+    uint64_t seed;
+};
+
+struct Wavefront {
+    uint32_t capacity = 0;
+    float4* ray_o[2] = {nullptr, nullptr};  // origin xyz, origin primitive
+    float4* ray_d[2] = {nullptr, nullptr};  // direction xyz, pixel
+    float4* state[2] = {nullptr, nullptr};  // throughput rgb, sample << 8 | bounce
+    float2* hits = nullptr;                 // t, primitive
+    DCounters* counters = nullptr;
+    DCounters* h_counters = nullptr;  // pinned
+};
+
+struct SceneImpl {
+    int device = 0;
+    int num_sms = 0;
+    DScene d{};
+    // owned device allocations
+    DPrim* prims = nullptr;
+    DNodeHalf* nodes = nullptr;
+    DMat* mats = nullptr;
+    float4* emis = nullptr;
+    float4* hdri = nullptr;
+    RrsPrim* prims_f64 = nullptr;
+    RrsNodeF64* nodes_f64 = nullptr;
+    uint32_t n_prims = 0, n_nodes = 0;
+    uint32_t max_depth = 0;
+    double tmin = 0, tmax = 0;
+    Wavefront wf;
+    RrsStats stats{};
+    float4* accum = nullptr;  // private accumulation buffer of rrs_render
+    size_t accum_pixels = 0;
+    unsigned long long* census = nullptr;  // [nan, negative]
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+// wavefront.cu
+int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderParams* p, float4* d_accum,
+                         cudaStream_t stream, std::string& err);
+int wf_resolve(SceneImpl* s, const float4* d_accum, uint32_t w, uint32_t h, uint32_t spp_total, float* out,
+               bool out_is_device, cudaStream_t stream, std::string& err);
+int wf_intersect32(SceneImpl* s, const RrsRay* rays, size_t n, int32_t* obj_id, double* t, std::string& err);
+int wf_material_evaluate(SceneImpl* s, uint32_t material, const double* nv, const double* u, size_t n, float* out,
+                         std::string& err);
+int wf_background(SceneImpl* s, const double* dirs, size_t n, float* out, std::string& err);
+int wf_rng_uniforms(SceneImpl* s, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, float* out4,
+                    std::string& err);
+void wf_free(SceneImpl* s);
+// verify_f64.cu
+int vf_intersect64(SceneImpl* s, const RrsRay* rays, size_t n, int32_t* obj_id, double* t, std::string& err);
+
+#define RRS_CUDA_CHECK(expr, errstr)                                                           \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            (errstr) = std::string(#expr) + ": " + cudaGetErrorString(_e);                     \
+            return RRS_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+}  // namespace rrs

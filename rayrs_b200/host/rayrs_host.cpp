@@ -1,0 +1,675 @@
+// Host mirror implementation: constructors with the reference's assert!s, the BVH builder
+// (same tree as rayrs-lib/src/bvh.rs:227-389) and its flattening into RrsNode[].
+#include "rayrs_host.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <future>
+#include <limits>
+#include <mutex>
+#include <thread>
+
+namespace rayrs {
+
+// ---------------------------------------------------------------------------------------
+// vecmath (rayrs-lib/src/vecmath.rs)
+// ---------------------------------------------------------------------------------------
+Vec3 operator+(Vec3 a, Vec3 b) { return Vec3(a.x + b.x, a.y + b.y, a.z + b.z); }
+Vec3 operator-(Vec3 a, Vec3 b) { return Vec3(a.x - b.x, a.y - b.y, a.z - b.z); }
+Vec3 operator*(Vec3 a, double s) { return Vec3(a.x * s, a.y * s, a.z * s); }
+Vec3 operator*(double s, Vec3 a) { return Vec3(s * a.x, s * a.y, s * a.z); }
+Vec3 operator/(Vec3 a, double s) {
+    double inv = 1. / s;
+    return a * inv;
+}
+double dot(Vec3 a, Vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+Vec3 cross(Vec3 a, Vec3 b) { return Vec3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+Vec3 unit(Vec3 a) { return a / std::sqrt(dot(a, a)); }
+
+// ---------------------------------------------------------------------------------------
+// AABB (geometry.rs:577-582,640-645,674-683)
+// ---------------------------------------------------------------------------------------
+Vec3 AxisAlignedBoundingBox::center() const {
+    return Vec3((xmax - xmin) / 2. + xmin, (ymax - ymin) / 2. + ymin, (zmax - zmin) / 2. + zmin);
+}
+double AxisAlignedBoundingBox::surface_area() const {
+    double x = xmax - xmin, y = ymax - ymin, z = zmax - zmin;
+    return 2. * x * y + 2. * y * z + 2. * x * z;
+}
+AxisAlignedBoundingBox AxisAlignedBoundingBox::expand(const AxisAlignedBoundingBox& o) const {
+    return AxisAlignedBoundingBox{std::fmin(xmin, o.xmin), std::fmax(xmax, o.xmax), std::fmin(ymin, o.ymin),
+                                  std::fmax(ymax, o.ymax), std::fmin(zmin, o.zmin), std::fmax(zmax, o.zmax)};
+}
+
+// ---------------------------------------------------------------------------------------
+// Materials (material.rs:595-901): same assertions, as exceptions
+// ---------------------------------------------------------------------------------------
+static void require(bool ok, const char* what) {
+    if (!ok) throw Panic(what);
+}
+static void set3(double* d, Vec3 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
+
+Material Material::LambertianDiffuse(Vec3 color) {
+    require(color.xyz_in_range_inclusive(0., 1.), "LambertianDiffuse::new: color not in [0,1]");
+    Material r;
+    r.m.tag = RRS_MAT_LAMBERTIAN;
+    set3(r.m.color, color);
+    return r;
+}
+Material Material::Reflect(Vec3 color) {
+    require(color.xyz_in_range_inclusive(0., 1.), "Reflect::new: color not in [0,1]");
+    Material r;
+    r.m.tag = RRS_MAT_REFLECT;
+    set3(r.m.color, color);
+    return r;
+}
+Material Material::Refract(Vec3 color, double ior) {
+    require(color.xyz_in_range_inclusive(0., 1.), "Refract::new: color not in [0,1]");
+    require(ior > 0. && std::isfinite(ior), "Refract::new: ior must be positive and finite");
+    Material r;
+    r.m.tag = RRS_MAT_REFRACT;
+    set3(r.m.color, color);
+    r.m.ior = ior;
+    return r;
+}
+Material Material::Glass(Vec3 color, double ior) {
+    require(color.xyz_in_range_inclusive(0., 1.), "Glass::new: color not in [0,1]");
+    require(ior > 0. && std::isfinite(ior), "Glass::new: ior must be positive and finite");
+    Material r;
+    r.m.tag = RRS_MAT_GLASS;
+    set3(r.m.color, color);
+    r.m.ior = ior;
+    return r;
+}
+Material Material::CookTorrance(Vec3 color, double alpha, Fresnel fresnel) {
+    require(color.xyz_in_range_inclusive(0., 1.), "CookTorrance::new: color not in [0,1]");
+    require(alpha > 0. && std::isfinite(alpha), "CookTorrance::new: alpha must be positive and finite");
+    Material r;
+    r.m.tag = RRS_MAT_COOK_TORRANCE;
+    set3(r.m.color, color);
+    r.m.alpha = alpha;
+    r.m.fresnel_kind = fresnel.kind;
+    if (fresnel.kind == RRS_FRESNEL_METALLIC) set3(r.m.spec_color, fresnel.r0);
+    else r.m.ior = fresnel.ior;
+    return r;
+}
+Material Material::CookTorranceRefract(Vec3 color, double alpha, double ior) {
+    require(color.xyz_in_range_inclusive(0., 1.), "CookTorranceRefract::new: color not in [0,1]");
+    require(alpha > 0. && std::isfinite(alpha), "CookTorranceRefract::new: alpha must be positive and finite");
+    require(ior > 0. && std::isfinite(ior), "CookTorranceRefract::new: ior must be positive and finite");
+    Material r;
+    r.m.tag = RRS_MAT_COOK_TORRANCE_REFRACT;
+    set3(r.m.color, color);
+    r.m.alpha = alpha;
+    r.m.ior = ior;
+    return r;
+}
+Material Material::CookTorranceGlass(Vec3 color, double alpha, double ior) {
+    require(color.xyz_in_range_inclusive(0., 1.), "CookTorranceGlass::new: color not in [0,1]");
+    require(alpha > 0. && std::isfinite(alpha), "CookTorranceGlass::new: alpha must be positive and finite");
+    require(ior > 0. && std::isfinite(ior), "CookTorranceGlass::new: ior must be positive and finite");
+    Material r;
+    r.m.tag = RRS_MAT_COOK_TORRANCE_GLASS;
+    set3(r.m.color, color);
+    r.m.alpha = alpha;
+    r.m.ior = ior;
+    return r;
+}
+Material Material::Plastic(Vec3 color, Vec3 spec_color, double alpha, double ior) {
+    require(color.xyz_in_range_inclusive(0., 1.), "Plastic::new: color not in [0,1]");
+    require(spec_color.xyz_in_range_inclusive(0., 1.), "Plastic::new: spec_color not in [0,1]");
+    require(alpha > 0. && std::isfinite(alpha), "Plastic::new: alpha must be positive and finite");
+    require(ior > 0. && std::isfinite(ior), "Plastic::new: ior must be positive and finite");
+    Material r;
+    r.m.tag = RRS_MAT_PLASTIC;
+    set3(r.m.color, color);
+    set3(r.m.spec_color, spec_color);
+    r.m.alpha = alpha;
+    r.m.ior = ior;
+    return r;
+}
+Material Material::NoReflect() {
+    Material r;
+    r.m.tag = RRS_MAT_NO_REFLECT;
+    return r;
+}
+
+Emission Emission::Emissive(double strength, Vec3 color) {
+    require(strength >= 0., "Emission::new: strength must be >= 0");
+    require(color.xyz_in_range_inclusive(0., 1.), "RGB values need to be between 0 and 1");
+    Emission e;
+    e.dark = false;
+    e.strength = strength;
+    e.color = color;
+    return e;
+}
+
+// ---------------------------------------------------------------------------------------
+// Geometry / Object (geometry.rs, lib.rs:321-507)
+// ---------------------------------------------------------------------------------------
+AxisAlignedBoundingBox Geometry::bbox() const {
+    if (type == RRS_SPHERE) {  // geometry.rs:687-696 (bbox uses sqrt(radius2))
+        double r = std::sqrt(v[0]);
+        return AxisAlignedBoundingBox{v[1] - r, v[1] + r, v[2] - r, v[2] + r, v[3] - r, v[3] + r};
+    }
+    if (type == RRS_PLANE) {  // geometry.rs:699-718
+        int axis = ((int)v[0]) >> 1;
+        if (axis == 0) return AxisAlignedBoundingBox{v[5], v[5], v[1], v[2], v[3], v[4]};
+        if (axis == 1) return AxisAlignedBoundingBox{v[1], v[2], v[5], v[5], v[3], v[4]};
+        return AxisAlignedBoundingBox{v[1], v[2], v[3], v[4], v[5], v[5]};
+    }
+    // geometry.rs:721-733
+    return AxisAlignedBoundingBox{std::fmin(v[0], std::fmin(v[3], v[6])), std::fmax(v[0], std::fmax(v[3], v[6])),
+                                  std::fmin(v[1], std::fmin(v[4], v[7])), std::fmax(v[1], std::fmax(v[4], v[7])),
+                                  std::fmin(v[2], std::fmin(v[5], v[8])), std::fmax(v[2], std::fmax(v[5], v[8]))};
+}
+
+Object Object::sphere(double radius, Vec3 origin, Material mat, Emission emission) {
+    require(radius > 0., "Radius has to be positive");  // geometry.rs:97
+    Object o;
+    o.geom.type = RRS_SPHERE;
+    std::memset(o.geom.v, 0, sizeof(o.geom.v));
+    o.geom.v[0] = radius * radius;  // Sphere stores radius2 (geometry.rs:98-101)
+    o.geom.v[1] = origin.x; o.geom.v[2] = origin.y; o.geom.v[3] = origin.z;
+    o.mat = mat;
+    o.emission = emission;
+    return o;
+}
+Object Object::plane(Axis axis, double umin, double umax, double vmin, double vmax, double pos, Material mat,
+                     Emission emission) {
+    require(umin < umax && vmin < vmax, "Plane cannot be constructed with these ranges");  // geometry.rs:205-212
+    Object o;
+    o.geom.type = RRS_PLANE;
+    std::memset(o.geom.v, 0, sizeof(o.geom.v));
+    o.geom.v[0] = (double)(int)axis;
+    o.geom.v[1] = umin; o.geom.v[2] = umax; o.geom.v[3] = vmin; o.geom.v[4] = vmax; o.geom.v[5] = pos;
+    o.mat = mat;
+    o.emission = emission;
+    return o;
+}
+Object Object::triangle(Vec3 p1, Vec3 p2, Vec3 p3, Material mat, Emission emission) {
+    Object o;
+    o.geom.type = RRS_TRIANGLE;
+    o.geom.v[0] = p1.x; o.geom.v[1] = p1.y; o.geom.v[2] = p1.z;
+    o.geom.v[3] = p2.x; o.geom.v[4] = p2.y; o.geom.v[5] = p2.z;
+    o.geom.v[6] = p3.x; o.geom.v[7] = p3.y; o.geom.v[8] = p3.z;
+    o.mat = mat;
+    o.emission = emission;
+    return o;
+}
+std::vector<Object> Object::box_geom(Vec3 ll, Vec3 ur, Material mat, Emission emission) {
+    // lib.rs:438-507, same six planes in the same order (note: the last one really is at
+    // lower_left.y like the one before it)
+    return {
+        Object::plane(Axis::X, ll.y, ur.y, ll.z, ur.z, ll.x, mat, emission),
+        Object::plane(Axis::XRev, ll.y, ur.y, ll.z, ur.z, ur.x, mat, emission),
+        Object::plane(Axis::ZRev, ll.x, ur.x, ll.y, ur.y, ll.z, mat, emission),
+        Object::plane(Axis::Z, ll.x, ur.x, ll.y, ur.y, ur.z, mat, emission),
+        Object::plane(Axis::YRev, ll.x, ur.x, ll.z, ur.z, ll.y, mat, emission),
+        Object::plane(Axis::Y, ll.x, ur.x, ll.z, ur.z, ll.y, mat, emission),
+    };
+}
+
+// ---------------------------------------------------------------------------------------
+// BVH build (bvh.rs:227-389) on index ranges
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct BNode {
+    AxisAlignedBoundingBox box;
+    int32_t child[2] = {-1, -1};  // build-node index, or -1
+    uint32_t first = 0, count = 0; // leaf group / bare leaf: range in `order`
+    uint8_t kind = 0;              // 0 binary Node, 1 group Node (<=4 LeafNodes), 2 bare LeafNode
+};
+
+struct Builder {
+    const std::vector<AxisAlignedBoundingBox>& boxes;
+    const std::vector<Vec3>& centers;
+    std::vector<uint32_t>& order;
+    BvhHeuristic heur;
+    std::vector<BNode> nodes;
+    std::mutex mu;
+    std::atomic<int> spare_threads{0};
+
+    Builder(const std::vector<AxisAlignedBoundingBox>& b, const std::vector<Vec3>& c, std::vector<uint32_t>& o,
+            BvhHeuristic h)
+        : boxes(b), centers(c), order(o), heur(h) {}
+
+    int32_t alloc(const BNode& n) {
+        std::lock_guard<std::mutex> g(mu);
+        nodes.push_back(n);
+        return (int32_t)nodes.size() - 1;
+    }
+    static double key(const Vec3& c, int axis) { return axis == 0 ? c.x : (axis == 1 ? c.y : c.z); }
+
+    AxisAlignedBoundingBox range_box(size_t lo, size_t hi) const {
+        AxisAlignedBoundingBox b = boxes[order[lo]];
+        for (size_t i = lo + 1; i < hi; ++i) b = b.expand(boxes[order[i]]);
+        return b;
+    }
+
+    int32_t build(size_t lo, size_t hi, int depth) {
+        const size_t n = hi - lo;
+        if (n == 0) throw Panic("Having a BVH for 0 objects does not make sense");  // bvh.rs:229
+        BNode node;
+        node.box = range_box(lo, hi);
+        if (n <= 4) {  // bvh.rs:304-315
+            node.kind = 1;
+            node.first = (uint32_t)lo;
+            node.count = (uint32_t)n;
+            return alloc(node);
+        }
+        const AxisAlignedBoundingBox& bb = node.box;
+        double x = bb.xmax - bb.xmin, y = bb.ymax - bb.ymin, z = bb.zmax - bb.zmin;
+        int axis;
+        double amin, alen;
+        if (x >= y && x >= z) { axis = 0; amin = bb.xmin; alen = x; }
+        else if (y >= z) { axis = 1; amin = bb.ymin; alen = y; }
+        else { axis = 2; amin = bb.zmin; alen = z; }
+        // BvhData::sort — Rust's sort_by is stable
+        std::stable_sort(order.begin() + lo, order.begin() + hi, [&](uint32_t a, uint32_t b) {
+            return key(centers[a], axis) < key(centers[b], axis);
+        });
+        std::vector<double> keys(n);
+        for (size_t k = 0; k < n; ++k) {
+            keys[k] = key(centers[order[lo + k]], axis);
+            if (std::isnan(keys[k])) throw Panic("partial_cmp().unwrap() on NaN centre");  // bvh.rs:104
+        }
+        long ind = -1;
+        if (heur.kind == BvhHeuristic::kSah) {
+            // bvh.rs:258-271 with calculate_sah bvh.rs:15-38.  left(k) = [0,k), right(k) = [k,n)
+            std::vector<AxisAlignedBoundingBox> suf(n);
+            suf[n - 1] = boxes[order[hi - 1]];
+            for (size_t k = n - 1; k-- > 0;) suf[k] = boxes[order[lo + k]].expand(suf[k + 1]);
+            std::vector<AxisAlignedBoundingBox> pre(n);  // pre[k] = box of [0,k], so left(k) = pre[k-1]
+            pre[0] = boxes[order[lo]];
+            for (size_t k = 1; k < n; ++k) pre[k] = pre[k - 1].expand(boxes[order[lo + k]]);
+            const double surface_area = bb.surface_area();
+            const double split_dist = alen / (double)(heur.splits - 1);
+            double min_sah = std::numeric_limits<double>::infinity();
+            long last = -2;
+            for (uint32_t i = 1; i < heur.splits + 1; ++i) {
+                double thr = amin + (double)i * split_dist;
+                size_t k = std::upper_bound(keys.begin(), keys.end(), thr) - keys.begin();  // first centre > thr
+                if (k >= n) continue;           // split_index -> None
+                if ((long)k == last) continue;  // same split => same cost; strict < keeps the first
+                last = (long)k;
+                double p_left = k > 0 ? pre[k - 1].surface_area() / surface_area : 0.;
+                double p_right = suf[k].surface_area() / surface_area;
+                double sah = 0.3 + 1. * (p_left * (double)k + p_right * (double)(n - k));
+                if (sah < min_sah) {
+                    min_sah = sah;
+                    ind = (long)k;
+                }
+            }
+        } else {
+            // bvh.rs:337-350
+            double split = axis == 0 ? bb.center().x : (axis == 1 ? bb.center().y : bb.center().z);
+            size_t k = std::upper_bound(keys.begin(), keys.end(), split) - keys.begin();
+            ind = k >= n ? -1 : (long)k;
+        }
+        if (ind < 0 || ind == 0 || ind == (long)n - 1) ind = (long)(n / 2);  // bvh.rs:279-287
+        keys.clear();
+        keys.shrink_to_fit();
+        node.kind = 0;
+        const size_t mid = lo + (size_t)ind;
+        auto side = [&](size_t a, size_t b) -> int32_t {
+            if (b - a > 1) return build(a, b, depth + 1);
+            BNode leaf;
+            leaf.kind = 2;
+            leaf.first = (uint32_t)a;
+            leaf.count = 1;
+            leaf.box = boxes[order[a]];
+            return alloc(leaf);
+        };
+        // independent subtrees: run the left one on another thread while there are spares
+        bool forked = false;
+        std::future<int32_t> fut;
+        if (n > 20000) {
+            int v = spare_threads.load();
+            while (v > 0 && !spare_threads.compare_exchange_weak(v, v - 1)) {
+            }
+            forked = v > 0;
+        }
+        if (forked) fut = std::async(std::launch::async, [&, lo, mid]() { return side(lo, mid); });
+        int32_t right = side(mid, hi);
+        int32_t left;
+        if (forked) {
+            left = fut.get();
+            spare_threads.fetch_add(1);
+        } else {
+            left = side(lo, mid);
+        }
+        node.child[0] = left;
+        node.child[1] = right;
+        return alloc(node);
+    }
+};
+
+float round_down(double x) {
+    float f = (float)x;
+    if ((double)f > x) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
+float round_up(double x) {
+    float f = (float)x;
+    if ((double)f < x) f = std::nextafterf(f, INFINITY);
+    return f;
+}
+
+struct Flattener {
+    const std::vector<BNode>& bn;
+    FlatBvh& out;
+
+    void set_child(uint32_t node, int ch, uint32_t ref, bool bare, const AxisAlignedBoundingBox* f64box,
+                   const AxisAlignedBoundingBox* f32box) {
+        RrsNode& n = out.nodes[node];
+        RrsNodeF64& d = out.nodes_f64[node];
+        float* lo = ch ? n.lo1 : n.lo0;
+        float* hi = ch ? n.hi1 : n.hi0;
+        double* dlo = ch ? d.lo1 : d.lo0;
+        double* dhi = ch ? d.hi1 : d.hi0;
+        (ch ? n.ref1 : n.ref0) = ref;
+        (ch ? d.ref1 : d.ref0) = ref;
+        if (bare) {
+            n.flags |= 1u << ch;
+            d.flags |= 1u << ch;
+        }
+        if (ref == RRS_REF_EMPTY || !f32box) {
+            for (int k = 0; k < 3; ++k) {
+                lo[k] = INFINITY; hi[k] = -INFINITY;
+                dlo[k] = INFINITY; dhi[k] = -INFINITY;
+            }
+            return;
+        }
+        lo[0] = round_down(f32box->xmin); lo[1] = round_down(f32box->ymin); lo[2] = round_down(f32box->zmin);
+        hi[0] = round_up(f32box->xmax); hi[1] = round_up(f32box->ymax); hi[2] = round_up(f32box->zmax);
+        dlo[0] = f64box->xmin; dlo[1] = f64box->ymin; dlo[2] = f64box->zmin;
+        dhi[0] = f64box->xmax; dhi[1] = f64box->ymax; dhi[2] = f64box->zmax;
+    }
+
+    // reference of a child as seen from its parent (whose own box is `parent_box`)
+    void attach(uint32_t node, int ch, int32_t b, const AxisAlignedBoundingBox& parent_box,
+                const std::vector<int32_t>& flat_index) {
+        const BNode& c = bn[b];
+        if (c.kind == 2) {
+            // bare LeafNode: no box in the reference; cull with the primitive's own box when
+            // that box is a real volume, else with the parent's
+            const AxisAlignedBoundingBox* fb = c.box.degenerate() ? &parent_box : &c.box;
+            set_child(node, ch, RRS_MAKE_LEAF(c.first, 1), true, &c.box, fb);
+            return;
+        }
+        if (c.box.degenerate()) {  // slab test can never accept a zero-extent box
+            out.dead_nodes++;
+            set_child(node, ch, RRS_REF_EMPTY, false, nullptr, nullptr);
+            return;
+        }
+        if (c.kind == 1) {
+            set_child(node, ch, RRS_MAKE_LEAF(c.first, c.count), false, &c.box, &c.box);
+            return;
+        }
+        set_child(node, ch, (uint32_t)flat_index[b], false, &c.box, &c.box);
+    }
+};
+
+void dump_topology(const std::vector<BNode>& bn, int32_t b, const std::vector<uint32_t>& order, FlatBvh& out) {
+    const BNode& n = bn[b];
+    if (n.kind == 2) {
+        out.topology.push_back(order[n.first]);
+        return;
+    }
+    const double box[6] = {n.box.xmin, n.box.xmax, n.box.ymin, n.box.ymax, n.box.zmin, n.box.zmax};
+    out.boxes.insert(out.boxes.end(), box, box + 6);
+    if (n.kind == 1) {
+        out.topology.push_back(-(int64_t)n.count);
+        for (uint32_t k = 0; k < n.count; ++k) out.topology.push_back(order[n.first + k]);
+        return;
+    }
+    out.topology.push_back(-2);
+    dump_topology(bn, n.child[0], order, out);
+    dump_topology(bn, n.child[1], order, out);
+}
+
+}  // namespace
+
+FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, uint32_t bfs_nodes, int threads) {
+    if (objects.empty()) throw Panic("Having a BVH for 0 objects does not make sense");
+    if (heuristic.kind == BvhHeuristic::kSah && heuristic.splits < 2) throw Panic("Sah needs at least 2 splits");
+    const size_t n = objects.size();
+    std::vector<AxisAlignedBoundingBox> boxes(n);
+    std::vector<Vec3> centers(n);
+    for (size_t i = 0; i < n; ++i) {
+        boxes[i] = objects[i].bbox();
+        centers[i] = boxes[i].center();  // BvhData::new bvh.rs:87-98
+    }
+    FlatBvh out;
+    out.prim_order.resize(n);
+    for (size_t i = 0; i < n; ++i) out.prim_order[i] = (uint32_t)i;
+    Builder b(boxes, centers, out.prim_order, heuristic);
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    b.spare_threads = threads - 1;
+    b.nodes.reserve(n);
+    const int32_t root = b.build(0, n, 0);
+    const std::vector<BNode>& bn = b.nodes;
+
+    // ---- flat numbering: virtual root = 0, then binary Nodes breadth-first for the first
+    // `bfs_nodes` (hot top of the tree contiguous), depth-first below (subtrees contiguous)
+    std::vector<int32_t> flat_index(bn.size(), -1);
+    std::vector<int32_t> flat_to_build;
+    flat_to_build.push_back(-1);  // virtual root
+    {
+        std::vector<int32_t> frontier;
+        if (bn[root].kind == 0 && !bn[root].box.degenerate()) frontier.push_back(root);
+        size_t head = 0;
+        while (head < frontier.size() && flat_to_build.size() < (size_t)bfs_nodes + 1) {
+            int32_t cur = frontier[head++];
+            flat_index[cur] = (int32_t)flat_to_build.size();
+            flat_to_build.push_back(cur);
+            for (int c = 0; c < 2; ++c) {
+                int32_t ch = bn[cur].child[c];
+                if (bn[ch].kind == 0 && !bn[ch].box.degenerate()) frontier.push_back(ch);
+            }
+        }
+        // the rest depth-first
+        std::vector<int32_t> stack(frontier.begin() + head, frontier.end());
+        std::reverse(stack.begin(), stack.end());
+        while (!stack.empty()) {
+            int32_t cur = stack.back();
+            stack.pop_back();
+            flat_index[cur] = (int32_t)flat_to_build.size();
+            flat_to_build.push_back(cur);
+            for (int c = 1; c >= 0; --c) {
+                int32_t ch = bn[cur].child[c];
+                if (bn[ch].kind == 0 && !bn[ch].box.degenerate()) stack.push_back(ch);
+            }
+        }
+    }
+    out.nodes.assign(flat_to_build.size(), RrsNode{});
+    out.nodes_f64.assign(flat_to_build.size(), RrsNodeF64{});
+    Flattener fl{bn, out};
+    // virtual root
+    {
+        AxisAlignedBoundingBox rb = bn[root].box;
+        if (rb.degenerate()) {
+            out.dead_nodes++;
+            fl.set_child(0, 0, RRS_REF_EMPTY, false, nullptr, nullptr);
+        } else if (bn[root].kind == 1) {
+            fl.set_child(0, 0, RRS_MAKE_LEAF(bn[root].first, bn[root].count), false, &rb, &rb);
+        } else {
+            fl.set_child(0, 0, (uint32_t)flat_index[root], false, &rb, &rb);
+        }
+        fl.set_child(0, 1, RRS_REF_EMPTY, false, nullptr, nullptr);
+    }
+    for (size_t f = 1; f < flat_to_build.size(); ++f) {
+        const BNode& nd = bn[flat_to_build[f]];
+        fl.attach((uint32_t)f, 0, nd.child[0], nd.box, flat_index);
+        fl.attach((uint32_t)f, 1, nd.child[1], nd.box, flat_index);
+    }
+    // depth (stack bound): longest chain of flat nodes
+    {
+        std::vector<uint32_t> depth(out.nodes.size(), 0);
+        uint32_t mx = 1;
+        depth[0] = 1;
+        // parents always precede... not in DFS/BFS mix; do an explicit walk
+        std::vector<uint32_t> st{0};
+        while (!st.empty()) {
+            uint32_t f = st.back();
+            st.pop_back();
+            mx = std::max(mx, depth[f]);
+            const uint32_t refs[2] = {out.nodes[f].ref0, out.nodes[f].ref1};
+            for (uint32_t r : refs)
+                if (r != RRS_REF_EMPTY && !(r & RRS_REF_LEAF)) {
+                    depth[r] = depth[f] + 1;
+                    st.push_back(r);
+                }
+        }
+        out.max_depth = mx;
+    }
+    dump_topology(bn, root, out.prim_order, out);
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------
+// Camera (lib.rs:99-177)
+// ---------------------------------------------------------------------------------------
+Camera::Camera(Vec3 origin, Vec3 up, Vec3 lookat, double fov, double width, double height, uint32_t ppi) {
+    require(fov > 0. && fov < 180., "Camera::new: fov must be within (0, 180)");
+    require(width > 0., "Camera::new: width must be positive");
+    require(height > 0., "Camera::new: height must be positive");
+    require(!(origin.x == lookat.x && origin.y == lookat.y && origin.z == lookat.z), "Camera::new: origin == lookat");
+    ppc_ = (uint32_t)std::round((double)ppi * 2.54);
+    Vec3 z = unit(lookat - origin);
+    Vec3 x = unit(cross(up, z));
+    Vec3 y = unit(cross(z, x));
+    origin_ = origin;
+    e_x_ = x;
+    e_y_ = y;
+    width_ = width;
+    height_ = height;
+    const double pi = 3.14159265358979323846264338327950288;
+    double rad = fov * (pi / 180.0);
+    z_ = (width / std::tan(rad / 2.)) * z;  // lib.rs:131 (sic: width, not width/2)
+}
+size_t Camera::x_pixels() const { return (size_t)std::round(width_ * (double)ppc_); }
+size_t Camera::y_pixels() const { return (size_t)std::round(height_ * (double)ppc_); }
+RrsCamera Camera::derived() const {
+    RrsCamera c{};
+    set3(c.origin, origin_);
+    set3(c.e_x, e_x_);
+    set3(c.e_y, e_y_);
+    set3(c.z_scaled, z_);
+    c.width = width_;
+    c.height = height_;
+    c.ppc = ppc_;
+    c.x_pixels = (uint32_t)x_pixels();
+    c.y_pixels = (uint32_t)y_pixels();
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------
+// Scene (lib.rs:227-245)
+// ---------------------------------------------------------------------------------------
+Scene::Scene(const std::vector<Object>& objects, double z_near, double z_far, BvhHeuristic heuristic, const Image& hdri,
+             int device, bool with_f64, bool upload) {
+    require(z_near >= 0., "Scene::new: z_near must be >= 0");
+    require(z_far > z_near, "Scene::new: z_far must be > z_near");
+    auto t0 = std::chrono::steady_clock::now();
+    bvh_ = Bvh::build(heuristic, objects);
+    build_seconds_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+    // materials / emissions: objects carry them by value (mat.clone() in lib.rs:407-415);
+    // identical ones share one table entry
+    auto mat_index = [&](const RrsMaterial& m) -> uint32_t {
+        for (size_t i = 0; i < materials_.size(); ++i)
+            if (std::memcmp(&materials_[i], &m, sizeof(RrsMaterial)) == 0) return (uint32_t)i;
+        materials_.push_back(m);
+        return (uint32_t)materials_.size() - 1;
+    };
+    auto emi_index = [&](const Emission& e) -> int32_t {
+        if (e.dark) return -1;
+        RrsEmission r{e.strength, {e.color.x, e.color.y, e.color.z}};
+        for (size_t i = 0; i < emissions_.size(); ++i)
+            if (std::memcmp(&emissions_[i], &r, sizeof(RrsEmission)) == 0) return (int32_t)i;
+        emissions_.push_back(r);
+        return (int32_t)emissions_.size() - 1;
+    };
+    prims_.resize(objects.size());
+    uint32_t last_mat = 0;
+    const RrsMaterial* last_ptr = nullptr;
+    for (size_t k = 0; k < bvh_.prim_order.size(); ++k) {
+        const Object& o = objects[bvh_.prim_order[k]];
+        RrsPrim& p = prims_[k];
+        p.type = o.geom.type;
+        p.obj_id = bvh_.prim_order[k];
+        // fast path for meshes: consecutive objects usually share the material
+        if (!last_ptr || std::memcmp(last_ptr, &o.mat.m, sizeof(RrsMaterial)) != 0) {
+            last_mat = mat_index(o.mat.m);
+            last_ptr = &o.mat.m;
+        }
+        p.material = last_mat;
+        p.emission = emi_index(o.emission);
+        std::memcpy(p.v, o.geom.v, sizeof(p.v));
+    }
+    if (!upload) return;
+    std::vector<float> rgb(hdri.pixels.size() * 3);
+    for (size_t i = 0; i < hdri.pixels.size(); ++i) {
+        rgb[3 * i] = (float)hdri.pixels[i].x;
+        rgb[3 * i + 1] = (float)hdri.pixels[i].y;
+        rgb[3 * i + 2] = (float)hdri.pixels[i].z;
+    }
+    RrsSceneDesc d{};
+    d.abi_version = RRS_ABI_VERSION;
+    d.n_prims = (uint32_t)prims_.size();
+    d.prims = prims_.data();
+    d.n_nodes = (uint32_t)bvh_.nodes.size();
+    d.nodes = bvh_.nodes.data();
+    d.nodes_f64 = with_f64 ? bvh_.nodes_f64.data() : nullptr;
+    d.max_depth = bvh_.max_depth;
+    d.n_materials = (uint32_t)materials_.size();
+    d.materials = materials_.data();
+    d.n_emissions = (uint32_t)emissions_.size();
+    d.emissions = emissions_.data();
+    d.hdri_width = (uint32_t)hdri.width;
+    d.hdri_height = (uint32_t)hdri.height;
+    d.hdri_rgb = rgb.data();
+    d.t_min = z_near;
+    d.t_max = z_far;
+    int rc = rrs_scene_create(&d, device, &handle_);
+    if (rc != RRS_OK) throw Panic(std::string("rrs_scene_create failed: ") + rrs_last_error());
+}
+
+Scene::~Scene() {
+    if (handle_) rrs_scene_destroy(handle_);
+}
+
+void render_gpu_into(const Camera& c, const Scene& s, uint32_t spp, uint32_t max_bounces, const RenderOptions& opt,
+                     float* out_rgb) {
+    if (!s.handle()) throw Panic("render_gpu: scene has no device half");
+    RrsCamera cam = c.derived();
+    RrsRenderParams p{};
+    p.width = cam.x_pixels;
+    p.height = cam.y_pixels;
+    p.spp = spp;
+    p.sample_offset = opt.sample_offset;
+    p.spp_total = opt.spp_total;
+    p.max_bounces = max_bounces;
+    p.seed = opt.seed;
+    p.queue_capacity = opt.queue_capacity;
+    p.flags = opt.flags;
+    int rc = rrs_render(s.handle(), &cam, &p, out_rgb);
+    if (rc != RRS_OK) throw Panic(std::string("rrs_render failed: ") + rrs_last_error());
+}
+
+Image render_gpu(const Camera& c, const Scene& s, uint32_t spp, uint32_t max_bounces, const RenderOptions& opt) {
+    size_t w = c.x_pixels(), h = c.y_pixels();
+    std::vector<float> buf(w * h * 3);
+    render_gpu_into(c, s, spp, max_bounces, opt, buf.data());
+    std::vector<Vec3> px(w * h);
+    for (size_t i = 0; i < w * h; ++i) px[i] = Vec3(buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]);
+    return Image::from_pixels(w, h, std::move(px));  // image.rs:167-173
+}
+
+}  // namespace rayrs

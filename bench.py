@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py — the render hot path on N B200s, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1..c5] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over the workload: every scene of the named BASELINE
+configuration rendered once at its full resolution / spp / depth (default c2 = BASELINE.json
+configs[1]: Cook-Torrance metallic + plastic sphere series, 1024x1024, 256 spp).
+
+  value   Mrays/s with the scene resident in HBM: rrs_render_accumulate into a device buffer
+          (+ the NCCL reduce at N > 1 + resolve), CUDA events on the launching stream, max over ranks.
+  e2e     the same metric through the public render call with HOST buffers (rrs_render: camera and
+          parameters host->device, image device->host every step), wall clock.
+  N > 1   weak scaling: every GPU renders the configuration's spp over its own disjoint global
+          sample range (spp_total = N * spp), one reduce(sum) merges the radiance buffers.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mrays/s (all bounces)"
+UNIT = "Mrays/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--spp", type=int, default=0, help="override spp (invalidates the headline; for experiments)")
+    ap.add_argument("--queue", type=int, default=0, help="rays in flight (0 = library default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def bytes_per_ray_model(workload: str):
+    """B_ray = 32*N_nodes + S_prim*N_prims + 144 + 64*P_miss (+16 per path).  The
+    per-config constants are counted by the oracle offline (scripts/bytes_per_ray.py) and committed."""
+    p = ROOT / "profiles" / "bytes_per_ray.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        if workload in d:
+            return d[workload]
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in Path(self.path).read_text().splitlines():
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path, timed on the host cores.
+# The Rust crate cannot be built in this image (no cargo/rustc), so it is the oracle port.
+# ---------------------------------------------------------------------------------------------
+def cpu_render_sample(cfg, specs, hdri, spp, threads):
+    """Render every scene of the workload at `spp` samples with the oracle; returns (rays, seconds)."""
+    import oracle
+    rays, secs = 0, 0.0
+    for spec in specs:
+        osc = oracle.OracleScene(spec.tables(), hdri.pixels, heuristic=(spec.heuristic.kind, spec.heuristic.splits), build_mode=1)
+        cam17 = oracle.camera_new(**spec.camera_args)
+        _, st = osc.render(cam17, cfg.width, cfg.height, spp, max_bounces=cfg.max_bounces, rng_mode=oracle.RNG_WIDE, nthreads=threads)
+        rays += st["rays"]
+        secs += st["seconds"]  # the tile loop only, like rayrs/src/main.rs:59-100
+        osc.close()
+    return rays, secs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from rayrs_b200 import scenes
+    oracle.build()
+    cfg = scenes.CONFIGS[args.workload]
+    specs = cfg.specs()
+    hdri = scenes.synthetic_hdri(2048, 1024)
+    threads = oracle.hardware_threads()
+    # size the per-step sample from a 1-spp probe so that the whole run ends within a few minutes
+    r1, s1 = cpu_render_sample(cfg, specs, hdri, 1, threads)
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    spp = int(max(1, min(cfg.spp, budget / max(s1, 1e-3))))
+    for _ in range(args.warmup):
+        cpu_render_sample(cfg, specs, hdri, spp, threads)
+    rays, secs = 0, 0.0
+    for _ in range(args.steps):
+        r, s = cpu_render_sample(cfg, specs, hdri, spp, threads)
+        rays += r
+        secs += s
+    value = rays / secs / 1e6
+    sample = f"{args.workload}: all {len(specs)} scene(s) at {cfg.width}x{cfg.height}, {spp} of {cfg.spp} spp per step (Mrays/s is spp-invariant)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": secs / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg.description, "cpu_threads": threads,
+                   "note": "restated reference (oracle port, g++ -O2 -ffp-contract=off), not the Rust binary: no Rust toolchain in the image"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from rayrs_b200 import _ffi, api, scenes
+    from rayrs_b200.multigpu import sample_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — rayrs_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = scenes.CONFIGS[args.workload]
+    spp = args.spp or cfg.spp
+    specs = cfg.specs()
+    hdri = scenes.synthetic_hdri(2048, 1024)
+    t_setup = time.time()
+    built = [(spec, spec.scene(hdri, device=local, with_f64=False), spec.camera()) for spec in specs]
+    t_setup = time.time() - t_setup
+    W, H = cfg.width, cfg.height
+    first, count = sample_range(rank, world, spp * world)  # weak scaling: `spp` samples per GPU
+    assert count == spp
+    spp_total = spp * world
+    stream = torch.cuda.current_stream(dev)
+    sptr = stream.cuda_stream
+    acc = [torch.zeros((H, W, 4), dtype=torch.float32, device=dev) for _ in built]
+    out = [torch.empty((H, W, 3), dtype=torch.float32, device=dev) for _ in built]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_device(flags=0):
+        """inputs resident in HBM; returns (rays, launches, phase dict)"""
+        rays = launches = 0
+        ph = {"generate_ms": 0.0, "extend_ms": 0.0, "shade_ms": 0.0, "iterations": 0}
+        flush.fill_(1)  # L2 flush between timed iterations (inside the region: ~0.1 ms)
+        launches += 1
+        for k, (spec, sc, cam) in enumerate(built):
+            acc[k].zero_()
+            api.render_accumulate(cam, sc, spp, cfg.max_bounces, acc[k].data_ptr(), sptr, sample_offset=first,
+                                  spp_total=spp_total, queue_capacity=args.queue, flags=flags)
+            st = sc.stats()
+            rays += st["rays"]
+            launches += st["kernel_launches"] + 1
+            for key in ph:
+                ph[key] += st[key]
+            if world > 1:
+                dist.reduce(acc[k], dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                api.resolve(sc, acc[k].data_ptr(), W, H, spp_total, out[k].data_ptr(), True, sptr)
+                launches += 1
+        return rays, launches, ph
+
+    host_out = [np.empty((H, W, 3), dtype=np.float32) for _ in built]
+
+    def step_e2e():
+        """public API with HOST buffers.  N == 1: rrs_render (h2d camera+params, d2h image).
+        N > 1: accumulate + reduce + resolve to a host buffer on rank 0."""
+        rays = 0
+        for k, (spec, sc, cam) in enumerate(built):
+            if world == 1:
+                api.render_gpu(cam, sc, spp, cfg.max_bounces, out=host_out[k], queue_capacity=args.queue)
+            else:
+                acc[k].zero_()
+                api.render_accumulate(cam, sc, spp, cfg.max_bounces, acc[k].data_ptr(), sptr, sample_offset=first,
+                                      spp_total=spp_total, queue_capacity=args.queue)
+                dist.reduce(acc[k], dst=0, op=dist.ReduceOp.SUM)
+                if rank == 0:
+                    api.resolve(sc, acc[k].data_ptr(), W, H, spp_total, host_out[k].ctypes.data, False, sptr)
+            rays += sc.stats()["rays"]
+        return rays
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing -----------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    rays = launches = 0
+    phases = {"generate_ms": 0.0, "extend_ms": 0.0, "shade_ms": 0.0, "iterations": 0}
+    for _ in range(args.steps):
+        r, l, ph = step_device(_ffi.RRS_FLAG_TIME_PHASES)
+        rays += r
+        launches += l
+        for key in phases:
+            phases[key] += ph[key]
+    e1.record(stream)
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(rays), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = float(ms.item())
+    rays_all, launches_all = float(tot[0].item()), int(tot[1].item())
+
+    # ---- end to end ---------------------------------------------------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    rays_e2e = 0
+    for _ in range(args.steps):
+        rays_e2e += step_e2e()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    e2e_r = torch.tensor([float(rays_e2e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_r, op=dist.ReduceOp.SUM)
+
+    if rank == 0:
+        value = rays_all / (ms_total * 1e-3) / 1e6
+        e2e_value = float(e2e_r.item()) / float(e2e_s.item()) / 1e6
+        peak, peak_src = measured_peaks()
+        model = bytes_per_ray_model(args.workload)
+        # dominant kernel of the step, from the live per-launch CUDA events of the timed region
+        kern = max(("shade", "extend", "generate"), key=lambda k: phases[k + "_ms"])
+        kms = phases[kern + "_ms"]
+        n_launch = max(1, int(phases["iterations"]))
+        rays_rank0 = rays  # phases were timed on this rank over its own rays
+        roof = {"bound": "hbm", "kernel": "k_" + kern, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+                "traffic": None, "peak_source": peak_src, "avg_launch_ms": kms / n_launch, "launches": n_launch,
+                "share_of_step": kms / ms_total}
+        if model:
+            b = model["kernel_bytes_per_ray"][kern]
+            roof["bytes_per_ray"] = b
+            roof["achieved"] = rays_rank0 * b / (kms * 1e-3) / 1e9
+            roof["frac"] = roof["achieved"] / peak
+            roof["traffic"] = model.get("ncu_dram_bytes_per_launch", {}).get(kern)
+            roof["step_bytes_per_ray"] = model["bytes_per_ray"]
+            roof["step_hbm_frac"] = value * 1e6 / world * model["bytes_per_ray"] / 1e9 / peak
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle  # cpu_baseline leg: the one place bench.py may execute oracle/
+            oracle.build()
+            threads = oracle.hardware_threads()
+            r1, s1 = cpu_render_sample(cfg, specs, hdri, 1, threads)
+            s_spp = int(max(1, min(cfg.spp, args.cpu_seconds / max(s1, 1e-3))))
+            r, s = cpu_render_sample(cfg, specs, hdri, s_spp, threads)
+            cpu = {"value": r / s / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{args.workload}: all {len(specs)} scene(s) at {W}x{H}, {s_spp} of {cfg.spp} spp, {r} rays in {s:.1f} s"}
+        cam_bytes = (len(bytes(_ffi.RrsCamera())) + len(bytes(_ffi.RrsRenderParams()))) * len(built)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg.description + (f" [spp overridden to {spp}]" if args.spp else ""),
+                       "scenes": [s.name for s in specs], "width": W, "height": H, "spp_per_gpu": spp, "spp_total": spp_total,
+                       "max_bounces": cfg.max_bounces, "hdri": "synthetic 2048x1024",
+                       "parallelism": f"sample-split x{world}, one NCCL reduce(sum) of the fp32 radiance buffer",
+                       "l2": "256 MB flush between steps; wavefront state (436 MB at the default queue) streams through HBM",
+                       "rays_per_step": rays_all / args.steps, "scene_setup_s": t_setup},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cam_bytes,
+                    "d2h_bytes_per_step": W * H * 3 * 4 * len(built)},
+            "gpu_launches": launches_all,
+            "clocks": clocks,
+            "roofline": roof,
+            "phases_ms": {k: v for k, v in phases.items()},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    for _, sc, _ in built:
+        sc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -145,9 +145,10 @@ class OracleScene:
 
     def traversal_counts(self, rays):
         r = _d(rays).reshape(-1, 6)
-        b, p, h = C.c_uint64(), C.c_uint64(), C.c_uint64()
-        lib().orc_traversal_counts(self._p, r.ctypes.data, r.shape[0], C.byref(b), C.byref(p), C.byref(h))
-        return b.value, p.value, h.value
+        b, h = C.c_uint64(), C.c_uint64()
+        p = (C.c_uint64 * 3)()
+        lib().orc_traversal_counts(self._p, r.ctypes.data, r.shape[0], C.byref(b), p, C.byref(h))
+        return b.value, [int(x) for x in p], h.value  # boxes tested, [spheres, planes, triangles] tested, hits
 
     def collect_path_rays(self, cam17, W, H, spp, max_bounces, seed=0x5EEDB200, rng_mode=RNG_MATCHED, pixel_stride=1,
                           cap=1 << 20):

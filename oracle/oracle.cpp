@@ -1270,7 +1270,7 @@ void orc_rng_uniforms(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t s
 // would do it: for each ray, the number of child boxes tested and of
 // primitives tested.  This defines N_nodes / N_prims in the bytes-per-ray model.
 static void pruned_counts_rec(const BvhTree* n, const Ray& ray, double tmin, double& tbest, uint64_t& boxes,
-                              uint64_t& prims) {
+                              uint64_t* prims) {
     // n is a Node whose own box has already been accepted
     struct Ent { const BvhTree* c; double entry; bool go; };
     Ent e[4];
@@ -1301,19 +1301,21 @@ static void pruned_counts_rec(const BvhTree* n, const Ray& ray, double tmin, dou
     for (size_t i = 0; i < k; ++i) {
         if (!e[i].go) continue;
         if (e[i].c->leaf) {
-            prims++;
+            const Hittable* g = e[i].c->obj->geom.get();
+            prims[dynamic_cast<const Sphere*>(g) ? 0 : (dynamic_cast<const Plane*>(g) ? 1 : 2)]++;
             double t;
-            if (e[i].c->obj->geom->intersect(ray, t) && t > tmin && t < tbest) tbest = t;
+            if (g->intersect(ray, t) && t > tmin && t < tbest) tbest = t;
         } else {
             if (e[i].entry > tbest) continue;
             pruned_counts_rec(e[i].c, ray, tmin, tbest, boxes, prims);
         }
     }
 }
+// prims_out: 3 counters = spheres, planes, triangles tested
 void orc_traversal_counts(const OrcScene* h, const double* rays, uint64_t n, uint64_t* boxes_out, uint64_t* prims_out,
                           uint64_t* hits_out) {
     const Scene& s = h->s;
-    uint64_t boxes = 0, prims = 0, hits = 0;
+    uint64_t boxes = 0, prims[3] = {0, 0, 0}, hits = 0;
     for (uint64_t i = 0; i < n; ++i) {
         Ray r{v3(rays[i * 6], rays[i * 6 + 1], rays[i * 6 + 2]), v3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5])};
         double tbest = s.tmax;
@@ -1322,7 +1324,7 @@ void orc_traversal_counts(const OrcScene* h, const double* rays, uint64_t n, uin
         if (tbest < s.tmax) hits++;
     }
     *boxes_out = boxes;
-    *prims_out = prims;
+    prims_out[0] = prims[0]; prims_out[1] = prims[1]; prims_out[2] = prims[2];
     *hits_out = hits;
 }
 

@@ -1,0 +1,149 @@
+"""Closest-hit parity on fixed ray sets (north_star: primitive IDs bit-exact, t within 1e-5
+relative).  GPU, through the C ABI (rrs_intersect).
+
+ * precision=64 (literal fp64 traversal of the flattened tree): IDs equal on EVERY ray, t to 1e-12.
+ * precision=32 (production traversal): IDs equal on every ray whose answer is stable under a
+   2e-6 perturbation in the oracle (the others sit on a primitive edge / silhouette / t-tie where
+   fp32 may legitimately decide differently; their count is reported and bounded), t to 1e-5.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from rayrs_b200 import scenes
+from rayrs_b200.api import BvhHeuristic
+
+pytestmark = pytest.mark.gpu
+
+N_RAYS = 1 << 17
+
+
+def fixed_ray_set(spec, osc, n, seed=7):
+    """half primary rays (oracle raygen, counter RNG), half uniform origins in 1.5x the scene
+    box with uniform directions; generated in f64, rounded to f32 — the rounded values are what
+    both sides consume."""
+    cam = spec.camera()
+    W, H = cam.x_pixels(), cam.y_pixels()
+    rng = np.random.default_rng(seed)
+    h = n // 2
+    prim = oracle.primary_rays(cam.derived17(), W, H, rng.integers(0, H, h), rng.integers(0, W, h), rng.integers(0, 4096, h))
+    b = osc.bbox()
+    lo, hi = np.array([b[0], b[2], b[4]]), np.array([b[1], b[3], b[5]])
+    c, e = (lo + hi) / 2, (hi - lo) / 2
+    # keep the random half near the interesting part of the scene (the floor is 50 x 50)
+    e = np.minimum(e, 8.0)
+    org = c + rng.uniform(-1.5, 1.5, (n - h, 3)) * e
+    d = rng.normal(size=(n - h, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([prim, np.concatenate([org, d], axis=1)], axis=0)
+    return rays.astype(np.float32).astype(np.float64)
+
+
+SCENES = {
+    "diffuse_single_sphere": lambda: scenes.diffuse_single_sphere(256, 256),
+    "spheres_metallic": lambda: scenes.cook_torrance_spheres_metallic(320, 128),
+    "material_test": lambda: scenes.material_test(320, 64),
+    "copper_torus_20k": lambda: scenes.copper_torus(100, 100, 256, 192),
+    "copper_torus_20k_midpoint": lambda: scenes.copper_torus(100, 100, 256, 192, heuristic=BvhHeuristic.Midpoint()),
+    "mixed_5k": lambda: scenes.mixed_scene(50, 50, 320, 180),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_ids_and_t_against_oracle(name, hdri_small):
+    spec = SCENES[name]()
+    sc = spec.scene(hdri_small)
+    osc = oracle.OracleScene(spec.tables(), hdri_small.pixels, heuristic=(spec.heuristic.kind, spec.heuristic.splits), build_mode=1)
+    rays = fixed_ray_set(spec, osc, N_RAYS)
+    oid, ot = osc.intersect(rays)
+    hit = oid >= 0
+    assert hit.mean() > 0.2  # the ray set actually exercises the scene
+
+    # ---- fp64 verification traversal: everything, everywhere
+    did, dt = sc.intersect(rays, 64)
+    assert np.array_equal(did, oid)
+    assert np.all(np.isinf(dt[~hit]))
+    assert np.max(np.abs(dt[hit] - ot[hit]) / ot[hit]) <= 1e-12
+    print(f"[{name}] fp64: {N_RAYS} rays, ids all equal, t bit-exact on {np.mean(dt[hit] == ot[hit]) * 100:.3f}%")
+
+    # ---- production fp32 traversal
+    gid, gt = sc.intersect(rays, 32)
+    stable = osc.intersect_stable(rays)
+    dropped = int((~stable).sum())
+    assert dropped < 0.05 * N_RAYS
+    mism_all = int((gid != oid).sum())
+    assert np.array_equal(gid[stable], oid[stable]), f"{int((gid[stable] != oid[stable]).sum())} stable rays differ"
+    ok = stable & hit
+    rel = np.abs(gt[ok] - ot[ok]) / ot[ok]
+    assert rel.max() <= 1e-5, rel.max()
+    print(f"[{name}] fp32: ids equal on all {int(stable.sum())} stable rays ({dropped} unstable dropped, "
+          f"{mism_all} of those differ), max rel t err {rel.max():.2e}")
+    sc.close()
+
+
+def test_fp32_matches_fp64_at_full_size_1m_triangles(hdri_small):
+    """BASELINE config 4 mesh (1.0M triangles, SAH-1000): the production traversal against the fp64
+    literal traversal of the same flattened tree, 2^20 rays; plus an oracle spot check."""
+    spec = scenes.copper_torus(1000, 500, 1920, 1080)
+    sc = spec.scene(hdri_small)
+    assert sc.n_prims == 1_000_001
+    cam = spec.camera()
+    rng = np.random.default_rng(11)
+    n = 1 << 20
+    rays = oracle.primary_rays(cam.derived17(), 1920, 1080, rng.integers(0, 1080, n), rng.integers(0, 1920, n),
+                               rng.integers(0, 256, n)).astype(np.float32).astype(np.float64)
+    gid, gt = sc.intersect(rays, 32)
+    did, dt = sc.intersect(rays, 64)
+    agree = gid == did
+    # edges of 1M tiny triangles: a few rays per 10^4 land within fp32 noise of an edge
+    assert agree.mean() > 0.999
+    hit = agree & (did >= 0)
+    assert hit.mean() > 0.3
+    rel = np.abs(gt[hit] - dt[hit]) / dt[hit]
+    assert np.quantile(rel, 0.9999) <= 1e-5
+    # where they disagree the two answers are neighbouring surfaces at (almost) the same distance
+    dis = (~agree) & (gid >= 0) & (did >= 0)
+    if dis.any():
+        assert np.max(np.abs(gt[dis] - dt[dis]) / dt[dis]) < 1e-2
+    print(f"[torus 1M] fp32 == fp64 ids on {agree.mean() * 100:.4f}% of {n} rays; p99.99 rel t err {np.quantile(rel, 0.9999):.2e}")
+    # oracle spot check of the fp64 kernel on a subset (the oracle walks the pointer tree unpruned)
+    osc = oracle.OracleScene(spec.tables(), hdri_small.pixels, build_mode=1)
+    sub = rays[: 1 << 14]
+    oid, ot = osc.intersect(sub)
+    assert np.array_equal(oid, did[: 1 << 14])
+    h = oid >= 0
+    assert np.max(np.abs(ot[h] - dt[: 1 << 14][h]) / ot[h]) <= 1e-12
+    sc.close()
+
+
+def test_edge_cases(hdri_small):
+    spec = scenes.diffuse_single_sphere(64, 64)
+    sc = spec.scene(hdri_small)
+    # empty batch
+    ids, t = sc.intersect(np.zeros((0, 6)), 32)
+    assert ids.size == 0
+    # axis-parallel rays (zero direction components: inf reciprocals), rays starting inside the
+    # sphere, rays pointing away, rays along the floor plane
+    rays = np.array([
+        [0, 5, 0, 0, -1, 0],      # straight down onto the sphere
+        [0, 1, 0, 0, 1, 0],       # from the centre of the sphere upward (inside hit)
+        [0, 1, 0, 1, 0, 0],
+        [10, 5, 0, 0, -1, 0],     # straight down onto the floor
+        [10, 5, 0, 0, 1, 0],      # away from everything
+        [0, 0.5, 10, 0, 0, -1],   # horizontal into the sphere
+        [30, 5, 0, 0, -1, 0],     # outside the floor rectangle
+        [24.5, 5, 24.5, 0, -1, 0],
+        [-25.0, 5, 0, 0, -1, 0],  # on the closed edge of the half-open range
+        [25.0, 5, 0, 0, -1, 0],   # on the open edge
+    ], dtype=np.float64)
+    osc = oracle.OracleScene(spec.tables(), hdri_small.pixels)
+    oid, ot = osc.intersect(rays)
+    for prec in (32, 64):
+        gid, gt = sc.intersect(rays, prec)
+        assert np.array_equal(gid, oid), (prec, gid, oid)
+        h = oid >= 0
+        assert np.allclose(gt[h], ot[h], rtol=1e-6)
+    assert list(oid) == [1, 1, 1, 0, -1, 1, -1, 0, 0, -1]
+    with pytest.raises(Exception):
+        sc.intersect(rays, 16)
+    sc.close()

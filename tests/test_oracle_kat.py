@@ -1,0 +1,137 @@
+"""The oracle against every numeric known-answer test the reference holds for the hot path
+(SURVEY.md 4 / 8c).  Each case cites the reference test it restates.  CPU only."""
+import numpy as np
+import pytest
+
+import oracle
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built(native_built):
+    return native_built
+
+
+# ---- RNG: Random123 known answers for Philox4x32-10 (kat_vectors of the Random123 distribution)
+@pytest.mark.parametrize("ctr,key,expect", [
+    ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+    ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+    ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+     [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+])
+def test_philox_known_answers(ctr, key, expect):
+    assert list(oracle.philox(ctr, key)) == expect
+
+
+def test_rng_uniform_ranges():
+    for mode in (oracle.RNG_WIDE, oracle.RNG_MATCHED):
+        u = np.array([oracle.rng_uniforms(7, p, s, 1, mode) for p in range(50) for s in range(4)])
+        assert (u >= 0).all() and (u < 1).all()
+        assert 0.4 < u.mean() < 0.6
+
+
+# ---- bvh.rs:543-559 test_bvh_intersect_node_leafnode: t == 4.0 exactly
+def test_bvh_node_leafnode_t_equals_4():
+    from rayrs_b200.api import Material, Object, build_tables
+    tables = build_tables([Object.sphere(1.0, (0, 0, 0), Material.no_reflect())])
+    s = oracle.OracleScene(tables, np.ones((2, 2, 3)), z_near=0.001, z_far=1000.0)
+    ids, t = s.intersect(np.array([[-5.0, 0, 0, 1, 0, 0]]))
+    assert ids[0] == 0 and t[0] == 4.0
+
+
+# ---- geometry.rs:744-774 sphere tests
+def test_sphere_outside():
+    assert oracle.sphere_intersect(1.0, [0, 0, 0], [0, 0, 5, 0, 0, -1]) > 0
+
+
+def test_sphere_inside():
+    assert oracle.sphere_intersect(1.0, [0, 0, 0], [0, 0, 0, 0, 1, 0]) > 0
+
+
+def test_sphere_miss():
+    assert oracle.sphere_intersect(1.0, [0, 0, 0], [0, 5, 0, 0, 1, 0]) is None
+
+
+def test_sphere_glancing():
+    assert oracle.sphere_intersect(1.0, [0, 0, 0], [0.99999, -5, 0, 0, 1, 0]) > 0
+
+
+# ---- geometry.rs:782-828 plane tests (front and back for each axis)
+@pytest.mark.parametrize("axis,ray", [
+    (0, [5, 0, 0, -1, 0, 0]), (0, [-5, 0, 0, 1, 0, 0]),
+    (2, [0, 5, 0, 0, -1, 0]), (2, [0, -5, 0, 0, 1, 0]),
+    (4, [0, 0, 5, 0, 0, -1]), (4, [0, 0, -5, 0, 0, 1]),
+])
+def test_plane_front_back(axis, ray):
+    assert oracle.plane_intersect(axis, -1, 1, -1, 1, 0.0, ray) > 0
+
+
+def test_plane_half_open_ranges():
+    # Range::contains is [start, end): geometry.rs:229-271
+    assert oracle.plane_intersect(2, -1, 1, -1, 1, 0.0, [-1.0, 5, 0, 0, -1, 0]) is not None
+    assert oracle.plane_intersect(2, -1, 1, -1, 1, 0.0, [1.0, 5, 0, 0, -1, 0]) is None
+    # parallel ray: d_k == 0 -> None
+    assert oracle.plane_intersect(2, -1, 1, -1, 1, 0.0, [0, 5, 0, 1, 0, 0]) is None
+    # any sign of t is returned
+    assert oracle.plane_intersect(2, -1, 1, -1, 1, 0.0, [0, 5, 0, 0, 1, 0]) == -5.0
+
+
+# ---- geometry.rs:847-887 AABB tests
+@pytest.mark.parametrize("ray,tmin,expect", [
+    ([-5, 0, 0, 1, 0, 0], 0.001, True),
+    ([0, -5, 0, 0, 1, 0], 0.0001, True),
+    ([0, 0, -5, 0, 0, 1], 0.001, True),
+    ([0, 0, 0, 0, 0, 1], 0.001, True),
+    ([1.1, 0, 0, 0, 1, 1], 0.001, False),
+    ([2, 0, 0, -1, -2, 0], 0.001, False),
+])
+def test_aabb(ray, tmin, expect):
+    assert oracle.aabb_intersect([-1, 1, -1, 1, -1, 1], ray, tmin, 1000.0) is expect
+
+
+def test_aabb_zero_extent_never_hit():
+    # geometry.rs:474,491,508: tmax <= tmin -> false; a flat box has tmin == tmax on its flat axis
+    assert oracle.aabb_intersect([-1, 1, 0, 0, -1, 1], [0, 5, 0, 0.1, -1, 0.1], 1e-6, 1e6) is False
+
+
+# ---- doctests lib.rs:150-151,172-173: pixel counts
+def test_camera_pixel_counts():
+    c = oracle.camera_new([1, 1, 1], [0, 1, 0], [0, 0, 0], 90.0, 20.0, 10.0, 90)
+    assert c[15] == 4580 and c[16] == 2290
+    assert c[14] == 229  # ppc = round(90 * 2.54)
+
+
+# ---- doctests geometry.rs:540-542,575,607,638: box of two unit spheres at x = +-1
+def test_bbox_two_spheres():
+    from rayrs_b200.api import Material, Object, build_tables
+    m = Material.no_reflect()
+    tables = build_tables([Object.sphere(1.0, (1, 0, 0), m), Object.sphere(1.0, (-1, 0, 0), m)])
+    s = oracle.OracleScene(tables, np.ones((2, 2, 3)))
+    b = s.bbox()
+    assert b[0] == -2.0 and b[1] == 2.0
+    assert tuple(b[6:9]) == (0.0, 0.0, 0.0)
+    assert b[9] == 16.0 and b[10] == 40.0
+
+
+# ---- doctest vecmath.rs:336-339: right-handed basis
+def test_orthonormal_basis_handedness():
+    e1, e2 = oracle.orthonormal_basis([0, 0, 1])
+    assert np.allclose(np.cross(e1, e2), [0, 0, 1], atol=0, rtol=0)
+    for n in ([1, 0, 0], [0, 1, 0], [0.6, 0.0, 0.8], [-0.3, 0.9, np.sqrt(1 - 0.09 - 0.81)]):
+        e1, e2 = oracle.orthonormal_basis(n)
+        assert abs(np.dot(e1, n)) < 1e-15 and abs(np.dot(e2, n)) < 1e-15
+        assert np.allclose(np.cross(e1, e2), n, atol=1e-15)
+
+
+# ---- triangle (unpinned by the reference; closed-form cases)
+def test_triangle_basic():
+    tri = [-1, 0, 0, 1, 0, 0, 0, 1, 0]
+    t, n = oracle.triangle_intersect(tri, [0, 0.25, 5, 0, 0, -1])
+    assert t == 5.0 and tuple(n) == (0.0, 0.0, 1.0)
+    t, _ = oracle.triangle_intersect(tri, [0, 0.25, -5, 0, 0, 1])  # two sided
+    assert t == 5.0
+    t, _ = oracle.triangle_intersect(tri, [0, 2.0, 5, 0, 0, -1])
+    assert t is None
+    t, _ = oracle.triangle_intersect(tri, [0, 0.25, 5, 0, 0, 1])  # behind
+    assert t is None
+    t, _ = oracle.triangle_intersect(tri, [0, 0.25, 5, 1, 0, 0])  # parallel: NaN/inf quotients
+    assert t is None or not np.isfinite(t)

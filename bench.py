@@ -295,8 +295,11 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     rays_e2e = 0
+    e2e_step_ms = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         rays_e2e += step_e2e()
+        e2e_step_ms.append((time.perf_counter() - ts) * 1e3)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     e2e_r = torch.tensor([float(rays_e2e)], dtype=torch.float64, device=dev)
@@ -347,7 +350,7 @@ def run_ours(args):
                        "l2": "256 MB flush between steps; wavefront state (436 MB at the default queue) streams through HBM",
                        "rays_per_step": rays_all / args.steps, "scene_setup_s": t_setup},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cam_bytes,
-                    "d2h_bytes_per_step": W * H * 3 * 4 * len(built)},
+                    "d2h_bytes_per_step": W * H * 3 * 4 * len(built), "ms_per_step": e2e_step_ms},
             "gpu_launches": launches_all,
             "clocks": clocks,
             "roofline": roof,

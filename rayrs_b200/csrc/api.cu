@@ -147,10 +147,11 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
         std::memcpy(&fobj, &p.obj_id, 4);
         std::memcpy(&femi, &emi, 4);
         if (p.type == RRS_TRIANGLE) {
-            // Triangle::new geometry.rs:341-355: edges derived in f64, then rounded
+            // the three vertices (shared vertices of a mesh must stay bit-identical across triangles
+            // for the watertight test, so no per-triangle edge vectors are stored)
             q.a = make_float4((float)p.v[0], (float)p.v[1], (float)p.v[2], fmeta);
-            q.b = make_float4((float)(p.v[3] - p.v[0]), (float)(p.v[4] - p.v[1]), (float)(p.v[5] - p.v[2]), fobj);
-            q.c = make_float4((float)(p.v[6] - p.v[0]), (float)(p.v[7] - p.v[1]), (float)(p.v[8] - p.v[2]), femi);
+            q.b = make_float4((float)p.v[3], (float)p.v[4], (float)p.v[5], fobj);
+            q.c = make_float4((float)p.v[6], (float)p.v[7], (float)p.v[8], femi);
         } else if (p.type == RRS_SPHERE) {
             q.a = make_float4((float)p.v[1], (float)p.v[2], (float)p.v[3], fmeta);
             q.b = make_float4((float)p.v[0], 0.f, 0.f, fobj);
@@ -231,7 +232,9 @@ void rrs_scene_destroy(RrsScene* scene) {
     cudaSetDevice(s.device);
     wf_free(&s);
     cudaFree(s.prims); cudaFree(s.nodes); cudaFree(s.mats); cudaFree(s.emis); cudaFree(s.hdri);
-    cudaFree(s.prims_f64); cudaFree(s.nodes_f64); cudaFree(s.accum); cudaFree(s.census);
+    cudaFree(s.prims_f64); cudaFree(s.nodes_f64); cudaFree(s.accum); cudaFree(s.census); cudaFree(s.resolve_dev);
+    if (s.resolve_pinned) cudaFreeHost(s.resolve_pinned);
+    if (s.h_census) cudaFreeHost(s.h_census);
     delete scene;
 }
 

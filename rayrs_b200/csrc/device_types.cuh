@@ -12,7 +12,7 @@ namespace rrs {
 // ---------------------------------------------------------------------------------------
 // Primitive record, 48 B, three float4 so that it is fetched with 128-bit loads.
 //   meta = type | material << 2          (a.w)
-//   triangle : a = (p1, meta)  b = (e1, obj_id)  c = (e2, emission)
+//   triangle : a = (p1, meta)  b = (p2, obj_id)  c = (p3, emission)
 //   sphere   : a = (centre, meta) b = (r^2, -, -, obj_id) c = (-, -, -, emission)
 //   plane    : a = (pos, umin, umax, meta) b = (vmin, vmax, axis, obj_id) c = (-, -, -, emission)
 struct DPrim {

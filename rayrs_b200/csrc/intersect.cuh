@@ -78,20 +78,56 @@ __device__ __forceinline__ bool hit_plane(float4 a, float4 b, float3 o, float3 d
     return false;
 }
 
-// Triangle: Moeller-Trumbore exactly as coded (no determinant epsilon, two-sided).  NaN/inf
-// quotients fall out at the caller's t > tmin && t < tbest.
-__device__ __forceinline__ bool hit_triangle(float4 a, float4 b, float4 c, float3 o, float3 d, float& t) {
-    float3 e1 = xyz(b), e2 = xyz(c);
-    float3 T = sub3(o, xyz(a));
-    float3 P = cross3(d, e2);
-    float3 Q = cross3(T, e1);
-    float den = dot3(P, e1);
-    float inv = 1.0f / den;
-    float dist = dot3(Q, e2) * inv;
-    float u = dot3(P, T) * inv;
-    float v = dot3(Q, d) * inv;
-    if (dist < 0.f || u < 0.f || v < 0.f || u + v > 1.f) return false;
-    t = dist;
+// Triangle.  The reference is Moeller-Trumbore in f64 (geometry.rs:359-375): two-sided, edges
+// inclusive (u >= 0, v >= 0, u + v <= 1), no determinant epsilon.  In fp32 that formulation leaks:
+// with the origin ~10 units from a 0.007-unit triangle the barycentrics carry ~1e-4 of rounding
+// and a ray can miss BOTH triangles of a shared edge (measured: ~1e-4 of rays on the 1M-triangle
+// mesh passed through the surface).  The production test is therefore the watertight edge-function
+// test of Woop, Benthin & Wald (JCGT 2013): vertices are translated to the ray origin and sheared
+// into ray space; the edge function of a shared edge is computed from the SAME two translated
+// vertices with exactly negated rounding in both triangles (no FMA contraction), so one of them
+// always accepts.  Same decisions as the reference away from edges, same inclusive edges, two-sided.
+struct RayShear {
+    int kx, ky, kz;
+    float sx, sy, sz;
+};
+__device__ __forceinline__ float comp(float3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+__device__ __forceinline__ RayShear make_shear(float3 d) {
+    RayShear r;
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    r.kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+    r.kx = r.kz == 2 ? 0 : r.kz + 1;
+    r.ky = r.kx == 2 ? 0 : r.kx + 1;
+    float dz = comp(d, r.kz);
+    if (dz < 0.f) {  // preserve winding
+        int t = r.kx;
+        r.kx = r.ky;
+        r.ky = t;
+    }
+    r.sz = 1.0f / dz;
+    r.sx = comp(d, r.kx) * r.sz;
+    r.sy = comp(d, r.ky) * r.sz;
+    return r;
+}
+__device__ __forceinline__ bool hit_triangle(float4 a, float4 b, float4 c, float3 o, const RayShear& rs, float& t) {
+    float3 A = sub3(xyz(a), o), B = sub3(xyz(b), o), C = sub3(xyz(c), o);
+    float Az = comp(A, rs.kz), Bz = comp(B, rs.kz), Cz = comp(C, rs.kz);
+    float Ax = __fmaf_rn(-rs.sx, Az, comp(A, rs.kx)), Ay = __fmaf_rn(-rs.sy, Az, comp(A, rs.ky));
+    float Bx = __fmaf_rn(-rs.sx, Bz, comp(B, rs.kx)), By = __fmaf_rn(-rs.sy, Bz, comp(B, rs.ky));
+    float Cx = __fmaf_rn(-rs.sx, Cz, comp(C, rs.kx)), Cy = __fmaf_rn(-rs.sy, Cz, comp(C, rs.ky));
+    float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+    float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+    float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
+    if (U == 0.f || V == 0.f || W == 0.f) {  // exactly on an edge in fp32: decide in fp64
+        U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+        V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+        W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+    }
+    if ((U < 0.f || V < 0.f || W < 0.f) && (U > 0.f || V > 0.f || W > 0.f)) return false;
+    float det = U + V + W;
+    if (det == 0.f) return false;
+    float T = U * (rs.sz * Az) + V * (rs.sz * Bz) + W * (rs.sz * Cz);
+    t = T / det;
     return true;
 }
 
@@ -110,6 +146,7 @@ __device__ __forceinline__ void closest_hit(const DScene& sc, const DNodeHalf* _
     tbest = sc.tmax;
     best = RRS_NO_PRIM;
     float3 idir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const RayShear shear = make_shear(d);
     int sp = 0;
     uint32_t cur = 0;  // virtual root
     const uint32_t DONE = 0x7FFFFFFFu;
@@ -175,7 +212,7 @@ __device__ __forceinline__ void closest_hit(const DScene& sc, const DNodeHalf* _
                 if (type == RRS_TRIANGLE) {
                     if (pi == origin_prim) continue;  // planar primitive cannot re-hit itself
                     float4 c = __ldg(pp + 2);
-                    hit = hit_triangle(a, b, c, o, d, t);
+                    hit = hit_triangle(a, b, c, o, shear, t);
                 } else if (type == RRS_SPHERE) {
                     hit = hit_sphere(a, b, o, d, pi == origin_prim, t);
                 } else {

@@ -295,7 +295,8 @@ __device__ __forceinline__ float3 prim_normal(const DPrim* prims, uint32_t pi, f
         return f3(k == 0 ? s : 0.f, k == 1 ? s : 0.f, k == 2 ? s : 0.f);
     }
     float4 c = __ldg(pp + 2);
-    return normalize3(cross3(xyz(b), xyz(c)));
+    float3 p1 = xyz(a);
+    return normalize3(cross3(sub3(xyz(b), p1), sub3(xyz(c), p1)));  // Triangle::new geometry.rs:341-355
 }
 
 }  // namespace rrs

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 
 #include "intersect.cuh"
 #include "shading.cuh"
@@ -28,57 +29,96 @@ static constexpr int kBlock = 128;  // threads per block of the persistent kerne
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 // ---------------------------------------------------------------------------------------
-// plan
+// Queue layout: the ray / state / hit queues are split into `regions` stripes of `region_cap`
+// slots; block b of every kernel owns stripe b.  All queue bookkeeping (work cursor, append
+// cursor of the compaction) is therefore a SHARED-MEMORY atomic; the only global atomics left
+// are one per block per iteration (claiming new paths, ray statistics).  The first version of
+// this file used one global work cursor and one global append counter: ncu showed 75 % of
+// k_shade's stall samples on the shuffle behind those two same-address atomics
+// (profiles/r01a_c2_globalqueue_stalls.txt).
 // ---------------------------------------------------------------------------------------
-__global__ void k_plan(DCounters* c, uint32_t capacity) {
+// One direction of the ping-pong, resolved on the host (no dynamic indexing of kernel parameters).
+struct QueueSet {
+    float4* ray_o;      // current queue: origin xyz, origin primitive
+    float4* ray_d;      //                direction xyz, pixel
+    float4* state;      //                throughput rgb, sample << 8 | bounce
+    float2* hits;       //                t, primitive
+    uint32_t* count;    // rays per stripe of the current queue
+    float4* out_o;      // the other queue (survivors of shade)
+    float4* out_d;
+    float4* out_state;
+    uint32_t* out_count;
+    uint32_t region_cap;
+};
+
+// ---------------------------------------------------------------------------------------
+// plan (1 thread): rotate the live-ray counters, raise `done`
+// ---------------------------------------------------------------------------------------
+__global__ void k_plan(DCounters* c) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    // n_cur still holds what the previous iteration extended
-    c->rays += c->n_cur;
     uint32_t live = c->n_next;
-    unsigned long long left = c->total_paths - c->next_path;
-    uint32_t room = capacity - live;
-    uint32_t gen = (uint32_t)(left < (unsigned long long)room ? left : (unsigned long long)room);
-    c->gen_first = c->next_path;
-    c->gen_count = gen;
-    c->next_path += gen;
-    c->n_cur = live;  // generate appends behind the survivors
+    c->n_cur = live;
     c->n_next = 0;
-    c->work_extend = 0;
-    c->work_shade = 0;
-    c->done = (live == 0 && gen == 0) ? 1u : 0u;
+    c->done = (live == 0 && c->next_path >= c->total_paths) ? 1u : 0u;
     if (!c->done) c->iterations++;
 }
 
 // ---------------------------------------------------------------------------------------
-// generate
+// generate: refill stripe b behind its survivors with new primary rays
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_generate(RenderConst rc, DCounters* __restrict__ c, float4* __restrict__ ray_o,
-                                                      float4* __restrict__ ray_d, float4* __restrict__ state) {
-    const uint32_t gen = c->gen_count;
-    const unsigned long long first = c->gen_first;
+template <bool EXACT_TILES>
+__device__ __forceinline__ void phase_generate(const RenderConst& rc, DCounters* __restrict__ c, const QueueSet& q,
+                                               uint32_t* s_u32, unsigned long long* s_u64) {
+    const uint32_t b = blockIdx.x;
+    const uint32_t n0 = q.count[b];
+    if (threadIdx.x == 0) {
+        uint32_t need = q.region_cap - n0, got = 0;
+        unsigned long long base = 0;
+        // claim `need` consecutive padded path indices (one global atomic per block per iteration)
+        if (need && c->next_path < c->total_paths) {
+            base = atomicAdd(&c->next_path, (unsigned long long)need);
+            if (base < c->total_paths) {
+                unsigned long long left = c->total_paths - base;
+                got = left < need ? (uint32_t)left : need;
+            }
+        }
+        s_u64[0] = base;
+        s_u32[0] = got;
+        s_u32[1] = n0;  // append cursor
+    }
+    __syncthreads();
+    const uint32_t got = s_u32[0];
+    const unsigned long long first = s_u64[0];
     const uint32_t lane = lane_id();
-    // padded to whole warps so that every lane takes part in the ballot
-    const uint32_t gen_pad = (gen + 31u) & ~31u;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < gen_pad; k += gridDim.x * blockDim.x) {
-        bool valid = k < gen;
+    const size_t off = (size_t)b * q.region_cap;
+    float4* __restrict__ ray_o = q.ray_o + off;
+    float4* __restrict__ ray_d = q.ray_d + off;
+    float4* __restrict__ state = q.state + off;
+    const uint32_t got_pad = (got + 31u) & ~31u;
+    for (uint32_t k = threadIdx.x; k < got_pad; k += blockDim.x) {
+        bool valid = k < got;
         uint32_t row = 0, col = 0, s_local = 0;
         if (valid) {
             unsigned long long p = first + k;
             s_local = (uint32_t)(p / rc.npix_pad);
-            uint32_t q = (uint32_t)(p - (unsigned long long)s_local * rc.npix_pad);
-            uint32_t tile = q >> 5, l = q & 31u;
+            uint32_t pq = (uint32_t)(p - (unsigned long long)s_local * rc.npix_pad);
+            uint32_t tile = pq >> 5, l = pq & 31u;
             uint32_t ty = tile / rc.tiles_x, tx = tile - ty * rc.tiles_x;
             col = tx * 8u + (l & 7u);
             row = ty * 4u + (l >> 3);
-            valid = col < rc.cam.W && row < rc.cam.H;
+            if (!EXACT_TILES) valid = col < rc.cam.W && row < rc.cam.H;
         }
-        uint32_t ballot = __ballot_sync(0xFFFFFFFFu, valid);
-        if (ballot == 0) continue;
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&c->n_cur, __popc(ballot));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        uint32_t slot;
+        if (EXACT_TILES) {
+            slot = n0 + k;
+        } else {
+            uint32_t ballot = __ballot_sync(0xFFFFFFFFu, valid);
+            uint32_t base = 0;
+            if (lane == 0 && ballot) base = atomicAdd(&s_u32[1], __popc(ballot));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            slot = base + __popc(ballot & ((1u << lane) - 1u));
+        }
         if (!valid) continue;
-        uint32_t slot = base + __popc(ballot & ((1u << lane) - 1u));
         uint32_t pixel = row * rc.cam.W + col;
         uint32_t sample = rc.sample_offset + s_local;
         float4 u = rng_uniforms(rc.seed, pixel, sample, 0u);
@@ -91,35 +131,39 @@ __global__ void __launch_bounds__(kBlock) k_generate(RenderConst rc, DCounters* 
         ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
         state[slot] = make_float4(1.f, 1.f, 1.f, __uint_as_float(sample << 8));
     }
+    __syncthreads();
+    if (threadIdx.x == 0) q.count[b] = EXACT_TILES ? n0 + got : s_u32[1];
+}
+
+template <bool EXACT_TILES>
+__global__ void __launch_bounds__(kBlock) k_generate(RenderConst rc, DCounters* __restrict__ c, QueueSet q) {
+    __shared__ uint32_t s_u32[2];
+    __shared__ unsigned long long s_u64[1];
+    phase_generate<EXACT_TILES>(rc, c, q, s_u32, s_u64);
 }
 
 // ---------------------------------------------------------------------------------------
-// extend
+// extend: closest hit for every ray of stripe b; warps pull 32-ray batches from a shared cursor
 // ---------------------------------------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DCounters* __restrict__ c, const float4* __restrict__ ray_o,
-                                                    const float4* __restrict__ ray_d, float2* __restrict__ hits) {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
-    // [smem_nodes * 64 B top-of-tree nodes][stack_entries * blockDim.x * 4 B traversal stacks]
-    DNodeHalf* s_nodes = reinterpret_cast<DNodeHalf*>(smem_raw);
-    uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem_raw + (size_t)sc.smem_nodes * 64u);
-    if (sc.smem_nodes) {
-        const float4* src = reinterpret_cast<const float4*>(sc.nodes);
-        float4* dst = reinterpret_cast<float4*>(s_nodes);
-        for (uint32_t i = threadIdx.x; i < sc.smem_nodes * 4u; i += blockDim.x) dst[i] = __ldg(src + i);
-        __syncthreads();
-    }
-    const uint32_t n = c->n_cur;
+__device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __restrict__ c, const QueueSet& q,
+                                             const DNodeHalf* s_nodes, uint32_t* s_stack, uint32_t* s_cursor) {
+    const uint32_t b = blockIdx.x;
+    const uint32_t n = q.count[b];
     const uint32_t lane = lane_id();
+    const size_t off = (size_t)b * q.region_cap;
+    const float4* __restrict__ ray_o = q.ray_o + off;
+    const float4* __restrict__ ray_d = q.ray_d + off;
+    float2* __restrict__ hits = q.hits + off;
     TravCounters cnt{0, 0};
     for (;;) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&c->work_extend, 32u);
+        if (lane == 0) base = atomicAdd(s_cursor, 32u);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= n) break;
         uint32_t i = base + lane;
         if (i < n) {
-            float4 o4 = __ldg(ray_o + i), d4 = __ldg(ray_d + i);
+            float4 o4 = ray_o[i], d4 = ray_d[i];
             float t;
             uint32_t prim;
             closest_hit<COUNT>(sc, s_nodes, xyz(o4), xyz(d4), __float_as_uint(o4.w), s_stack + threadIdx.x, blockDim.x, t,
@@ -129,31 +173,56 @@ __global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DCounters* __restr
         __syncwarp();
     }
     if (COUNT) {
-        uint32_t a = cnt.nodes, b = cnt.prims;
+        uint32_t a = cnt.nodes, p = cnt.prims;
         for (int o = 16; o > 0; o >>= 1) {
             a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
-            b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+            p += __shfl_xor_sync(0xFFFFFFFFu, p, o);
         }
         if (lane == 0) {
             atomicAdd(&c->nodes_visited, (unsigned long long)a);
-            atomicAdd(&c->prims_tested, (unsigned long long)b);
+            atomicAdd(&c->prims_tested, (unsigned long long)p);
         }
     }
 }
 
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DCounters* __restrict__ c, QueueSet q) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    // [smem_nodes * 64 B top-of-tree nodes][stack_entries * blockDim.x * 4 B traversal stacks]
+    DNodeHalf* s_nodes = reinterpret_cast<DNodeHalf*>(smem_raw);
+    uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem_raw + (size_t)sc.smem_nodes * 64u);
+    __shared__ uint32_t s_cursor;
+    if (threadIdx.x == 0) s_cursor = 0;
+    if (sc.smem_nodes) {
+        const float4* src = reinterpret_cast<const float4*>(sc.nodes);
+        float4* dst = reinterpret_cast<float4*>(s_nodes);
+        for (uint32_t i = threadIdx.x; i < sc.smem_nodes * 4u; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    phase_extend<COUNT>(sc, c, q, s_nodes, s_stack, &s_cursor);
+}
+
 // ---------------------------------------------------------------------------------------
-// shade
+// shade: Material::evaluate + Russian roulette + background for stripe b of queue `cur`;
+// survivors are compacted into stripe b of the other queue
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_shade(DScene sc, RenderConst rc, DCounters* __restrict__ c,
-                                                   const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
-                                                   const float4* __restrict__ state, const float2* __restrict__ hits,
-                                                   float4* __restrict__ out_o, float4* __restrict__ out_d,
-                                                   float4* __restrict__ out_state, float4* __restrict__ accum) {
-    const uint32_t n = c->n_cur;
+__device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst& rc, DCounters* __restrict__ c,
+                                            const QueueSet& q, float4* __restrict__ accum, uint32_t* s_cursor,
+                                            uint32_t* s_out) {
+    const uint32_t b = blockIdx.x;
+    const uint32_t n = q.count[b];
     const uint32_t lane = lane_id();
+    const size_t off = (size_t)b * q.region_cap;
+    const float4* __restrict__ ray_o = q.ray_o + off;
+    const float4* __restrict__ ray_d = q.ray_d + off;
+    const float4* __restrict__ state = q.state + off;
+    const float2* __restrict__ hits = q.hits + off;
+    float4* __restrict__ out_o = q.out_o + off;
+    float4* __restrict__ out_d = q.out_d + off;
+    float4* __restrict__ out_state = q.out_state + off;
     for (;;) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&c->work_shade, 32u);
+        if (lane == 0) base = atomicAdd(s_cursor, 32u);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= n) break;
         uint32_t i = base + lane;
@@ -207,11 +276,11 @@ __global__ void __launch_bounds__(kBlock) k_shade(DScene sc, RenderConst rc, DCo
                 if (finished) atomicAdd(accum + pixel, make_float4(0.f, 0.f, 0.f, 1.f));
             }
         }
-        // queue compaction: survivors of this warp take consecutive slots
+        // queue compaction: survivors of this warp take consecutive slots of the stripe
         uint32_t ballot = __ballot_sync(0xFFFFFFFFu, alive);
         if (ballot) {
             uint32_t obase = 0;
-            if (lane == 0) obase = atomicAdd(&c->n_next, __popc(ballot));
+            if (lane == 0) obase = atomicAdd(s_out, __popc(ballot));
             obase = __shfl_sync(0xFFFFFFFFu, obase, 0);
             if (alive) {
                 uint32_t slot = obase + __popc(ballot & ((1u << lane) - 1u));
@@ -221,6 +290,24 @@ __global__ void __launch_bounds__(kBlock) k_shade(DScene sc, RenderConst rc, DCo
             }
         }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t survivors = *s_out;
+        q.out_count[b] = survivors;
+        if (n) atomicAdd(&c->rays, (unsigned long long)n);
+        if (survivors) atomicAdd(&c->n_next, survivors);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock, 8) k_shade(DScene sc, RenderConst rc, DCounters* __restrict__ c, QueueSet q,
+                                                      float4* __restrict__ accum) {
+    __shared__ uint32_t s_cursor, s_out;
+    if (threadIdx.x == 0) {
+        s_cursor = 0;
+        s_out = 0;
+    }
+    __syncthreads();
+    phase_shade(sc, rc, c, q, accum, &s_cursor, &s_out);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -310,33 +397,40 @@ static size_t extend_smem_bytes(const DScene& d) {
     return (size_t)d.smem_nodes * 64u + (size_t)d.stack_entries * kBlock * sizeof(uint32_t);
 }
 
-static int ensure_wavefront(SceneImpl* s, uint32_t capacity, std::string& err) {
-    Wavefront& w = s->wf;
-    if (w.capacity == capacity && w.counters) return RRS_OK;
+static void free_queues(Wavefront& w) {
     for (int k = 0; k < 2; ++k) {
-        cudaFree(w.ray_o[k]); cudaFree(w.ray_d[k]); cudaFree(w.state[k]);
+        cudaFree(w.ray_o[k]); cudaFree(w.ray_d[k]); cudaFree(w.state[k]); cudaFree(w.count[k]);
         w.ray_o[k] = w.ray_d[k] = w.state[k] = nullptr;
+        w.count[k] = nullptr;
     }
     cudaFree(w.hits);
     w.hits = nullptr;
+    w.capacity = 0;
+}
+
+static int ensure_wavefront(SceneImpl* s, uint32_t regions, uint32_t region_cap, std::string& err) {
+    Wavefront& w = s->wf;
+    if (w.regions == regions && w.region_cap == region_cap && w.capacity && w.counters) return RRS_OK;
+    free_queues(w);
+    const size_t cap = (size_t)regions * region_cap;
     for (int k = 0; k < 2; ++k) {
-        RRS_CUDA_CHECK(cudaMalloc(&w.ray_o[k], sizeof(float4) * (size_t)capacity), err);
-        RRS_CUDA_CHECK(cudaMalloc(&w.ray_d[k], sizeof(float4) * (size_t)capacity), err);
-        RRS_CUDA_CHECK(cudaMalloc(&w.state[k], sizeof(float4) * (size_t)capacity), err);
+        RRS_CUDA_CHECK(cudaMalloc(&w.ray_o[k], sizeof(float4) * cap), err);
+        RRS_CUDA_CHECK(cudaMalloc(&w.ray_d[k], sizeof(float4) * cap), err);
+        RRS_CUDA_CHECK(cudaMalloc(&w.state[k], sizeof(float4) * cap), err);
+        RRS_CUDA_CHECK(cudaMalloc(&w.count[k], sizeof(uint32_t) * regions), err);
     }
-    RRS_CUDA_CHECK(cudaMalloc(&w.hits, sizeof(float2) * (size_t)capacity), err);
+    RRS_CUDA_CHECK(cudaMalloc(&w.hits, sizeof(float2) * cap), err);
     if (!w.counters) RRS_CUDA_CHECK(cudaMalloc(&w.counters, sizeof(DCounters)), err);
     if (!w.h_counters) RRS_CUDA_CHECK(cudaMallocHost(&w.h_counters, sizeof(DCounters)), err);
-    w.capacity = capacity;
+    w.capacity = (uint32_t)cap;
+    w.regions = regions;
+    w.region_cap = region_cap;
     return RRS_OK;
 }
 
 void wf_free(SceneImpl* s) {
     Wavefront& w = s->wf;
-    for (int k = 0; k < 2; ++k) {
-        cudaFree(w.ray_o[k]); cudaFree(w.ray_d[k]); cudaFree(w.state[k]);
-    }
-    cudaFree(w.hits);
+    free_queues(w);
     cudaFree(w.counters);
     if (w.h_counters) cudaFreeHost(w.h_counters);
     for (auto e : s->ev_pool) cudaEventDestroy(e);
@@ -370,11 +464,40 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     if ((unsigned long long)p->sample_offset + p->spp > (1ull << 24)) { err = "sample index exceeds 2^24"; return RRS_ERR_INVALID; }
     if ((unsigned long long)p->width * p->height > 0xFFFFFFFFull) { err = "image too large"; return RRS_ERR_INVALID; }
     RRS_CUDA_CHECK(cudaSetDevice(s->device), err);
-    uint32_t capacity = p->queue_capacity ? p->queue_capacity : (1u << 22);
-    capacity = std::max(capacity, 1024u) & ~31u;
-    int rc_ = ensure_wavefront(s, capacity, err);
+    // ---- launch geometry: every kernel runs `regions` blocks, block b owns queue stripe b ----
+    const bool count = (p->flags & RRS_FLAG_COUNT_TRAVERSAL) != 0;
+    const bool phases = (p->flags & RRS_FLAG_TIME_PHASES) != 0;
+    const bool exact_tiles = (p->width % 8u == 0) && (p->height % 4u == 0);
+    size_t smem = extend_smem_bytes(s->d);
+    auto extend_fn = count ? k_extend<true> : k_extend<false>;
+    auto generate_fn = exact_tiles ? k_generate<true> : k_generate<false>;
+    RRS_CUDA_CHECK(cudaFuncSetAttribute(extend_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err);
+    int occ_ext = 0, occ_shade = 0;
+    RRS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ext, extend_fn, kBlock, smem), err);
+    RRS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_shade, k_shade, kBlock, 0), err);
+    if (occ_ext < 1 || occ_shade < 1) { err = "kernel does not fit on an SM (traversal stack too deep)"; return RRS_ERR_TOO_DEEP; }
+    // one wave of the most register-hungry kernel: all stripes are resident at once
+    const uint32_t regions = (uint32_t)s->num_sms * (uint32_t)std::min(occ_ext, occ_shade);
+    uint32_t want = p->queue_capacity ? p->queue_capacity : (1u << 22);
+    uint32_t region_cap = std::max(32u, ((want + regions - 1) / regions + 31u) & ~31u);
+    int rc_ = ensure_wavefront(s, regions, region_cap, err);
     if (rc_ != RRS_OK) return rc_;
     Wavefront& w = s->wf;
+    RRS_CUDA_CHECK(cudaMemsetAsync(w.count[0], 0, sizeof(uint32_t) * regions, stream), err);
+    RRS_CUDA_CHECK(cudaMemsetAsync(w.count[1], 0, sizeof(uint32_t) * regions, stream), err);
+    QueueSet qs[2];
+    for (int k = 0; k < 2; ++k) {
+        qs[k].ray_o = w.ray_o[k];
+        qs[k].ray_d = w.ray_d[k];
+        qs[k].state = w.state[k];
+        qs[k].count = w.count[k];
+        qs[k].out_o = w.ray_o[k ^ 1];
+        qs[k].out_d = w.ray_d[k ^ 1];
+        qs[k].out_state = w.state[k ^ 1];
+        qs[k].out_count = w.count[k ^ 1];
+        qs[k].hits = w.hits;
+        qs[k].region_cap = region_cap;
+    }
 
     RenderConst rc;
     rc.cam = make_camera(cam, p->width, p->height);
@@ -391,19 +514,6 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     if (p->max_bounces == 0) init.total_paths = 0;  // radiance() with 0 bounces returns black
     *w.h_counters = init;
     RRS_CUDA_CHECK(cudaMemcpyAsync(w.counters, w.h_counters, sizeof(DCounters), cudaMemcpyHostToDevice, stream), err);
-
-    const bool count = (p->flags & RRS_FLAG_COUNT_TRAVERSAL) != 0;
-    const bool phases = (p->flags & RRS_FLAG_TIME_PHASES) != 0;
-    size_t smem = extend_smem_bytes(s->d);
-    auto extend_fn = count ? k_extend<true> : k_extend<false>;
-    RRS_CUDA_CHECK(cudaFuncSetAttribute(extend_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err);
-    int occ_ext = 0, occ_shade = 0, occ_gen = 0;
-    RRS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ext, extend_fn, kBlock, smem), err);
-    RRS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_shade, k_shade, kBlock, 0), err);
-    RRS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gen, k_generate, kBlock, 0), err);
-    if (occ_ext < 1) { err = "extend kernel does not fit on an SM (traversal stack too deep)"; return RRS_ERR_TOO_DEEP; }
-    const int grid_ext = s->num_sms * occ_ext, grid_shade = s->num_sms * std::max(1, occ_shade),
-              grid_gen = s->num_sms * std::max(1, occ_gen);
 
     // event pool: [0]=start [1]=stop, then 5 per iteration when phase timing is on
     auto get_event = [&](size_t idx) -> cudaEvent_t {
@@ -434,14 +544,13 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
                 phase_ev.push_back(e0);
                 cudaEventRecord(s->ev_pool[e0], stream);
             }
-            k_plan<<<1, 32, 0, stream>>>(w.counters, capacity);
+            k_plan<<<1, 32, 0, stream>>>(w.counters);
             if (phases) cudaEventRecord(s->ev_pool[e0 + 1], stream);
-            k_generate<<<grid_gen, kBlock, 0, stream>>>(rc, w.counters, w.ray_o[cur], w.ray_d[cur], w.state[cur]);
+            generate_fn<<<regions, kBlock, 0, stream>>>(rc, w.counters, qs[cur]);
             if (phases) cudaEventRecord(s->ev_pool[e0 + 2], stream);
-            extend_fn<<<grid_ext, kBlock, smem, stream>>>(s->d, w.counters, w.ray_o[cur], w.ray_d[cur], w.hits);
+            extend_fn<<<regions, kBlock, smem, stream>>>(s->d, w.counters, qs[cur]);
             if (phases) cudaEventRecord(s->ev_pool[e0 + 3], stream);
-            k_shade<<<grid_shade, kBlock, 0, stream>>>(s->d, rc, w.counters, w.ray_o[cur], w.ray_d[cur], w.state[cur], w.hits,
-                                                        w.ray_o[nxt], w.ray_d[nxt], w.state[nxt], d_accum);
+            k_shade<<<regions, kBlock, 0, stream>>>(s->d, rc, w.counters, qs[cur], d_accum);
             if (phases) cudaEventRecord(s->ev_pool[e0 + 4], stream);
             launches += 4;
             cur = nxt;
@@ -485,22 +594,36 @@ int wf_resolve(SceneImpl* s, const float4* d_accum, uint32_t w, uint32_t h, uint
                bool out_is_device, cudaStream_t stream, std::string& err) {
     if (!d_accum || !out || spp_total == 0) { err = "bad resolve argument"; return RRS_ERR_INVALID; }
     RRS_CUDA_CHECK(cudaSetDevice(s->device), err);
-    uint32_t npix = w * h;
-    if (!s->census) RRS_CUDA_CHECK(cudaMalloc(&s->census, 2 * sizeof(unsigned long long)), err);
+    const uint32_t npix = w * h;
+    const size_t bytes = sizeof(float) * 3 * (size_t)npix;
+    if (!s->census) {
+        RRS_CUDA_CHECK(cudaMalloc(&s->census, 2 * sizeof(unsigned long long)), err);
+        RRS_CUDA_CHECK(cudaMallocHost(&s->h_census, 2 * sizeof(unsigned long long)), err);
+    }
     RRS_CUDA_CHECK(cudaMemsetAsync(s->census, 0, 2 * sizeof(unsigned long long), stream), err);
     float* d_out = out;
-    if (!out_is_device) RRS_CUDA_CHECK(cudaMalloc(&d_out, sizeof(float) * 3 * (size_t)npix), err);
+    if (!out_is_device) {
+        // persistent device image + pinned staging buffer: the host copy is one async D2H
+        if (s->resolve_bytes < bytes) {
+            cudaFree(s->resolve_dev);
+            if (s->resolve_pinned) cudaFreeHost(s->resolve_pinned);
+            s->resolve_dev = nullptr;
+            s->resolve_pinned = nullptr;
+            s->resolve_bytes = 0;
+            RRS_CUDA_CHECK(cudaMalloc(&s->resolve_dev, bytes), err);
+            RRS_CUDA_CHECK(cudaMallocHost(&s->resolve_pinned, bytes), err);
+            s->resolve_bytes = bytes;
+        }
+        d_out = s->resolve_dev;
+    }
     int grid = std::min<uint32_t>((npix + 255) / 256, (uint32_t)s->num_sms * 8u);
     k_resolve<<<grid, 256, 0, stream>>>(d_accum, d_out, npix, 1.0f / (float)spp_total, s->census);
-    unsigned long long cs[2] = {0, 0};
-    if (!out_is_device) {
-        RRS_CUDA_CHECK(cudaMemcpyAsync(out, d_out, sizeof(float) * 3 * (size_t)npix, cudaMemcpyDeviceToHost, stream), err);
-    }
-    RRS_CUDA_CHECK(cudaMemcpyAsync(cs, s->census, sizeof(cs), cudaMemcpyDeviceToHost, stream), err);
+    if (!out_is_device) RRS_CUDA_CHECK(cudaMemcpyAsync(s->resolve_pinned, d_out, bytes, cudaMemcpyDeviceToHost, stream), err);
+    RRS_CUDA_CHECK(cudaMemcpyAsync(s->h_census, s->census, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), err);
     RRS_CUDA_CHECK(cudaStreamSynchronize(stream), err);
-    if (!out_is_device) cudaFree(d_out);
-    s->stats.nan_pixels = cs[0];
-    s->stats.negative_pixels = cs[1];
+    if (!out_is_device) std::memcpy(out, s->resolve_pinned, bytes);
+    s->stats.nan_pixels = s->h_census[0];
+    s->stats.negative_pixels = s->h_census[1];
     s->stats.kernel_launches += 1;
     return RRS_OK;
 }

@@ -24,8 +24,7 @@ struct DCounters {
     unsigned long long paths;        // primary rays generated so far
     unsigned long long nodes_visited, prims_tested;
     unsigned long long iterations;
-    uint32_t work_extend, work_shade;  // dynamic work cursors of the persistent kernels
-    uint32_t pad[2];
+    uint32_t pad[4];
 };
 
 struct RenderConst {
@@ -37,7 +36,10 @@ struct RenderConst {
 };
 
 struct Wavefront {
-    uint32_t capacity = 0;
+    uint32_t capacity = 0;     // regions * region_cap
+    uint32_t regions = 0;      // stripes == grid size of the persistent kernels
+    uint32_t region_cap = 0;   // slots per stripe (multiple of 32)
+    uint32_t* count[2] = {nullptr, nullptr};  // rays per stripe
     float4* ray_o[2] = {nullptr, nullptr};  // origin xyz, origin primitive
     float4* ray_d[2] = {nullptr, nullptr};  // direction xyz, pixel
     float4* state[2] = {nullptr, nullptr};  // throughput rgb, sample << 8 | bounce
@@ -66,6 +68,10 @@ struct SceneImpl {
     float4* accum = nullptr;  // private accumulation buffer of rrs_render
     size_t accum_pixels = 0;
     unsigned long long* census = nullptr;  // [nan, negative]
+    unsigned long long* h_census = nullptr;  // pinned
+    float* resolve_dev = nullptr;     // device RGB image of rrs_render / rrs_resolve(host)
+    float* resolve_pinned = nullptr;  // pinned staging for the device->host copy
+    size_t resolve_bytes = 0;
     std::vector<cudaEvent_t> ev_pool;
 };
 

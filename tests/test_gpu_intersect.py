@@ -95,17 +95,24 @@ def test_fp32_matches_fp64_at_full_size_1m_triangles(hdri_small):
     gid, gt = sc.intersect(rays, 32)
     did, dt = sc.intersect(rays, 64)
     agree = gid == did
-    # edges of 1M tiny triangles: a few rays per 10^4 land within fp32 noise of an edge
+    # edges of 1M tiny triangles: a few rays per 10^4 land within fp32 noise of an edge and pick the
+    # neighbouring triangle (benign: same surface, same distance)
     assert agree.mean() > 0.999
     hit = agree & (did >= 0)
     assert hit.mean() > 0.3
     rel = np.abs(gt[hit] - dt[hit]) / dt[hit]
     assert np.quantile(rel, 0.9999) <= 1e-5
-    # where they disagree the two answers are neighbouring surfaces at (almost) the same distance
-    dis = (~agree) & (gid >= 0) & (did >= 0)
-    if dis.any():
-        assert np.max(np.abs(gt[dis] - dt[dis]) / dt[dis]) < 1e-2
-    print(f"[torus 1M] fp32 == fp64 ids on {agree.mean() * 100:.4f}% of {n} rays; p99.99 rel t err {np.quantile(rel, 0.9999):.2e}")
+    # where they disagree it must be the neighbouring triangle at (almost) the same distance; a
+    # different SURFACE (a ray leaking through a crack between triangles, or a silhouette graze)
+    # must be vanishingly rare: the watertight edge test leaves only silhouette grazes
+    dis = ~agree
+    both = dis & (gid >= 0) & (did >= 0)
+    far = np.zeros(n, dtype=bool)
+    far[both] = np.abs(gt[both] - dt[both]) / dt[both] > 1e-3
+    far |= dis & ((gid < 0) != (did < 0))
+    print(f"[torus 1M] fp32 == fp64 ids on {agree.mean() * 100:.4f}% of {n} rays; {int(dis.sum())} differ, of which "
+          f"{int(far.sum())} land on a different surface; p99.99 rel t err {np.quantile(rel, 0.9999):.2e}")
+    assert far.sum() <= 3e-5 * n, int(far.sum())
     # oracle spot check of the fp64 kernel on a subset (the oracle walks the pointer tree unpruned)
     osc = oracle.OracleScene(spec.tables(), hdri_small.pixels, build_mode=1)
     sub = rays[: 1 << 14]

@@ -125,12 +125,13 @@ class OracleScene:
 
     def render(self, cam17, W, H, spp, max_bounces=50, seed=0x5EEDB200, sample_offset=0, rng_mode=RNG_MATCHED, nthreads=0):
         out = np.zeros((H, W, 3), dtype=np.float64)
-        stats = np.zeros(5, dtype=np.uint64)
+        stats = np.zeros(7, dtype=np.uint64)
         c = _d(cam17)
         lib().orc_render(self._p, c.ctypes.data, W, H, spp, sample_offset, max_bounces, seed, rng_mode,
                          nthreads or hardware_threads(), out.ctypes.data, stats.ctypes.data)
         return out, dict(rays=int(stats[0]), scatters=int(stats[1]), nan_pixels=int(stats[2]),
-                         negative_pixels=int(stats[3]), seconds=float(stats[4]) * 1e-6)
+                         negative_pixels=int(stats[3]), seconds=float(stats[4]) * 1e-6,
+                         reentry_total=int(stats[5]), reentry_lost=int(stats[6]))
 
     def background(self, dirs):
         d = _d(dirs).reshape(-1, 3)

@@ -907,16 +907,30 @@ struct PathStats {
     uint64_t scatters = 0;
     uint64_t nan_pixels = 0;
     uint64_t neg_pixels = 0;
+    // diagnostics of the sphere re-entry quirk: rays spawned ON a sphere that point
+    // into it, and how many of them lose the far-side hit because the near root came out >= 0
+    uint64_t reentry_total = 0;
+    uint64_t reentry_lost = 0;
 };
 
 // radiance lib.rs:521-560
 static V3 radiance(const Scene& s, Ray r, uint32_t max_bounces, Rng& rng, PathStats& st) {
     V3 throughput = v3(1., 1., 1.);
     V3 light = v3(0., 0., 0.);
+    const Object* origin_obj = nullptr;
     for (uint32_t b = 0; b < max_bounces; ++b) {
         st.rays++;
         Hit h = tree_intersect(s.bvh.get(), r, s.tmin, s.tmax);
+        if (origin_obj) {  // diagnostics only (does not influence the result)
+            const Sphere* sp = dynamic_cast<const Sphere*>(origin_obj->geom.get());
+            if (sp && dot(r.d, r.o - sp->origin) < 0.) {
+                double ts;
+                st.reentry_total++;
+                if (!(sp->intersect(r, ts) && ts > s.tmin)) st.reentry_lost++;
+            }
+        }
         if (h.hit) {
+            origin_obj = h.obj;
             V3 position = r.point(h.t);
             V3 normal = h.obj->geom->normal(position);
             V3 view = unit(-1. * r.d);
@@ -1137,7 +1151,7 @@ void orc_primary_rays(const double* cam17, uint32_t W, uint32_t H, const uint32_
 }
 
 // The render call being replaced: rayrs/src/main.rs:52-94.  out: H x W x 3 mean radiance.
-// stats_out: [rays, scatters, nan_pixels, negative_pixels, seconds*1e6]
+// stats_out: [rays, scatters, nan_pixels, negative_pixels, seconds*1e6, reentry_total, reentry_lost]
 void orc_render(const OrcScene* h, const double* cam17, uint32_t W, uint32_t H, uint32_t spp,
                 uint32_t sample_offset, uint32_t max_bounces, uint64_t seed, int rng_mode, int nthreads,
                 double* out, uint64_t* stats_out) {
@@ -1184,12 +1198,15 @@ void orc_render(const OrcScene* h, const double* cam17, uint32_t W, uint32_t H, 
         for (auto& st : stats) {
             tot.rays += st.rays; tot.scatters += st.scatters;
             tot.nan_pixels += st.nan_pixels; tot.neg_pixels += st.neg_pixels;
+            tot.reentry_total += st.reentry_total; tot.reentry_lost += st.reentry_lost;
         }
         stats_out[0] = tot.rays;
         stats_out[1] = tot.scatters;
         stats_out[2] = tot.nan_pixels;
         stats_out[3] = tot.neg_pixels;
         stats_out[4] = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+        stats_out[5] = tot.reentry_total;
+        stats_out[6] = tot.reentry_lost;
     }
 }
 

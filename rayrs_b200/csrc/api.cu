@@ -137,6 +137,8 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
 
     // --- fp32 records ---------------------------------------------------------------------
     std::vector<DPrim> hp(desc->n_prims);
+    std::vector<double4> hs64;  // exact sphere parameters (see "sphere re-entry" in intersect.cuh)
+    bool transmissive_sphere = false;
     for (uint32_t i = 0; i < desc->n_prims; ++i) {
         const RrsPrim& p = desc->prims[i];
         DPrim q;
@@ -153,8 +155,16 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
             q.b = make_float4((float)p.v[3], (float)p.v[4], (float)p.v[5], fobj);
             q.c = make_float4((float)p.v[6], (float)p.v[7], (float)p.v[8], femi);
         } else if (p.type == RRS_SPHERE) {
+            uint32_t sidx = (uint32_t)hs64.size();
+            float fsidx;
+            std::memcpy(&fsidx, &sidx, 4);
+            hs64.push_back(make_double4(p.v[1], p.v[2], p.v[3], p.v[0]));
+            uint32_t tag = desc->materials[p.material].tag;
+            if (tag == RRS_MAT_REFRACT || tag == RRS_MAT_GLASS || tag == RRS_MAT_COOK_TORRANCE_REFRACT ||
+                tag == RRS_MAT_COOK_TORRANCE_GLASS)
+                transmissive_sphere = true;
             q.a = make_float4((float)p.v[1], (float)p.v[2], (float)p.v[3], fmeta);
-            q.b = make_float4((float)p.v[0], 0.f, 0.f, fobj);
+            q.b = make_float4((float)p.v[0], fsidx, 0.f, fobj);
             q.c = make_float4(0.f, 0.f, 0.f, femi);
         } else {
             uint32_t axis = (uint32_t)p.v[0];
@@ -200,6 +210,7 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
     if (rc == RRS_OK) rc = upload(&s.mats, hm.data(), hm.size(), err);
     if (rc == RRS_OK) rc = upload(&s.emis, he.data(), he.size(), err);
     if (rc == RRS_OK) rc = upload(&s.hdri, hh.data(), hh.size(), err);
+    if (rc == RRS_OK && transmissive_sphere) rc = upload(&s.sphere64, hs64.data(), hs64.size(), err);
     if (rc == RRS_OK && desc->nodes_f64) {
         rc = upload(&s.nodes_f64, desc->nodes_f64, desc->n_nodes, err);
         if (rc == RRS_OK) rc = upload(&s.prims_f64, desc->prims, desc->n_prims, err);
@@ -220,6 +231,9 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
     s.d.hdri_h = desc->hdri_height;
     s.d.tmin = (float)desc->t_min;
     s.d.tmax = (float)desc->t_max;
+    s.d.tmin64 = desc->t_min;
+    s.d.tmax64 = desc->t_max;
+    s.d.sphere64 = s.sphere64;
     s.d.stack_entries = std::max<uint32_t>(desc->max_depth + 2, 4);
     s.d.smem_nodes = 0;
     *out = sc;
@@ -232,7 +246,7 @@ void rrs_scene_destroy(RrsScene* scene) {
     cudaSetDevice(s.device);
     wf_free(&s);
     cudaFree(s.prims); cudaFree(s.nodes); cudaFree(s.mats); cudaFree(s.emis); cudaFree(s.hdri);
-    cudaFree(s.prims_f64); cudaFree(s.nodes_f64); cudaFree(s.accum); cudaFree(s.census); cudaFree(s.resolve_dev);
+    cudaFree(s.prims_f64); cudaFree(s.nodes_f64); cudaFree(s.sphere64); cudaFree(s.accum); cudaFree(s.census); cudaFree(s.resolve_dev);
     if (s.resolve_pinned) cudaFreeHost(s.resolve_pinned);
     if (s.h_census) cudaFreeHost(s.h_census);
     delete scene;

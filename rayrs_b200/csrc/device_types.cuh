@@ -13,7 +13,7 @@ namespace rrs {
 // Primitive record, 48 B, three float4 so that it is fetched with 128-bit loads.
 //   meta = type | material << 2          (a.w)
 //   triangle : a = (p1, meta)  b = (p2, obj_id)  c = (p3, emission)
-//   sphere   : a = (centre, meta) b = (r^2, -, -, obj_id) c = (-, -, -, emission)
+//   sphere   : a = (centre, meta) b = (r^2, index into sphere64, -, obj_id) c = (-, -, -, emission)
 //   plane    : a = (pos, umin, umax, meta) b = (vmin, vmax, axis, obj_id) c = (-, -, -, emission)
 struct DPrim {
     float4 a, b, c;
@@ -36,6 +36,9 @@ struct __align__(32) DNodeHalf {
 };
 
 #define RRS_NO_PRIM 0xFFFFFFFFu
+// origin word of a ray: primitive index (28 bits) | RRS_ORG64 when the ray also carries an f64 origin
+#define RRS_ORG64 0x80000000u
+#define RRS_PRIM_MASK 0x0FFFFFFFu
 
 // ---------------------------------------------------------------------------------------
 // float3 helpers (no operator overloading on CUDA's builtin float3 to keep call sites explicit
@@ -104,6 +107,10 @@ struct DScene {
     uint32_t n_prims, n_nodes, n_mats;
     uint32_t hdri_w, hdri_h;
     float tmin, tmax;
+    double tmin64, tmax64;
+    // exact f64 (centre xyz, r^2) of every sphere; non-null only when the scene holds a sphere with a
+    // transmissive material — see "sphere re-entry" in intersect.cuh
+    const double4* sphere64;
     uint32_t stack_entries;  // per-thread traversal stack size (entries)
     uint32_t smem_nodes;     // top-of-tree nodes staged in shared memory (0 = none)
 };

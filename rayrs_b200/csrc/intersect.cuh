@@ -60,6 +60,43 @@ __device__ __forceinline__ bool hit_sphere(float4 a, float4 b, float3 o, float3 
     return true;
 }
 
+// ---------------------------------------------------------------------------------------
+// Sphere re-entry in f64.  A ray spawned ON a sphere and pointing into it (refraction) meets the
+// reference's Sphere::intersect with a near root of ~+-1e-16; `t1 < 0` decides between "far root"
+// and "near root returned, then rejected by the leaf's t > tmin" — i.e. the ray passes straight
+// through the far side.  The sign of that near root is NOT noise: it is dominated by
+// the f64 rounding of constants such as |camera - centre|^2 - r^2 in the intersection that produced
+// the hit point, so the loss probability is a fixed property of the scene (measured in the oracle:
+// 36 % for the sphere at x = 2.2, 81 % at x = +-6.6, 55 % at x = 0 of the seven-sphere scenes) and
+// shows in the converged image.  No fp32 rule reproduces it.  Spheres with a transmissive material
+// therefore get the reference's own arithmetic: hit distance, hit point and the re-entry test are
+// evaluated in f64, operation for operation (no FMA contraction), and the f64 hit point travels
+// with the ray.  Everything else stays fp32.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double dot64(double ax, double ay, double az, double bx, double by, double bz) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(ax, bx), __dmul_rn(ay, by)), __dmul_rn(az, bz));  // vecmath.rs:533-535
+}
+// Sphere::intersect geometry.rs:106-132, literally
+__device__ __forceinline__ bool sphere_intersect64(double4 s, double ox, double oy, double oz, double dx, double dy,
+                                                   double dz, double& t) {
+    double odx = __dsub_rn(ox, s.x), ody = __dsub_rn(oy, s.y), odz = __dsub_rn(oz, s.z);
+    double a = dot64(dx, dy, dz, dx, dy, dz);
+    double b = __dmul_rn(2., dot64(dx, dy, dz, odx, ody, odz));
+    double c = __dsub_rn(dot64(odx, ody, odz, odx, ody, odz), s.w);
+    double desc = __dsub_rn(__dmul_rn(b, b), __dmul_rn(__dmul_rn(4., a), c));
+    if (!(desc > 0.)) return false;
+    double sq = __dsqrt_rn(desc);
+    double t1 = __ddiv_rn(__dsub_rn(-b, sq), __dmul_rn(2., a));
+    double t2 = __ddiv_rn(__dadd_rn(-b, sq), __dmul_rn(2., a));
+    if (t1 < 0.) {
+        if (t2 < 0.) return false;
+        t = t2;
+        return true;
+    }
+    t = t1;
+    return true;
+}
+
 // Plane: a = (pos, umin, umax, meta), b = (vmin, vmax, axis, obj).  Half-open ranges, any
 // sign of t is returned (the leaf filter removes t <= tmin).
 __device__ __forceinline__ bool hit_plane(float4 a, float4 b, float3 o, float3 d, float& t) {
@@ -138,14 +175,18 @@ struct TravCounters {
 // Ordered traversal.  `stack` points at this thread's column of a [entries][blockDim.x]
 // shared-memory array (stride = blockDim.x -> conflict-free).  smem_nodes: first nodes of the
 // array (the top of the tree, breadth-first) staged in shared memory.
-template <bool COUNT>
+template <bool COUNT, bool SPH64>
 __device__ __forceinline__ void closest_hit(const DScene& sc, const DNodeHalf* __restrict__ smem_nodes, float3 o, float3 d,
-                                            uint32_t origin_prim, uint32_t* stack, int stride, float& tbest,
-                                            uint32_t& best, TravCounters& cnt) {
+                                            uint32_t origin_word, const double* __restrict__ org64, uint32_t* stack,
+                                            int stride, float& tbest, uint32_t& best, TravCounters& cnt) {
+    // origin word: RRS_NO_PRIM, or primitive index | RRS_ORG64 (the ray carries its f64 origin in org64)
+    const uint32_t origin_prim = origin_word == RRS_NO_PRIM ? RRS_NO_PRIM : (origin_word & RRS_PRIM_MASK);
+    const bool has64 = SPH64 && origin_word != RRS_NO_PRIM && (origin_word & RRS_ORG64) && org64 != nullptr;
     const float tmin = sc.tmin;
     tbest = sc.tmax;
     best = RRS_NO_PRIM;
     float3 idir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const bool neg_x = idir.x < 0.f, neg_y = idir.y < 0.f, neg_z = idir.z < 0.f;
     const RayShear shear = make_shear(d);
     int sp = 0;
     uint32_t cur = 0;  // virtual root
@@ -166,16 +207,19 @@ __device__ __forceinline__ void closest_hit(const DScene& sc, const DNodeHalf* _
             if (COUNT) cnt.nodes++;
             uint32_t ref0 = __float_as_uint(h1[4]), ref1 = __float_as_uint(h1[5]);
             // child 0: lo = h0[0..2], hi = h0[3..5]; child 1: lo = h0[6],h0[7],h1[0], hi = h1[1..3]
-            float ax0 = (h0[0] - o.x) * idir.x, ax1 = (h0[3] - o.x) * idir.x;
-            float ay0 = (h0[1] - o.y) * idir.y, ay1 = (h0[4] - o.y) * idir.y;
-            float az0 = (h0[2] - o.z) * idir.z, az1 = (h0[5] - o.z) * idir.z;
-            float n0 = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), tmin));
-            float f0 = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), tbest));
-            float bx0 = (h0[6] - o.x) * idir.x, bx1 = (h1[1] - o.x) * idir.x;
-            float by0 = (h0[7] - o.y) * idir.y, by1 = (h1[2] - o.y) * idir.y;
-            float bz0 = (h1[0] - o.z) * idir.z, bz1 = (h1[3] - o.z) * idir.z;
-            float n1 = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), tmin));
-            float f1 = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), tbest));
+            // Slab test as geometry.rs:458-513 writes it: the near/far plane is chosen by the sign of
+            // 1/d (not by min/max of the two products), and max/min drop NaNs — so a ray lying in a
+            // face plane of the box (0 * inf = NaN) is simply not constrained by that axis.
+            float ax0 = ((neg_x ? h0[3] : h0[0]) - o.x) * idir.x, ax1 = ((neg_x ? h0[0] : h0[3]) - o.x) * idir.x;
+            float ay0 = ((neg_y ? h0[4] : h0[1]) - o.y) * idir.y, ay1 = ((neg_y ? h0[1] : h0[4]) - o.y) * idir.y;
+            float az0 = ((neg_z ? h0[5] : h0[2]) - o.z) * idir.z, az1 = ((neg_z ? h0[2] : h0[5]) - o.z) * idir.z;
+            float n0 = fmaxf(fmaxf(ax0, ay0), fmaxf(az0, tmin));
+            float f0 = fminf(fminf(ax1, ay1), fminf(az1, tbest));
+            float bx0 = ((neg_x ? h1[1] : h0[6]) - o.x) * idir.x, bx1 = ((neg_x ? h0[6] : h1[1]) - o.x) * idir.x;
+            float by0 = ((neg_y ? h1[2] : h0[7]) - o.y) * idir.y, by1 = ((neg_y ? h0[7] : h1[2]) - o.y) * idir.y;
+            float bz0 = ((neg_z ? h1[3] : h1[0]) - o.z) * idir.z, bz1 = ((neg_z ? h1[0] : h1[3]) - o.z) * idir.z;
+            float n1 = fmaxf(fmaxf(bx0, by0), fmaxf(bz0, tmin));
+            float f1 = fminf(fminf(bx1, by1), fminf(bz1, tbest));
             // conservative acceptance: fp32 slab arithmetic is good to a few ulp, boxes are
             // rounded outward, so anything the f64 test accepts is accepted here
             bool go0 = (ref0 != RRS_REF_EMPTY) && (n0 <= f0 * 1.000001f);
@@ -214,7 +258,17 @@ __device__ __forceinline__ void closest_hit(const DScene& sc, const DNodeHalf* _
                     float4 c = __ldg(pp + 2);
                     hit = hit_triangle(a, b, c, o, shear, t);
                 } else if (type == RRS_SPHERE) {
-                    hit = hit_sphere(a, b, o, d, pi == origin_prim, t);
+                    if (SPH64 && pi == origin_prim && has64) {
+                        // re-entry: the reference's f64 arithmetic on the f64 hit point, then the
+                        // leaf filter of bvh.rs:404-413 in f64
+                        double t64;
+                        double4 s64 = sc.sphere64[__float_as_uint(b.y)];
+                        hit = sphere_intersect64(s64, org64[0], org64[1], org64[2], (double)d.x, (double)d.y, (double)d.z, t64) &&
+                              t64 > sc.tmin64 && t64 < sc.tmax64;
+                        t = (float)t64;
+                    } else {
+                        hit = hit_sphere(a, b, o, d, pi == origin_prim, t);
+                    }
                 } else {
                     if (pi == origin_prim) continue;
                     hit = hit_plane(a, b, o, d, t);

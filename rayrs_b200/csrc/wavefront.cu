@@ -48,6 +48,8 @@ struct QueueSet {
     float4* out_d;
     float4* out_state;
     uint32_t* out_count;
+    double* org64;      // f64 origins of the current queue (3 per slot) or nullptr
+    double* out_org64;
     uint32_t region_cap;
 };
 
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(kBlock) k_generate(RenderConst rc, DCounters* 
 // ---------------------------------------------------------------------------------------
 // extend: closest hit for every ray of stripe b; warps pull 32-ray batches from a shared cursor
 // ---------------------------------------------------------------------------------------
-template <bool COUNT>
+template <bool COUNT, bool SPH64>
 __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __restrict__ c, const QueueSet& q,
                                              const DNodeHalf* s_nodes, uint32_t* s_stack, uint32_t* s_cursor) {
     const uint32_t b = blockIdx.x;
@@ -166,8 +168,9 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
             float4 o4 = ray_o[i], d4 = ray_d[i];
             float t;
             uint32_t prim;
-            closest_hit<COUNT>(sc, s_nodes, xyz(o4), xyz(d4), __float_as_uint(o4.w), s_stack + threadIdx.x, blockDim.x, t,
-                               prim, cnt);
+            const double* o64 = (SPH64 && q.org64) ? q.org64 + 3 * (off + i) : nullptr;
+            closest_hit<COUNT, SPH64>(sc, s_nodes, xyz(o4), xyz(d4), __float_as_uint(o4.w), o64, s_stack + threadIdx.x, blockDim.x,
+                               t, prim, cnt);
             hits[i] = make_float2(t, __uint_as_float(prim));
         }
         __syncwarp();
@@ -185,7 +188,7 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
     }
 }
 
-template <bool COUNT>
+template <bool COUNT, bool SPH64>
 __global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DCounters* __restrict__ c, QueueSet q) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     // [smem_nodes * 64 B top-of-tree nodes][stack_entries * blockDim.x * 4 B traversal stacks]
@@ -199,13 +202,14 @@ __global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DCounters* __restr
         for (uint32_t i = threadIdx.x; i < sc.smem_nodes * 4u; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     __syncthreads();
-    phase_extend<COUNT>(sc, c, q, s_nodes, s_stack, &s_cursor);
+    phase_extend<COUNT, SPH64>(sc, c, q, s_nodes, s_stack, &s_cursor);
 }
 
 // ---------------------------------------------------------------------------------------
 // shade: Material::evaluate + Russian roulette + background for stripe b of queue `cur`;
 // survivors are compacted into stripe b of the other queue
 // ---------------------------------------------------------------------------------------
+template <bool SPH64>
 __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst& rc, DCounters* __restrict__ c,
                                             const QueueSet& q, float4* __restrict__ accum, uint32_t* s_cursor,
                                             uint32_t* s_out) {
@@ -226,8 +230,9 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= n) break;
         uint32_t i = base + lane;
-        bool alive = false;
+        bool alive = false, carry64 = false;
         float4 no, nd, ns;
+        double p64x = 0., p64y = 0., p64z = 0.;
         if (i < n) {
             float2 h = hits[i];
             float4 o4 = ray_o[i], d4 = ray_d[i], st = state[i];
@@ -244,13 +249,40 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
             } else {
                 const float4* pp = reinterpret_cast<const float4*>(sc.prims + prim);
                 float4 a = __ldg(pp);
-                float3 pos = madd3(d, h.x, o);  // Ray::point lib.rs:41-43
-                float3 nrm = prim_normal(sc.prims, prim, a, pos);
-                float3 view = normalize3(neg3(d));
-                float4 u = rng_uniforms(rc.seed, pixel, sample, bounce + 1u);
                 const float4* mp = reinterpret_cast<const float4*>(sc.mats + prim_material(a));
                 DMat m;
                 m.m0 = __ldg(mp);
+                float3 pos, nrm;
+                const uint32_t mtag = __float_as_uint(m.m0.w);
+                const bool transmissive = mtag == RRS_MAT_REFRACT || mtag == RRS_MAT_GLASS ||
+                                          mtag == RRS_MAT_COOK_TORRANCE_REFRACT || mtag == RRS_MAT_COOK_TORRANCE_GLASS;
+                if (SPH64 && sc.sphere64 != nullptr && prim_type(a) == RRS_SPHERE && transmissive) {
+                    // hit point on a transmissive sphere in the reference's f64 arithmetic
+                    // (intersect.cuh, "sphere re-entry"): Sphere::intersect, Ray::point, Sphere::normal
+                    const uint32_t ow = __float_as_uint(o4.w);
+                    double ox = o.x, oy = o.y, oz = o.z;
+                    if (ow != RRS_NO_PRIM && (ow & RRS_ORG64) && q.org64) {
+                        const double* o64 = q.org64 + 3 * (off + i);
+                        ox = o64[0]; oy = o64[1]; oz = o64[2];
+                    }
+                    double4 s64 = sc.sphere64[__float_as_uint(__ldg(pp + 1).y)];
+                    double t64;
+                    bool ok = sphere_intersect64(s64, ox, oy, oz, (double)d.x, (double)d.y, (double)d.z, t64);
+                    if (!ok || fabs(t64 - (double)h.x) > 1e-3 * (double)h.x) t64 = (double)h.x;  // rim: keep the fp32 root
+                    p64x = __dadd_rn(ox, __dmul_rn((double)d.x, t64));
+                    p64y = __dadd_rn(oy, __dmul_rn((double)d.y, t64));
+                    p64z = __dadd_rn(oz, __dmul_rn((double)d.z, t64));
+                    double nx = __dsub_rn(p64x, s64.x), ny = __dsub_rn(p64y, s64.y), nz = __dsub_rn(p64z, s64.z);
+                    double inv = 1. / sqrt(dot64(nx, ny, nz, nx, ny, nz));
+                    nrm = f3((float)(nx * inv), (float)(ny * inv), (float)(nz * inv));
+                    pos = f3((float)p64x, (float)p64y, (float)p64z);
+                    carry64 = true;
+                } else {
+                    pos = madd3(d, h.x, o);  // Ray::point lib.rs:41-43
+                    nrm = prim_normal(sc.prims, prim, a, pos);
+                }
+                float3 view = normalize3(neg3(d));
+                float4 u = rng_uniforms(rc.seed, pixel, sample, bounce + 1u);
                 m.m1 = __ldg(mp + 1);
                 m.m2 = __ldg(mp + 2);
                 ScatterOut so = material_evaluate(m, nrm, view, u.x, u.y, u.z);
@@ -268,7 +300,7 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
                         thr = f3(thr.x / p, thr.y / p, thr.z / p);
                         finished = false;
                         alive = true;
-                        no = make_float4(pos.x, pos.y, pos.z, __uint_as_float(prim));
+                        no = make_float4(pos.x, pos.y, pos.z, __uint_as_float(carry64 ? (prim | RRS_ORG64) : prim));
                         nd = make_float4(so.dir.x, so.dir.y, so.dir.z, d4.w);
                         ns = make_float4(thr.x, thr.y, thr.z, __uint_as_float((sample << 8) | (bounce + 1u)));
                     }
@@ -287,6 +319,10 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
                 out_o[slot] = no;
                 out_d[slot] = nd;
                 out_state[slot] = ns;
+                if (SPH64 && carry64 && q.out_org64) {
+                    double* o64 = q.out_org64 + 3 * (off + slot);
+                    o64[0] = p64x; o64[1] = p64y; o64[2] = p64z;
+                }
             }
         }
     }
@@ -299,15 +335,16 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
     }
 }
 
-__global__ void __launch_bounds__(kBlock, 8) k_shade(DScene sc, RenderConst rc, DCounters* __restrict__ c, QueueSet q,
-                                                      float4* __restrict__ accum) {
+template <bool SPH64>
+__global__ void __launch_bounds__(kBlock, SPH64 ? 6 : 8) k_shade(DScene sc, RenderConst rc, DCounters* __restrict__ c,
+                                                                  QueueSet q, float4* __restrict__ accum) {
     __shared__ uint32_t s_cursor, s_out;
     if (threadIdx.x == 0) {
         s_cursor = 0;
         s_out = 0;
     }
     __syncthreads();
-    phase_shade(sc, rc, c, q, accum, &s_cursor, &s_out);
+    phase_shade<SPH64>(sc, rc, c, q, accum, &s_cursor, &s_out);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -354,7 +391,7 @@ __global__ void __launch_bounds__(kBlock) k_intersect32(DScene sc, const float4*
         float4 o4 = ray_o[i], d4 = ray_d[i];
         float t;
         uint32_t prim;
-        closest_hit<false>(sc, s_nodes, xyz(o4), xyz(d4), RRS_NO_PRIM, s_stack + threadIdx.x, blockDim.x, t, prim, cnt);
+        closest_hit<false, false>(sc, s_nodes, xyz(o4), xyz(d4), RRS_NO_PRIM, nullptr, s_stack + threadIdx.x, blockDim.x, t, prim, cnt);
         if (prim == RRS_NO_PRIM) {
             obj_id[i] = -1;
             t_out[i] = INFINITY;
@@ -399,9 +436,10 @@ static size_t extend_smem_bytes(const DScene& d) {
 
 static void free_queues(Wavefront& w) {
     for (int k = 0; k < 2; ++k) {
-        cudaFree(w.ray_o[k]); cudaFree(w.ray_d[k]); cudaFree(w.state[k]); cudaFree(w.count[k]);
+        cudaFree(w.ray_o[k]); cudaFree(w.ray_d[k]); cudaFree(w.state[k]); cudaFree(w.count[k]); cudaFree(w.org64[k]);
         w.ray_o[k] = w.ray_d[k] = w.state[k] = nullptr;
         w.count[k] = nullptr;
+        w.org64[k] = nullptr;
     }
     cudaFree(w.hits);
     w.hits = nullptr;
@@ -418,6 +456,7 @@ static int ensure_wavefront(SceneImpl* s, uint32_t regions, uint32_t region_cap,
         RRS_CUDA_CHECK(cudaMalloc(&w.ray_d[k], sizeof(float4) * cap), err);
         RRS_CUDA_CHECK(cudaMalloc(&w.state[k], sizeof(float4) * cap), err);
         RRS_CUDA_CHECK(cudaMalloc(&w.count[k], sizeof(uint32_t) * regions), err);
+        if (s->sphere64) RRS_CUDA_CHECK(cudaMalloc(&w.org64[k], sizeof(double) * 3 * cap), err);
     }
     RRS_CUDA_CHECK(cudaMalloc(&w.hits, sizeof(float2) * cap), err);
     if (!w.counters) RRS_CUDA_CHECK(cudaMalloc(&w.counters, sizeof(DCounters)), err);
@@ -469,12 +508,14 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     const bool phases = (p->flags & RRS_FLAG_TIME_PHASES) != 0;
     const bool exact_tiles = (p->width % 8u == 0) && (p->height % 4u == 0);
     size_t smem = extend_smem_bytes(s->d);
-    auto extend_fn = count ? k_extend<true> : k_extend<false>;
+    const bool sph64 = s->sphere64 != nullptr;
+    auto extend_fn = sph64 ? (count ? k_extend<true, true> : k_extend<false, true>) : (count ? k_extend<true, false> : k_extend<false, false>);
+    auto shade_fn = sph64 ? k_shade<true> : k_shade<false>;
     auto generate_fn = exact_tiles ? k_generate<true> : k_generate<false>;
     RRS_CUDA_CHECK(cudaFuncSetAttribute(extend_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err);
     int occ_ext = 0, occ_shade = 0;
     RRS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ext, extend_fn, kBlock, smem), err);
-    RRS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_shade, k_shade, kBlock, 0), err);
+    RRS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_shade, shade_fn, kBlock, 0), err);
     if (occ_ext < 1 || occ_shade < 1) { err = "kernel does not fit on an SM (traversal stack too deep)"; return RRS_ERR_TOO_DEEP; }
     // one wave of the most register-hungry kernel: all stripes are resident at once
     const uint32_t regions = (uint32_t)s->num_sms * (uint32_t)std::min(occ_ext, occ_shade);
@@ -495,6 +536,8 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
         qs[k].out_d = w.ray_d[k ^ 1];
         qs[k].out_state = w.state[k ^ 1];
         qs[k].out_count = w.count[k ^ 1];
+        qs[k].org64 = w.org64[k];
+        qs[k].out_org64 = w.org64[k ^ 1];
         qs[k].hits = w.hits;
         qs[k].region_cap = region_cap;
     }
@@ -550,7 +593,7 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
             if (phases) cudaEventRecord(s->ev_pool[e0 + 2], stream);
             extend_fn<<<regions, kBlock, smem, stream>>>(s->d, w.counters, qs[cur]);
             if (phases) cudaEventRecord(s->ev_pool[e0 + 3], stream);
-            k_shade<<<regions, kBlock, 0, stream>>>(s->d, rc, w.counters, qs[cur], d_accum);
+            shade_fn<<<regions, kBlock, 0, stream>>>(s->d, rc, w.counters, qs[cur], d_accum);
             if (phases) cudaEventRecord(s->ev_pool[e0 + 4], stream);
             launches += 4;
             cur = nxt;

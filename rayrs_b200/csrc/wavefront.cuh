@@ -44,6 +44,7 @@ struct Wavefront {
     float4* ray_d[2] = {nullptr, nullptr};  // direction xyz, pixel
     float4* state[2] = {nullptr, nullptr};  // throughput rgb, sample << 8 | bounce
     float2* hits = nullptr;                 // t, primitive
+    double* org64[2] = {nullptr, nullptr};  // f64 hit points of rays spawned on transmissive spheres (3 per slot)
     DCounters* counters = nullptr;
     DCounters* h_counters = nullptr;  // pinned
 };
@@ -60,6 +61,7 @@ struct SceneImpl {
     float4* hdri = nullptr;
     RrsPrim* prims_f64 = nullptr;
     RrsNodeF64* nodes_f64 = nullptr;
+    double4* sphere64 = nullptr;
     uint32_t n_prims = 0, n_nodes = 0;
     uint32_t max_depth = 0;
     double tmin = 0, tmax = 0;

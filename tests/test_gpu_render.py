@@ -155,9 +155,13 @@ def test_shapes_queues_and_limits(hdri_small):
     # invalid arguments fail loudly with a status, not a crash
     with pytest.raises(api._ffi.RayrsError):
         api.render_gpu(cam, sc, 4, 300)
-    bad = scenes.cook_torrance_spheres_plastic(40, 19).camera()
-    with pytest.raises(api._ffi.RayrsError):
-        api.render_gpu(bad, sc, 4, 50, out=np.empty((19, 37, 3), dtype=np.float32))
+    # render size that disagrees with Camera::x_pixels/y_pixels (straight through the C ABI)
+    import ctypes as C
+    p = api.render_params(cam, 4, 50)
+    p.width = 40
+    buf = np.empty((19, 40, 3), dtype=np.float32)
+    rc = api._ffi.cuda_lib().rrs_render(sc.handle, C.byref(cam.c), C.byref(p), buf.ctypes.data)
+    assert rc == api._ffi.RRS_ERR_INVALID and b"x_pixels" in api._ffi.cuda_lib().rrs_last_error()
     sc.close()
 
 

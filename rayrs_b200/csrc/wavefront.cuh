@@ -29,6 +29,7 @@ struct DCounters {
 
 struct RenderConst {
     DCamera cam;
+    RrsCamera cam64;  // the f64 camera, for the f64 sphere path (primary directions as lib.rs:202-210 computes them)
     uint32_t tiles_x, tiles_y;
     unsigned long long npix_pad;  // tiles_x * tiles_y * 32
     uint32_t spp, sample_offset, max_bounces;

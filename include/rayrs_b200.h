@@ -193,7 +193,9 @@ typedef struct RrsStats {
 } RrsStats;
 
 #define RRS_FLAG_COUNT_TRAVERSAL 1u /* count nodes/primitives touched (slower; for the bytes/ray model) */
-#define RRS_FLAG_TIME_PHASES 2u     /* CUDA-event time every phase separately (adds syncs-free events) */
+#define RRS_FLAG_TIME_PHASES 2u     /* split kernels only: CUDA-event time every phase launch */
+#define RRS_FLAG_SPLIT_KERNELS 4u   /* one generate/extend/shade launch per wavefront iteration instead of the
+                                       single fused persistent kernel (per-phase profiling) */
 
 typedef struct RrsScene RrsScene;
 

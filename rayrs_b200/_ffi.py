@@ -19,6 +19,7 @@ RRS_REF_LEAF = 0x80000000
 RRS_REF_EMPTY = 0xFFFFFFFF
 RRS_FLAG_COUNT_TRAVERSAL = 1
 RRS_FLAG_TIME_PHASES = 2
+RRS_FLAG_SPLIT_KERNELS = 4
 
 
 class RrsPrim(C.Structure):

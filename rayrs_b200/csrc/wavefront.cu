@@ -37,19 +37,17 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 // k_shade's stall samples on the shuffle behind those two same-address atomics
 // (profiles/r01a_c2_globalqueue_stalls.txt).
 // ---------------------------------------------------------------------------------------
-// One direction of the ping-pong, resolved on the host (no dynamic indexing of kernel parameters).
+// Both halves of the ping-pong live in ONE allocation per array (half k at offset k * capacity), so a
+// kernel selects its half with one integer instead of a second set of pointers.
 struct QueueSet {
-    float4* ray_o;      // current queue: origin xyz, origin primitive
-    float4* ray_d;      //                direction xyz, pixel
-    float4* state;      //                throughput rgb, sample << 8 | bounce
-    float2* hits;       //                t, primitive
-    uint32_t* count;    // rays per stripe of the current queue
-    float4* out_o;      // the other queue (survivors of shade)
-    float4* out_d;
-    float4* out_state;
-    uint32_t* out_count;
-    double* org64;      // f64 origins of the current queue (3 per slot) or nullptr
-    double* out_org64;
+    float4* ray_o;     // [2][capacity] origin xyz, origin primitive
+    float4* ray_d;     // [2][capacity] direction xyz, pixel
+    float4* state;     // [2][capacity] throughput rgb, sample << 8 | bounce
+    float2* hits;      // [capacity]    t, primitive
+    uint32_t* count;   // [2][regions]  rays per stripe
+    double* org64;     // [2][capacity][3] f64 origins (transmissive spheres) or nullptr
+    uint32_t capacity;  // regions * region_cap
+    uint32_t regions;
     uint32_t region_cap;
 };
 
@@ -69,10 +67,11 @@ __global__ void k_plan(DCounters* c) {
 // generate: refill stripe b behind its survivors with new primary rays
 // ---------------------------------------------------------------------------------------
 template <bool EXACT_TILES>
-__device__ __forceinline__ void phase_generate(const RenderConst& rc, DCounters* __restrict__ c, const QueueSet& q,
+__device__ __forceinline__ void phase_generate(const RenderConst& rc, DCounters* __restrict__ c, const QueueSet& q, int cur,
                                                uint32_t* s_u32, unsigned long long* s_u64) {
     const uint32_t b = blockIdx.x;
-    const uint32_t n0 = q.count[b];
+    uint32_t* __restrict__ count = q.count + (size_t)cur * q.regions;
+    const uint32_t n0 = count[b];
     if (threadIdx.x == 0) {
         uint32_t need = q.region_cap - n0, got = 0;
         unsigned long long base = 0;
@@ -92,7 +91,7 @@ __device__ __forceinline__ void phase_generate(const RenderConst& rc, DCounters*
     const uint32_t got = s_u32[0];
     const unsigned long long first = s_u64[0];
     const uint32_t lane = lane_id();
-    const size_t off = (size_t)b * q.region_cap;
+    const size_t off = (size_t)cur * q.capacity + (size_t)b * q.region_cap;
     float4* __restrict__ ray_o = q.ray_o + off;
     float4* __restrict__ ray_d = q.ray_d + off;
     float4* __restrict__ state = q.state + off;
@@ -134,29 +133,29 @@ __device__ __forceinline__ void phase_generate(const RenderConst& rc, DCounters*
         state[slot] = make_float4(1.f, 1.f, 1.f, __uint_as_float(sample << 8));
     }
     __syncthreads();
-    if (threadIdx.x == 0) q.count[b] = EXACT_TILES ? n0 + got : s_u32[1];
+    if (threadIdx.x == 0) count[b] = EXACT_TILES ? n0 + got : s_u32[1];
 }
 
 template <bool EXACT_TILES>
-__global__ void __launch_bounds__(kBlock) k_generate(RenderConst rc, DCounters* __restrict__ c, QueueSet q) {
+__global__ void __launch_bounds__(kBlock) k_generate(RenderConst rc, DCounters* __restrict__ c, QueueSet q, int cur) {
     __shared__ uint32_t s_u32[2];
     __shared__ unsigned long long s_u64[1];
-    phase_generate<EXACT_TILES>(rc, c, q, s_u32, s_u64);
+    phase_generate<EXACT_TILES>(rc, c, q, cur, s_u32, s_u64);
 }
 
 // ---------------------------------------------------------------------------------------
 // extend: closest hit for every ray of stripe b; warps pull 32-ray batches from a shared cursor
 // ---------------------------------------------------------------------------------------
 template <bool COUNT, bool SPH64>
-__device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __restrict__ c, const QueueSet& q,
+__device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __restrict__ c, const QueueSet& q, int cur,
                                              const DNodeHalf* s_nodes, uint32_t* s_stack, uint32_t* s_cursor) {
     const uint32_t b = blockIdx.x;
-    const uint32_t n = q.count[b];
+    const uint32_t n = q.count[(size_t)cur * q.regions + b];
     const uint32_t lane = lane_id();
-    const size_t off = (size_t)b * q.region_cap;
+    const size_t roff = (size_t)b * q.region_cap, off = (size_t)cur * q.capacity + roff;
     const float4* __restrict__ ray_o = q.ray_o + off;
     const float4* __restrict__ ray_d = q.ray_d + off;
-    float2* __restrict__ hits = q.hits + off;
+    float2* __restrict__ hits = q.hits + roff;
     TravCounters cnt{0, 0};
     for (;;) {
         uint32_t base = 0;
@@ -189,7 +188,7 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
 }
 
 template <bool COUNT, bool SPH64>
-__global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DCounters* __restrict__ c, QueueSet q) {
+__global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DCounters* __restrict__ c, QueueSet q, int cur) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     // [smem_nodes * 64 B top-of-tree nodes][stack_entries * blockDim.x * 4 B traversal stacks]
     DNodeHalf* s_nodes = reinterpret_cast<DNodeHalf*>(smem_raw);
@@ -202,7 +201,7 @@ __global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DCounters* __restr
         for (uint32_t i = threadIdx.x; i < sc.smem_nodes * 4u; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     __syncthreads();
-    phase_extend<COUNT, SPH64>(sc, c, q, s_nodes, s_stack, &s_cursor);
+    phase_extend<COUNT, SPH64>(sc, c, q, cur, s_nodes, s_stack, &s_cursor);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -211,19 +210,20 @@ __global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DCounters* __restr
 // ---------------------------------------------------------------------------------------
 template <bool SPH64>
 __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst& rc, DCounters* __restrict__ c,
-                                            const QueueSet& q, float4* __restrict__ accum, uint32_t* s_cursor,
+                                            const QueueSet& q, int cur, float4* __restrict__ accum, uint32_t* s_cursor,
                                             uint32_t* s_out) {
     const uint32_t b = blockIdx.x;
-    const uint32_t n = q.count[b];
+    const uint32_t n = q.count[(size_t)cur * q.regions + b];
     const uint32_t lane = lane_id();
-    const size_t off = (size_t)b * q.region_cap;
+    const size_t roff = (size_t)b * q.region_cap;
+    const size_t off = (size_t)cur * q.capacity + roff, ooff = (size_t)(cur ^ 1) * q.capacity + roff;
     const float4* __restrict__ ray_o = q.ray_o + off;
     const float4* __restrict__ ray_d = q.ray_d + off;
     const float4* __restrict__ state = q.state + off;
-    const float2* __restrict__ hits = q.hits + off;
-    float4* __restrict__ out_o = q.out_o + off;
-    float4* __restrict__ out_d = q.out_d + off;
-    float4* __restrict__ out_state = q.out_state + off;
+    const float2* __restrict__ hits = q.hits + roff;
+    float4* __restrict__ out_o = q.ray_o + ooff;
+    float4* __restrict__ out_d = q.ray_d + ooff;
+    float4* __restrict__ out_state = q.state + ooff;
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(s_cursor, 32u);
@@ -336,8 +336,8 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
                 out_o[slot] = no;
                 out_d[slot] = nd;
                 out_state[slot] = ns;
-                if (SPH64 && carry64 && q.out_org64) {
-                    double* o64 = q.out_org64 + 3 * (off + slot);
+                if (SPH64 && carry64 && q.org64) {
+                    double* o64 = q.org64 + 3 * (ooff + slot);
                     o64[0] = p64x; o64[1] = p64y; o64[2] = p64z;
                 }
             }
@@ -346,7 +346,7 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t survivors = *s_out;
-        q.out_count[b] = survivors;
+        q.count[(size_t)(cur ^ 1) * q.regions + b] = survivors;
         if (n) atomicAdd(&c->rays, (unsigned long long)n);
         if (survivors) atomicAdd(&c->n_next, survivors);
     }
@@ -354,14 +354,85 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
 
 template <bool SPH64>
 __global__ void __launch_bounds__(kBlock, SPH64 ? 6 : 8) k_shade(DScene sc, RenderConst rc, DCounters* __restrict__ c,
-                                                                  QueueSet q, float4* __restrict__ accum) {
+                                                                  QueueSet q, int cur, float4* __restrict__ accum) {
     __shared__ uint32_t s_cursor, s_out;
     if (threadIdx.x == 0) {
         s_cursor = 0;
         s_out = 0;
     }
     __syncthreads();
-    phase_shade<SPH64>(sc, rc, c, q, accum, &s_cursor, &s_out);
+    phase_shade<SPH64>(sc, rc, c, q, cur, accum, &s_cursor, &s_out);
+}
+
+// ---------------------------------------------------------------------------------------
+// fused persistent kernel: because block b only ever touches stripe b, the three phases need no
+// grid-wide ordering at all — every block runs its OWN generate -> extend -> shade loop until the
+// global path cursor is exhausted and its stripe has drained.  One launch per render: no launch
+// gaps, no per-kernel tails, no host polling; a stripe that was just written by shade is re-read
+// by the same SM while it is still in L2.  The three-kernel form above is kept (RRS_FLAG_SPLIT_KERNELS)
+// because it gives per-phase ncu evidence.
+// ---------------------------------------------------------------------------------------
+template <bool EXACT_TILES, bool COUNT, bool SPH64>
+__device__ __forceinline__ bool wavefront_iteration(const DScene& sc, const RenderConst& rc, DCounters* __restrict__ c,
+                                                    const QueueSet& q, int cur, float4* __restrict__ accum,
+                                                    const DNodeHalf* s_nodes, uint32_t* s_stack, uint32_t* s_u32,
+                                                    unsigned long long* s_u64) {
+    // s_u64[1..3]: cycles spent in generate / extend / shade, s_u64[4]: iterations (thread 0 only)
+    long long t0 = 0;
+    if (threadIdx.x == 0) t0 = clock64();
+    phase_generate<EXACT_TILES>(rc, c, q, cur, s_u32, s_u64);
+    __syncthreads();
+    const uint32_t n = q.count[(size_t)cur * q.regions + blockIdx.x];
+    if (threadIdx.x == 0) {
+        s_u32[2] = 0;  // work cursor
+        s_u32[3] = 0;  // append cursor of the compaction
+        long long t1 = clock64();
+        s_u64[1] += (unsigned long long)(t1 - t0);
+        t0 = t1;
+    }
+    __syncthreads();
+    if (n == 0) return false;  // nothing live and no path left for this block
+    phase_extend<COUNT, SPH64>(sc, c, q, cur, s_nodes, s_stack, &s_u32[2]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_u32[2] = 0;
+        long long t1 = clock64();
+        s_u64[2] += (unsigned long long)(t1 - t0);
+        t0 = t1;
+    }
+    __syncthreads();
+    phase_shade<SPH64>(sc, rc, c, q, cur, accum, &s_u32[2], &s_u32[3]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_u64[3] += (unsigned long long)(clock64() - t0);
+        s_u64[4] += 1;
+    }
+    return true;
+}
+
+template <bool EXACT_TILES, bool COUNT, bool SPH64>
+__global__ void __launch_bounds__(kBlock, SPH64 ? 6 : 8) k_wavefront(DScene sc, RenderConst rc, DCounters* __restrict__ c,
+                                                                      QueueSet q, float4* __restrict__ accum) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    DNodeHalf* s_nodes = reinterpret_cast<DNodeHalf*>(smem_raw);
+    uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem_raw + (size_t)sc.smem_nodes * 64u);
+    __shared__ uint32_t s_u32[4];
+    __shared__ unsigned long long s_u64[5];
+    if (threadIdx.x < 5) s_u64[threadIdx.x] = 0;
+    if (sc.smem_nodes) {
+        const float4* src = reinterpret_cast<const float4*>(sc.nodes);
+        float4* dst = reinterpret_cast<float4*>(s_nodes);
+        for (uint32_t i = threadIdx.x; i < sc.smem_nodes * 4u; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    for (int cur = 0;; cur ^= 1)
+        if (!wavefront_iteration<EXACT_TILES, COUNT, SPH64>(sc, rc, c, q, cur, accum, s_nodes, s_stack, s_u32, s_u64)) break;
+    if (threadIdx.x == 0) {
+        atomicMax(&c->iterations, s_u64[4]);
+        atomicAdd(&c->cyc_generate, s_u64[1]);
+        atomicAdd(&c->cyc_extend, s_u64[2]);
+        atomicAdd(&c->cyc_shade, s_u64[3]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -452,13 +523,10 @@ static size_t extend_smem_bytes(const DScene& d) {
 }
 
 static void free_queues(Wavefront& w) {
-    for (int k = 0; k < 2; ++k) {
-        cudaFree(w.ray_o[k]); cudaFree(w.ray_d[k]); cudaFree(w.state[k]); cudaFree(w.count[k]); cudaFree(w.org64[k]);
-        w.ray_o[k] = w.ray_d[k] = w.state[k] = nullptr;
-        w.count[k] = nullptr;
-        w.org64[k] = nullptr;
-    }
-    cudaFree(w.hits);
+    cudaFree(w.ray_o); cudaFree(w.ray_d); cudaFree(w.state); cudaFree(w.count); cudaFree(w.org64); cudaFree(w.hits);
+    w.ray_o = w.ray_d = w.state = nullptr;
+    w.count = nullptr;
+    w.org64 = nullptr;
     w.hits = nullptr;
     w.capacity = 0;
 }
@@ -468,13 +536,11 @@ static int ensure_wavefront(SceneImpl* s, uint32_t regions, uint32_t region_cap,
     if (w.regions == regions && w.region_cap == region_cap && w.capacity && w.counters) return RRS_OK;
     free_queues(w);
     const size_t cap = (size_t)regions * region_cap;
-    for (int k = 0; k < 2; ++k) {
-        RRS_CUDA_CHECK(cudaMalloc(&w.ray_o[k], sizeof(float4) * cap), err);
-        RRS_CUDA_CHECK(cudaMalloc(&w.ray_d[k], sizeof(float4) * cap), err);
-        RRS_CUDA_CHECK(cudaMalloc(&w.state[k], sizeof(float4) * cap), err);
-        RRS_CUDA_CHECK(cudaMalloc(&w.count[k], sizeof(uint32_t) * regions), err);
-        if (s->sphere64) RRS_CUDA_CHECK(cudaMalloc(&w.org64[k], sizeof(double) * 3 * cap), err);
-    }
+    RRS_CUDA_CHECK(cudaMalloc(&w.ray_o, sizeof(float4) * 2 * cap), err);
+    RRS_CUDA_CHECK(cudaMalloc(&w.ray_d, sizeof(float4) * 2 * cap), err);
+    RRS_CUDA_CHECK(cudaMalloc(&w.state, sizeof(float4) * 2 * cap), err);
+    RRS_CUDA_CHECK(cudaMalloc(&w.count, sizeof(uint32_t) * 2 * regions), err);
+    if (s->sphere64) RRS_CUDA_CHECK(cudaMalloc(&w.org64, sizeof(double) * 3 * 2 * cap), err);
     RRS_CUDA_CHECK(cudaMalloc(&w.hits, sizeof(float2) * cap), err);
     if (!w.counters) RRS_CUDA_CHECK(cudaMalloc(&w.counters, sizeof(DCounters)), err);
     if (!w.h_counters) RRS_CUDA_CHECK(cudaMallocHost(&w.h_counters, sizeof(DCounters)), err);
@@ -528,12 +594,26 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     const bool sph64 = s->sphere64 != nullptr;
     auto extend_fn = sph64 ? (count ? k_extend<true, true> : k_extend<false, true>) : (count ? k_extend<true, false> : k_extend<false, false>);
     auto shade_fn = sph64 ? k_shade<true> : k_shade<false>;
+    typedef void (*FusedFn)(DScene, RenderConst, DCounters*, QueueSet, float4*);
+    FusedFn fused_fn;
+    {
+        const int sel = (exact_tiles ? 4 : 0) | (count ? 2 : 0) | (sph64 ? 1 : 0);
+        static const FusedFn table[8] = {k_wavefront<false, false, false>, k_wavefront<false, false, true>,
+                                         k_wavefront<false, true, false>,  k_wavefront<false, true, true>,
+                                         k_wavefront<true, false, false>,  k_wavefront<true, false, true>,
+                                         k_wavefront<true, true, false>,   k_wavefront<true, true, true>};
+        fused_fn = table[sel];
+    }
+    RRS_CUDA_CHECK(cudaFuncSetAttribute(fused_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err);
     auto generate_fn = exact_tiles ? k_generate<true> : k_generate<false>;
     RRS_CUDA_CHECK(cudaFuncSetAttribute(extend_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err);
     int occ_ext = 0, occ_shade = 0;
     RRS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ext, extend_fn, kBlock, smem), err);
     RRS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_shade, shade_fn, kBlock, 0), err);
-    if (occ_ext < 1 || occ_shade < 1) { err = "kernel does not fit on an SM (traversal stack too deep)"; return RRS_ERR_TOO_DEEP; }
+    int occ_fused = 0;
+    RRS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_fused, fused_fn, kBlock, smem), err);
+    if (occ_ext < 1 || occ_shade < 1 || occ_fused < 1) { err = "kernel does not fit on an SM (traversal stack too deep)"; return RRS_ERR_TOO_DEEP; }
+    if (!(p->flags & RRS_FLAG_SPLIT_KERNELS)) occ_ext = occ_shade = occ_fused;
     // one wave of the most register-hungry kernel: all stripes are resident at once
     const uint32_t regions = (uint32_t)s->num_sms * (uint32_t)std::min(occ_ext, occ_shade);
     uint32_t want = p->queue_capacity ? p->queue_capacity : (1u << 22);
@@ -541,23 +621,17 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     int rc_ = ensure_wavefront(s, regions, region_cap, err);
     if (rc_ != RRS_OK) return rc_;
     Wavefront& w = s->wf;
-    RRS_CUDA_CHECK(cudaMemsetAsync(w.count[0], 0, sizeof(uint32_t) * regions, stream), err);
-    RRS_CUDA_CHECK(cudaMemsetAsync(w.count[1], 0, sizeof(uint32_t) * regions, stream), err);
-    QueueSet qs[2];
-    for (int k = 0; k < 2; ++k) {
-        qs[k].ray_o = w.ray_o[k];
-        qs[k].ray_d = w.ray_d[k];
-        qs[k].state = w.state[k];
-        qs[k].count = w.count[k];
-        qs[k].out_o = w.ray_o[k ^ 1];
-        qs[k].out_d = w.ray_d[k ^ 1];
-        qs[k].out_state = w.state[k ^ 1];
-        qs[k].out_count = w.count[k ^ 1];
-        qs[k].org64 = w.org64[k];
-        qs[k].out_org64 = w.org64[k ^ 1];
-        qs[k].hits = w.hits;
-        qs[k].region_cap = region_cap;
-    }
+    RRS_CUDA_CHECK(cudaMemsetAsync(w.count, 0, sizeof(uint32_t) * 2 * regions, stream), err);
+    QueueSet q;
+    q.ray_o = w.ray_o;
+    q.ray_d = w.ray_d;
+    q.state = w.state;
+    q.hits = w.hits;
+    q.count = w.count;
+    q.org64 = w.org64;
+    q.capacity = w.capacity;
+    q.regions = regions;
+    q.region_cap = region_cap;
 
     RenderConst rc;
     rc.cam = make_camera(cam, p->width, p->height);
@@ -589,37 +663,47 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     RRS_CUDA_CHECK(cudaEventRecord(ev_start, stream), err);
 
     uint64_t launches = 0, iters = 0;
-    int cur = 0;
-    const uint32_t chunk = 8;
-    size_t ev_next = 2;
     std::vector<size_t> phase_ev;  // indices of per-iteration event groups
-    bool done = false;
-    while (!done) {
-        for (uint32_t k = 0; k < chunk; ++k) {
-            int nxt = cur ^ 1;
-            size_t e0 = 0;
-            if (phases) {
-                e0 = ev_next;
-                ev_next += 5;
-                get_event(e0 + 4);
-                phase_ev.push_back(e0);
-                cudaEventRecord(s->ev_pool[e0], stream);
-            }
-            k_plan<<<1, 32, 0, stream>>>(w.counters);
-            if (phases) cudaEventRecord(s->ev_pool[e0 + 1], stream);
-            generate_fn<<<regions, kBlock, 0, stream>>>(rc, w.counters, qs[cur]);
-            if (phases) cudaEventRecord(s->ev_pool[e0 + 2], stream);
-            extend_fn<<<regions, kBlock, smem, stream>>>(s->d, w.counters, qs[cur]);
-            if (phases) cudaEventRecord(s->ev_pool[e0 + 3], stream);
-            shade_fn<<<regions, kBlock, 0, stream>>>(s->d, rc, w.counters, qs[cur], d_accum);
-            if (phases) cudaEventRecord(s->ev_pool[e0 + 4], stream);
-            launches += 4;
-            cur = nxt;
-        }
+    const bool split = (p->flags & RRS_FLAG_SPLIT_KERNELS) != 0;
+    if (!split) {
+        // one persistent launch for the whole render
+        fused_fn<<<regions, kBlock, smem, stream>>>(s->d, rc, w.counters, q, d_accum);
+        launches = 1;
+        RRS_CUDA_CHECK(cudaGetLastError(), err);
         RRS_CUDA_CHECK(cudaMemcpyAsync(w.h_counters, w.counters, sizeof(DCounters), cudaMemcpyDeviceToHost, stream), err);
         RRS_CUDA_CHECK(cudaStreamSynchronize(stream), err);
-        RRS_CUDA_CHECK(cudaGetLastError(), err);
-        done = w.h_counters->done != 0;
+    } else {
+        int cur = 0;
+        const uint32_t chunk = 8;
+        size_t ev_next = 2;
+        bool done = false;
+        while (!done) {
+            for (uint32_t k = 0; k < chunk; ++k) {
+                int nxt = cur ^ 1;
+                size_t e0 = 0;
+                if (phases) {
+                    e0 = ev_next;
+                    ev_next += 5;
+                    get_event(e0 + 4);
+                    phase_ev.push_back(e0);
+                    cudaEventRecord(s->ev_pool[e0], stream);
+                }
+                k_plan<<<1, 32, 0, stream>>>(w.counters);
+                if (phases) cudaEventRecord(s->ev_pool[e0 + 1], stream);
+                generate_fn<<<regions, kBlock, 0, stream>>>(rc, w.counters, q, cur);
+                if (phases) cudaEventRecord(s->ev_pool[e0 + 2], stream);
+                extend_fn<<<regions, kBlock, smem, stream>>>(s->d, w.counters, q, cur);
+                if (phases) cudaEventRecord(s->ev_pool[e0 + 3], stream);
+                shade_fn<<<regions, kBlock, 0, stream>>>(s->d, rc, w.counters, q, cur, d_accum);
+                if (phases) cudaEventRecord(s->ev_pool[e0 + 4], stream);
+                launches += 4;
+                cur = nxt;
+            }
+            RRS_CUDA_CHECK(cudaMemcpyAsync(w.h_counters, w.counters, sizeof(DCounters), cudaMemcpyDeviceToHost, stream), err);
+            RRS_CUDA_CHECK(cudaStreamSynchronize(stream), err);
+            RRS_CUDA_CHECK(cudaGetLastError(), err);
+            done = w.h_counters->done != 0;
+        }
     }
     RRS_CUDA_CHECK(cudaEventRecord(ev_stop, stream), err);
     RRS_CUDA_CHECK(cudaEventSynchronize(ev_stop), err);
@@ -635,7 +719,16 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     st.nodes_visited = w.h_counters->nodes_visited;
     st.prims_tested = w.h_counters->prims_tested;
     st.generate_ms = st.extend_ms = st.shade_ms = 0.;
-    if (phases) {
+    if (!split) {
+        // per-phase share of the fused kernel from its in-kernel cycle counters (summed over blocks)
+        double cg = (double)w.h_counters->cyc_generate, ce = (double)w.h_counters->cyc_extend, cs = (double)w.h_counters->cyc_shade;
+        double tot = cg + ce + cs;
+        if (tot > 0) {
+            st.generate_ms = ms * cg / tot;
+            st.extend_ms = ms * ce / tot;
+            st.shade_ms = ms * cs / tot;
+        }
+    } else if (phases) {
         double g = 0, e = 0, sh = 0;
         for (size_t e0 : phase_ev) {
             float a = 0, b = 0, c2 = 0;

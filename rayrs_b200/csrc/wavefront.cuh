@@ -24,7 +24,8 @@ struct DCounters {
     unsigned long long paths;        // primary rays generated so far
     unsigned long long nodes_visited, prims_tested;
     unsigned long long iterations;
-    uint32_t pad[4];
+    unsigned long long cyc_generate, cyc_extend, cyc_shade;  // fused kernel: SM cycles per phase, summed over blocks
+    uint32_t pad[2];
 };
 
 struct RenderConst {
@@ -40,12 +41,13 @@ struct Wavefront {
     uint32_t capacity = 0;     // regions * region_cap
     uint32_t regions = 0;      // stripes == grid size of the persistent kernels
     uint32_t region_cap = 0;   // slots per stripe (multiple of 32)
-    uint32_t* count[2] = {nullptr, nullptr};  // rays per stripe
-    float4* ray_o[2] = {nullptr, nullptr};  // origin xyz, origin primitive
-    float4* ray_d[2] = {nullptr, nullptr};  // direction xyz, pixel
-    float4* state[2] = {nullptr, nullptr};  // throughput rgb, sample << 8 | bounce
-    float2* hits = nullptr;                 // t, primitive
-    double* org64[2] = {nullptr, nullptr};  // f64 hit points of rays spawned on transmissive spheres (3 per slot)
+    // both halves of the ping-pong in one allocation each: half k at offset k * capacity
+    uint32_t* count = nullptr;  // [2][regions] rays per stripe
+    float4* ray_o = nullptr;    // [2][capacity] origin xyz, origin primitive
+    float4* ray_d = nullptr;    // [2][capacity] direction xyz, pixel
+    float4* state = nullptr;    // [2][capacity] throughput rgb, sample << 8 | bounce
+    float2* hits = nullptr;     // [capacity]    t, primitive
+    double* org64 = nullptr;    // [2][capacity][3] f64 hit points of rays spawned on transmissive spheres
     DCounters* counters = nullptr;
     DCounters* h_counters = nullptr;  // pinned
 };

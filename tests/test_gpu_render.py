@@ -133,10 +133,12 @@ def test_shapes_queues_and_limits(hdri_small):
     assert relrmse(base, ref) < 5e-3
     rays0 = sc.stats()["rays"]
     for q in (1024, 4096, 1 << 16):
-        img = api.render_gpu(cam, sc, 40, 50, queue_capacity=q).astype(np.float64)
-        st = sc.stats()
-        assert st["rays"] == rays0                      # the set of paths does not depend on queue size
-        assert np.allclose(img, base, rtol=2e-5, atol=1e-6)  # only the fp32 summation order differs
+        for flags in (0, api._ffi.RRS_FLAG_SPLIT_KERNELS, api._ffi.RRS_FLAG_SPLIT_KERNELS | api._ffi.RRS_FLAG_TIME_PHASES):
+            img = api.render_gpu(cam, sc, 40, 50, queue_capacity=q, flags=flags).astype(np.float64)
+            st = sc.stats()
+            assert st["rays"] == rays0                      # the set of paths does not depend on queue size / kernel form
+            assert np.allclose(img, base, rtol=2e-5, atol=1e-6)  # only the fp32 summation order differs
+            assert st["kernel_launches"] == (2 if flags == 0 else st["kernel_launches"])  # fused: 1 render + 1 resolve
     # depth limits: max_bounces = 1 traces exactly one ray per path; 0 renders black (lib.rs:525,559)
     for mb in (1, 2, 3):
         img = api.render_gpu(cam, sc, 8, mb).astype(np.float64)

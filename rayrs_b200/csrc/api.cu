@@ -1,5 +1,7 @@
 // C ABI of the backend (include/rayrs_b200.h): scene validation, fp32 conversion, upload,
 // and the thin entry points over wavefront.cu / verify_f64.cu.
+#include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -110,7 +112,7 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
             }
         }
     }
-    if (desc->max_depth + 2 > 120) return fail(RRS_ERR_TOO_DEEP, "BVH deeper than the 118-entry shared-memory traversal stack");
+    if (desc->max_depth + 3 > 120) return fail(RRS_ERR_TOO_DEEP, "BVH deeper than the 117-entry shared-memory traversal stack");
 
     // --- device ---------------------------------------------------------------------------
     int ndev = 0;
@@ -138,7 +140,7 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
     // --- fp32 records ---------------------------------------------------------------------
     std::vector<DPrim> hp(desc->n_prims);
     std::vector<double4> hs64;  // exact sphere parameters (see "sphere re-entry" in intersect.cuh)
-    bool transmissive_sphere = false;
+    bool transmissive_sphere = false, has_triangles = false;
     for (uint32_t i = 0; i < desc->n_prims; ++i) {
         const RrsPrim& p = desc->prims[i];
         DPrim q;
@@ -149,6 +151,7 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
         std::memcpy(&fobj, &p.obj_id, 4);
         std::memcpy(&femi, &emi, 4);
         if (p.type == RRS_TRIANGLE) {
+            has_triangles = true;
             // the three vertices (shared vertices of a mesh must stay bit-identical across triangles
             // for the watertight test, so no per-triangle edge vectors are stored)
             q.a = make_float4((float)p.v[0], (float)p.v[1], (float)p.v[2], fmeta);
@@ -206,7 +209,18 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
     static_assert(sizeof(RrsNode) == 64, "RrsNode must be 64 bytes");
     static_assert(sizeof(RrsNodeF64) == 128, "RrsNodeF64 must be 128 bytes");
     if (rc == RRS_OK) rc = upload(&s.prims, hp.data(), hp.size(), err);
-    if (rc == RRS_OK) rc = upload(reinterpret_cast<RrsNode**>(&s.nodes), desc->nodes, desc->n_nodes, err);
+    {
+        // an RRS_REF_EMPTY child must fail the slab test by itself (the traversal does not look at the
+        // reference before testing the box): give it the inverted infinite box whatever the caller stored
+        std::vector<RrsNode> hn(desc->nodes, desc->nodes + desc->n_nodes);
+        for (RrsNode& nd : hn) {
+            for (int k = 0; k < 3; ++k) {
+                if (nd.ref0 == RRS_REF_EMPTY) { nd.lo0[k] = INFINITY; nd.hi0[k] = -INFINITY; }
+                if (nd.ref1 == RRS_REF_EMPTY) { nd.lo1[k] = INFINITY; nd.hi1[k] = -INFINITY; }
+            }
+        }
+        if (rc == RRS_OK) rc = upload(reinterpret_cast<RrsNode**>(&s.nodes), hn.data(), hn.size(), err);
+    }
     if (rc == RRS_OK) rc = upload(&s.mats, hm.data(), hm.size(), err);
     if (rc == RRS_OK) rc = upload(&s.emis, he.data(), he.size(), err);
     if (rc == RRS_OK) rc = upload(&s.hdri, hh.data(), hh.size(), err);
@@ -234,8 +248,11 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
     s.d.tmin64 = desc->t_min;
     s.d.tmax64 = desc->t_max;
     s.d.sphere64 = s.sphere64;
-    s.d.stack_entries = std::max<uint32_t>(desc->max_depth + 2, 4);
-    s.d.smem_nodes = 0;
+    s.d.stack_entries = std::max<uint32_t>(desc->max_depth + 3, 4);  // + the TRAV_DONE sentinel
+    s.d.has_triangles = has_triangles ? 1u : 0u;
+    // rays of a deep tree differ widely in length: refill early; a tiny scene amortises the fetch over more lanes
+    s.d.refill_lanes = desc->max_depth > 6 ? 4u : 12u;
+    if (const char* e = std::getenv("RRS_REFILL_LANES")) s.d.refill_lanes = std::min(32, std::max(1, std::atoi(e)));
     *out = sc;
     return RRS_OK;
 }

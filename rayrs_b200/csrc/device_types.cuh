@@ -111,8 +111,9 @@ struct DScene {
     // exact f64 (centre xyz, r^2) of every sphere; non-null only when the scene holds a sphere with a
     // transmissive material — see "sphere re-entry" in intersect.cuh
     const double4* sphere64;
-    uint32_t stack_entries;  // per-thread traversal stack size (entries)
-    uint32_t smem_nodes;     // top-of-tree nodes staged in shared memory (0 = none)
+    uint32_t stack_entries;  // per-thread traversal stack size (entries, including the sentinel)
+    uint32_t has_triangles;  // 0: no triangle in the scene (the per-ray shear setup is skipped)
+    uint32_t refill_lanes;   // extend refills a warp with new rays once this many lanes are idle
 };
 
 struct DCamera {

@@ -121,37 +121,45 @@ __device__ __forceinline__ bool hit_plane(float4 a, float4 b, float3 o, float3 d
 // and a ray can miss BOTH triangles of a shared edge (measured: ~1e-4 of rays on the 1M-triangle
 // mesh passed through the surface).  The production test is therefore the watertight edge-function
 // test of Woop, Benthin & Wald (JCGT 2013): vertices are translated to the ray origin and sheared
-// into ray space; the edge function of a shared edge is computed from the SAME two translated
+// into ray space; the edge function of a shared edge is computed from the SAME two projected
 // vertices with exactly negated rounding in both triangles (no FMA contraction), so one of them
 // always accepts.  Same decisions as the reference away from edges, same inclusive edges, two-sided.
-struct RayShear {
-    int kx, ky, kz;
-    float sx, sy, sz;
+//
+// The shear is applied as two dot products with per-ray rows P = e_kx - Sx e_kz, Q = e_ky - Sy e_kz
+// (entries 1, 0 and -S in ray-dependent positions) instead of per-vertex component selects: the
+// projected coordinates of a vertex still depend on that vertex and the ray only — which is all
+// watertightness needs — and the work moves from the ALU pipe (18 selects per triangle, the pipe
+// that limits traversal: profiles/r01c_c4_fused_metrics.csv) to the half-idle FMA pipe.
+struct RayProj {
+    float3 P, Q;
 };
-__device__ __forceinline__ float comp(float3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
-__device__ __forceinline__ RayShear make_shear(float3 d) {
-    RayShear r;
+__device__ __forceinline__ RayProj make_proj(float3 d) {
     float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-    r.kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
-    r.kx = r.kz == 2 ? 0 : r.kz + 1;
-    r.ky = r.kx == 2 ? 0 : r.kx + 1;
-    float dz = comp(d, r.kz);
+    const int kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+    int kx = kz == 2 ? 0 : kz + 1;
+    int ky = kx == 2 ? 0 : kx + 1;
+    const float dz = kz == 0 ? d.x : (kz == 1 ? d.y : d.z);
     if (dz < 0.f) {  // preserve winding
-        int t = r.kx;
-        r.kx = r.ky;
-        r.ky = t;
+        int t = kx;
+        kx = ky;
+        ky = t;
     }
-    r.sz = 1.0f / dz;
-    r.sx = comp(d, r.kx) * r.sz;
-    r.sy = comp(d, r.ky) * r.sz;
+    const float sz = 1.0f / dz;
+    const float sx = (kx == 0 ? d.x : (kx == 1 ? d.y : d.z)) * sz;
+    const float sy = (ky == 0 ? d.x : (ky == 1 ? d.y : d.z)) * sz;
+    RayProj r;
+    r.P = f3(kx == 0 ? 1.f : (kz == 0 ? -sx : 0.f), kx == 1 ? 1.f : (kz == 1 ? -sx : 0.f), kx == 2 ? 1.f : (kz == 2 ? -sx : 0.f));
+    r.Q = f3(ky == 0 ? 1.f : (kz == 0 ? -sy : 0.f), ky == 1 ? 1.f : (kz == 1 ? -sy : 0.f), ky == 2 ? 1.f : (kz == 2 ? -sy : 0.f));
     return r;
 }
-__device__ __forceinline__ bool hit_triangle(float4 a, float4 b, float4 c, float3 o, const RayShear& rs, float& t) {
+__device__ __forceinline__ float proj3(float3 p, float3 v) {  // fixed association: part of the watertightness argument
+    return __fmaf_rn(p.x, v.x, __fmaf_rn(p.y, v.y, __fmul_rn(p.z, v.z)));
+}
+__device__ __forceinline__ bool hit_triangle(float4 a, float4 b, float4 c, float3 o, float3 d, const RayProj& rp, float& t) {
     float3 A = sub3(xyz(a), o), B = sub3(xyz(b), o), C = sub3(xyz(c), o);
-    float Az = comp(A, rs.kz), Bz = comp(B, rs.kz), Cz = comp(C, rs.kz);
-    float Ax = __fmaf_rn(-rs.sx, Az, comp(A, rs.kx)), Ay = __fmaf_rn(-rs.sy, Az, comp(A, rs.ky));
-    float Bx = __fmaf_rn(-rs.sx, Bz, comp(B, rs.kx)), By = __fmaf_rn(-rs.sy, Bz, comp(B, rs.ky));
-    float Cx = __fmaf_rn(-rs.sx, Cz, comp(C, rs.kx)), Cy = __fmaf_rn(-rs.sy, Cz, comp(C, rs.ky));
+    float Ax = proj3(rp.P, A), Ay = proj3(rp.Q, A);
+    float Bx = proj3(rp.P, B), By = proj3(rp.Q, B);
+    float Cx = proj3(rp.P, C), Cy = proj3(rp.Q, C);
     float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
     float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
     float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
@@ -160,11 +168,12 @@ __device__ __forceinline__ bool hit_triangle(float4 a, float4 b, float4 c, float
         V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
         W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
     }
-    if ((U < 0.f || V < 0.f || W < 0.f) && (U > 0.f || V > 0.f || W > 0.f)) return false;
+    if (fminf(fminf(U, V), W) < 0.f && fmaxf(fmaxf(U, V), W) > 0.f) return false;
     float det = U + V + W;
     if (det == 0.f) return false;
-    float T = U * (rs.sz * Az) + V * (rs.sz * Bz) + W * (rs.sz * Cz);
-    t = T / det;
+    // hit point = barycentric mix of the translated vertices; its ray parameter is its projection on d
+    float T = U * dot3(A, d) + V * dot3(B, d) + W * dot3(C, d);
+    t = T / (det * dot3(d, d));
     return true;
 }
 
@@ -172,122 +181,150 @@ struct TravCounters {
     uint32_t nodes, prims;
 };
 
-// Ordered traversal.  `stack` points at this thread's column of a [entries][blockDim.x]
-// shared-memory array (stride = blockDim.x -> conflict-free).  smem_nodes: first nodes of the
-// array (the top of the tree, breadth-first) staged in shared memory.
-template <bool COUNT, bool SPH64>
-__device__ __forceinline__ void closest_hit(const DScene& sc, const DNodeHalf* __restrict__ smem_nodes, float3 o, float3 d,
-                                            uint32_t origin_word, const double* __restrict__ org64, uint32_t* stack,
-                                            int stride, float& tbest, uint32_t& best, TravCounters& cnt) {
+// ---------------------------------------------------------------------------------------
+// Ordered, t-pruned stack traversal, split into steps so that a warp can batch them
+// (phase_extend in wavefront.cu keeps the 32 lanes on the same kind of step and refills idle lanes
+// with new rays).  The per-thread stack is a column of a [entries][blockDim.x] shared-memory array
+// (stride = blockDim.x -> conflict-free); entry 0 holds a TRAV_DONE sentinel so a pop needs no
+// emptiness test.  TRAV_DONE == RRS_REF_EMPTY has the leaf bit set: "is an inner node" is one
+// signed compare.
+// ---------------------------------------------------------------------------------------
+#define TRAV_DONE 0xFFFFFFFFu
+
+struct RayK {
+    float3 o, d, idir;
+    RayProj proj;          // only initialised when the scene holds triangles
+    uint32_t origin_prim;  // primitive the ray was spawned on, RRS_NO_PRIM for camera rays
+    const double* org64;   // f64 origin carried with the ray (transmissive spheres), or nullptr
+};
+struct Trav {
+    uint32_t cur;   // node index, leaf run reference, or TRAV_DONE
+    uint32_t sp;    // stack entries in use (>= 1: the sentinel)
+    float tbest;
+    uint32_t best;
+};
+
+template <bool SPH64>
+__device__ __forceinline__ void trav_begin(const DScene& sc, float3 o, float3 d, uint32_t origin_word,
+                                           const double* __restrict__ org64, uint32_t* stack, RayK& r, Trav& tv) {
     // origin word: RRS_NO_PRIM, or primitive index | RRS_ORG64 (the ray carries its f64 origin in org64)
-    const uint32_t origin_prim = origin_word == RRS_NO_PRIM ? RRS_NO_PRIM : (origin_word & RRS_PRIM_MASK);
-    const bool has64 = SPH64 && origin_word != RRS_NO_PRIM && (origin_word & RRS_ORG64) && org64 != nullptr;
-    const float tmin = sc.tmin;
-    tbest = sc.tmax;
-    best = RRS_NO_PRIM;
-    float3 idir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    r.o = o;
+    r.d = d;
+    r.idir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    r.origin_prim = origin_word == RRS_NO_PRIM ? RRS_NO_PRIM : (origin_word & RRS_PRIM_MASK);
+    r.org64 = (SPH64 && origin_word != RRS_NO_PRIM && (origin_word & RRS_ORG64)) ? org64 : nullptr;
+    if (sc.has_triangles) r.proj = make_proj(d);
+    stack[0] = TRAV_DONE;
+    tv.cur = 0;  // virtual root
+    tv.sp = 1;
+    tv.tbest = sc.tmax;
+    tv.best = RRS_NO_PRIM;
+}
+
+__device__ __forceinline__ bool trav_on_inner(const Trav& tv) { return (int32_t)tv.cur >= 0; }
+
+// One inner node: both child boxes from one 2 x 256-bit fetch, near child first, far child pushed.
+template <bool COUNT>
+__device__ __forceinline__ void trav_node_step(const DScene& sc, const RayK& r, Trav& tv, uint32_t* stack, int stride,
+                                               TravCounters& cnt) {
+    float h0[8], h1[8];
+    ldg256(sc.nodes + 2 * tv.cur, h0);
+    ldg256(sc.nodes + 2 * tv.cur + 1, h1);
+    if (COUNT) cnt.nodes++;
+    const float3 o = r.o, idir = r.idir;
     const bool neg_x = idir.x < 0.f, neg_y = idir.y < 0.f, neg_z = idir.z < 0.f;
-    const RayShear shear = make_shear(d);
-    int sp = 0;
-    uint32_t cur = 0;  // virtual root
-    const uint32_t DONE = 0x7FFFFFFFu;
-    while (cur != DONE) {
-        // ---- inner nodes ----
-        while (!(cur & RRS_REF_LEAF) && cur != DONE) {
-            float h0[8], h1[8];
-            if (cur < sc.smem_nodes) {
-                const float4* s = reinterpret_cast<const float4*>(smem_nodes + 2 * cur);
-                float4 q0 = s[0], q1 = s[1], q2 = s[2], q3 = s[3];
-                h0[0] = q0.x; h0[1] = q0.y; h0[2] = q0.z; h0[3] = q0.w; h0[4] = q1.x; h0[5] = q1.y; h0[6] = q1.z; h0[7] = q1.w;
-                h1[0] = q2.x; h1[1] = q2.y; h1[2] = q2.z; h1[3] = q2.w; h1[4] = q3.x; h1[5] = q3.y; h1[6] = q3.z; h1[7] = q3.w;
+    const uint32_t ref0 = __float_as_uint(h1[4]), ref1 = __float_as_uint(h1[5]);
+    // child 0: lo = h0[0..2], hi = h0[3..5]; child 1: lo = h0[6],h0[7],h1[0], hi = h1[1..3]
+    // Slab test as geometry.rs:458-513 writes it: the near/far plane is chosen by the sign of
+    // 1/d (not by min/max of the two products), and max/min drop NaNs — so a ray lying in a
+    // face plane of the box (0 * inf = NaN) is simply not constrained by that axis.
+    float ax0 = ((neg_x ? h0[3] : h0[0]) - o.x) * idir.x, ax1 = ((neg_x ? h0[0] : h0[3]) - o.x) * idir.x;
+    float ay0 = ((neg_y ? h0[4] : h0[1]) - o.y) * idir.y, ay1 = ((neg_y ? h0[1] : h0[4]) - o.y) * idir.y;
+    float az0 = ((neg_z ? h0[5] : h0[2]) - o.z) * idir.z, az1 = ((neg_z ? h0[2] : h0[5]) - o.z) * idir.z;
+    float n0 = fmaxf(fmaxf(ax0, ay0), fmaxf(az0, sc.tmin));
+    float f0 = fminf(fminf(ax1, ay1), fminf(az1, tv.tbest));
+    float bx0 = ((neg_x ? h1[1] : h0[6]) - o.x) * idir.x, bx1 = ((neg_x ? h0[6] : h1[1]) - o.x) * idir.x;
+    float by0 = ((neg_y ? h1[2] : h0[7]) - o.y) * idir.y, by1 = ((neg_y ? h0[7] : h1[2]) - o.y) * idir.y;
+    float bz0 = ((neg_z ? h1[3] : h1[0]) - o.z) * idir.z, bz1 = ((neg_z ? h1[0] : h1[3]) - o.z) * idir.z;
+    float n1 = fmaxf(fmaxf(bx0, by0), fmaxf(bz0, sc.tmin));
+    float f1 = fminf(fminf(bx1, by1), fminf(bz1, tv.tbest));
+    // conservative acceptance: fp32 slab arithmetic is good to a few ulp, boxes are rounded
+    // outward, so anything the f64 test accepts is accepted here.  An RRS_REF_EMPTY child carries
+    // an inverted infinite box (enforced at scene creation) and fails the test by itself.
+    const bool go0 = n0 <= f0 * 1.000001f;
+    const bool go1 = n1 <= f1 * 1.000001f;
+    if (go0 && go1) {
+        const bool swap = n1 < n0;
+        stack[tv.sp * stride] = swap ? ref0 : ref1;
+        ++tv.sp;
+        tv.cur = swap ? ref1 : ref0;
+    } else if (go0 || go1) {
+        tv.cur = go0 ? ref0 : ref1;
+    } else {
+        --tv.sp;
+        tv.cur = stack[tv.sp * stride];
+    }
+}
+
+// One leaf run (1..4 primitives, DFS order), then pop.
+template <bool COUNT, bool SPH64>
+__device__ __forceinline__ void trav_leaf_step(const DScene& sc, const RayK& r, Trav& tv, uint32_t* stack, int stride,
+                                               TravCounters& cnt) {
+    const uint32_t first = tv.cur & 0x0FFFFFFFu;
+    const uint32_t count = ((tv.cur >> 28) & 7u) + 1u;
+    for (uint32_t k = 0; k < count; ++k) {
+        const uint32_t pi = first + k;
+        const float4* pp = reinterpret_cast<const float4*>(sc.prims + pi);
+        float4 a = __ldg(pp), b = __ldg(pp + 1);
+        const uint32_t type = prim_type(a);
+        float t;
+        bool hit;
+        if (COUNT) cnt.prims++;
+        if (type == RRS_TRIANGLE) {
+            if (pi == r.origin_prim) continue;  // planar primitive cannot re-hit itself
+            float4 c = __ldg(pp + 2);
+            hit = hit_triangle(a, b, c, r.o, r.d, r.proj, t);
+        } else if (type == RRS_SPHERE) {
+            if (SPH64 && pi == r.origin_prim && r.org64 != nullptr) {
+                // re-entry: the reference's f64 arithmetic on the f64 hit point, then the
+                // leaf filter of bvh.rs:404-413 in f64
+                double t64;
+                double4 s64 = sc.sphere64[__float_as_uint(b.y)];
+                hit = sphere_intersect64(s64, r.org64[0], r.org64[1], r.org64[2], (double)r.d.x, (double)r.d.y, (double)r.d.z, t64) &&
+                      t64 > sc.tmin64 && t64 < sc.tmax64;
+                t = (float)t64;
             } else {
-                ldg256(sc.nodes + 2 * cur, h0);
-                ldg256(sc.nodes + 2 * cur + 1, h1);
+                hit = hit_sphere(a, b, r.o, r.d, pi == r.origin_prim, t);
             }
-            if (COUNT) cnt.nodes++;
-            uint32_t ref0 = __float_as_uint(h1[4]), ref1 = __float_as_uint(h1[5]);
-            // child 0: lo = h0[0..2], hi = h0[3..5]; child 1: lo = h0[6],h0[7],h1[0], hi = h1[1..3]
-            // Slab test as geometry.rs:458-513 writes it: the near/far plane is chosen by the sign of
-            // 1/d (not by min/max of the two products), and max/min drop NaNs — so a ray lying in a
-            // face plane of the box (0 * inf = NaN) is simply not constrained by that axis.
-            float ax0 = ((neg_x ? h0[3] : h0[0]) - o.x) * idir.x, ax1 = ((neg_x ? h0[0] : h0[3]) - o.x) * idir.x;
-            float ay0 = ((neg_y ? h0[4] : h0[1]) - o.y) * idir.y, ay1 = ((neg_y ? h0[1] : h0[4]) - o.y) * idir.y;
-            float az0 = ((neg_z ? h0[5] : h0[2]) - o.z) * idir.z, az1 = ((neg_z ? h0[2] : h0[5]) - o.z) * idir.z;
-            float n0 = fmaxf(fmaxf(ax0, ay0), fmaxf(az0, tmin));
-            float f0 = fminf(fminf(ax1, ay1), fminf(az1, tbest));
-            float bx0 = ((neg_x ? h1[1] : h0[6]) - o.x) * idir.x, bx1 = ((neg_x ? h0[6] : h1[1]) - o.x) * idir.x;
-            float by0 = ((neg_y ? h1[2] : h0[7]) - o.y) * idir.y, by1 = ((neg_y ? h0[7] : h1[2]) - o.y) * idir.y;
-            float bz0 = ((neg_z ? h1[3] : h1[0]) - o.z) * idir.z, bz1 = ((neg_z ? h1[0] : h1[3]) - o.z) * idir.z;
-            float n1 = fmaxf(fmaxf(bx0, by0), fmaxf(bz0, tmin));
-            float f1 = fminf(fminf(bx1, by1), fminf(bz1, tbest));
-            // conservative acceptance: fp32 slab arithmetic is good to a few ulp, boxes are
-            // rounded outward, so anything the f64 test accepts is accepted here
-            bool go0 = (ref0 != RRS_REF_EMPTY) && (n0 <= f0 * 1.000001f);
-            bool go1 = (ref1 != RRS_REF_EMPTY) && (n1 <= f1 * 1.000001f);
-            if (go0 && go1) {
-                bool swap = n1 < n0;
-                uint32_t nearr = swap ? ref1 : ref0, farr = swap ? ref0 : ref1;
-                stack[sp * stride] = farr;
-                ++sp;
-                cur = nearr;
-            } else if (go0) {
-                cur = ref0;
-            } else if (go1) {
-                cur = ref1;
-            } else if (sp > 0) {
-                --sp;
-                cur = stack[sp * stride];
-            } else {
-                cur = DONE;
-            }
+        } else {
+            if (pi == r.origin_prim) continue;
+            hit = hit_plane(a, b, r.o, r.d, t);
         }
-        // ---- leaf run (1..4 primitives, DFS order) ----
-        if (cur != DONE) {
-            uint32_t first = cur & 0x0FFFFFFFu;
-            uint32_t count = ((cur >> 28) & 7u) + 1u;
-            for (uint32_t k = 0; k < count; ++k) {
-                uint32_t pi = first + k;
-                const float4* pp = reinterpret_cast<const float4*>(sc.prims + pi);
-                float4 a = __ldg(pp), b = __ldg(pp + 1);
-                uint32_t type = prim_type(a);
-                float t;
-                bool hit;
-                if (COUNT) cnt.prims++;
-                if (type == RRS_TRIANGLE) {
-                    if (pi == origin_prim) continue;  // planar primitive cannot re-hit itself
-                    float4 c = __ldg(pp + 2);
-                    hit = hit_triangle(a, b, c, o, shear, t);
-                } else if (type == RRS_SPHERE) {
-                    if (SPH64 && pi == origin_prim && has64) {
-                        // re-entry: the reference's f64 arithmetic on the f64 hit point, then the
-                        // leaf filter of bvh.rs:404-413 in f64
-                        double t64;
-                        double4 s64 = sc.sphere64[__float_as_uint(b.y)];
-                        hit = sphere_intersect64(s64, org64[0], org64[1], org64[2], (double)d.x, (double)d.y, (double)d.z, t64) &&
-                              t64 > sc.tmin64 && t64 < sc.tmax64;
-                        t = (float)t64;
-                    } else {
-                        hit = hit_sphere(a, b, o, d, pi == origin_prim, t);
-                    }
-                } else {
-                    if (pi == origin_prim) continue;
-                    hit = hit_plane(a, b, o, d, t);
-                }
-                // leaf filter + RayIntersection::update: strictly smaller t wins; equal t keeps
-                // the lower DFS index (ordered traversal may meet them in either order)
-                if (hit && t > tmin && (t < tbest || (t == tbest && best != RRS_NO_PRIM && pi < best))) {
-                    tbest = t;
-                    best = pi;
-                }
-            }
-            if (sp > 0) {
-                --sp;
-                cur = stack[sp * stride];
-            } else {
-                cur = DONE;
-            }
+        // leaf filter + RayIntersection::update: strictly smaller t wins; equal t keeps
+        // the lower DFS index (ordered traversal may meet them in either order)
+        if (hit && t > sc.tmin && (t < tv.tbest || (t == tv.tbest && tv.best != RRS_NO_PRIM && pi < tv.best))) {
+            tv.tbest = t;
+            tv.best = pi;
         }
     }
+    --tv.sp;
+    tv.cur = stack[tv.sp * stride];
+}
+
+// Per-thread traversal to completion (parity probes; the render path batches the steps per warp).
+template <bool COUNT, bool SPH64>
+__device__ __forceinline__ void closest_hit(const DScene& sc, float3 o, float3 d, uint32_t origin_word,
+                                            const double* __restrict__ org64, uint32_t* stack, int stride, float& tbest,
+                                            uint32_t& best, TravCounters& cnt) {
+    RayK r;
+    Trav tv;
+    trav_begin<SPH64>(sc, o, d, origin_word, org64, stack, r, tv);
+    while (tv.cur != TRAV_DONE) {
+        while (trav_on_inner(tv)) trav_node_step<COUNT>(sc, r, tv, stack, stride, cnt);
+        if (tv.cur != TRAV_DONE) trav_leaf_step<COUNT, SPH64>(sc, r, tv, stack, stride, cnt);
+    }
+    tbest = tv.tbest;
+    best = tv.best;
 }
 
 }  // namespace rrs

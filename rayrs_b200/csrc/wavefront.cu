@@ -146,33 +146,73 @@ __global__ void __launch_bounds__(kBlock) k_generate(RenderConst rc, DCounters* 
 // ---------------------------------------------------------------------------------------
 // extend: closest hit for every ray of stripe b; warps pull 32-ray batches from a shared cursor
 // ---------------------------------------------------------------------------------------
+// Warp-batched traversal with dynamic ray fetch.  The loop below is warp-uniform (every decision is
+// a ballot), so the 32 lanes always execute the same kind of step:
+//   refill   lanes without a ray take the next rays of the stripe as soon as `refill_lanes` of them are
+//            idle — a ray that ends after 3 nodes no longer idles its lane while a neighbour walks 60
+//            (the 32-rays-per-warp batch of the first version ran the node loop with 13.4 of 32 lanes
+//            active on the 1M-triangle scene: profiles/r01c_c4_fused_metrics.csv);
+//   nodes    inner-node steps while at least as many lanes want one as are parked on a leaf;
+//   leaf     all parked lanes test their leaf run together, pop, and the cycle repeats.
 template <bool COUNT, bool SPH64>
 __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __restrict__ c, const QueueSet& q, int cur,
-                                             const DNodeHalf* s_nodes, uint32_t* s_stack, uint32_t* s_cursor) {
+                                             uint32_t* s_stack, uint32_t* s_cursor) {
+    const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t b = blockIdx.x;
     const uint32_t n = q.count[(size_t)cur * q.regions + b];
     const uint32_t lane = lane_id();
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const size_t roff = (size_t)b * q.region_cap, off = (size_t)cur * q.capacity + roff;
     const float4* __restrict__ ray_o = q.ray_o + off;
     const float4* __restrict__ ray_d = q.ray_d + off;
     float2* __restrict__ hits = q.hits + roff;
+    uint32_t* stack = s_stack + threadIdx.x;
+    const int stride = blockDim.x;
     TravCounters cnt{0, 0};
+    RayK r;
+    Trav tv;
+    tv.cur = TRAV_DONE;
+    tv.sp = 1;
+    tv.tbest = 0.f;
+    tv.best = RRS_NO_PRIM;
+    bool has_ray = false, exhausted = false;
+    uint32_t my_i = 0;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(s_cursor, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n) break;
-        uint32_t i = base + lane;
-        if (i < n) {
-            float4 o4 = ray_o[i], d4 = ray_d[i];
-            float t;
-            uint32_t prim;
-            const double* o64 = (SPH64 && q.org64) ? q.org64 + 3 * (off + i) : nullptr;
-            closest_hit<COUNT, SPH64>(sc, s_nodes, xyz(o4), xyz(d4), __float_as_uint(o4.w), o64, s_stack + threadIdx.x, blockDim.x,
-                               t, prim, cnt);
-            hits[i] = make_float2(t, __uint_as_float(prim));
+        // ---- refill ----
+        uint32_t idle = __ballot_sync(FULL, !has_ray);
+        if (!exhausted && (uint32_t)__popc(idle) >= sc.refill_lanes) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(s_cursor, (uint32_t)__popc(idle));
+            base = __shfl_sync(FULL, base, 0);
+            exhausted = base + (uint32_t)__popc(idle) >= n;
+            const uint32_t i = base + (uint32_t)__popc(idle & lt_mask);
+            if (!has_ray && i < n) {
+                float4 o4 = ray_o[i], d4 = ray_d[i];
+                const double* o64 = (SPH64 && q.org64) ? q.org64 + 3 * (off + i) : nullptr;
+                trav_begin<SPH64>(sc, xyz(o4), xyz(d4), __float_as_uint(o4.w), o64, stack, r, tv);
+                has_ray = true;
+                my_i = i;
+            }
+            idle = __ballot_sync(FULL, !has_ray);
         }
-        __syncwarp();
+        if (idle == FULL) {
+            if (exhausted) break;
+            continue;  // fewer idle lanes than the threshold cannot be all 32: unreachable, kept for safety
+        }
+        // ---- inner nodes ----
+        for (;;) {
+            const bool inner = trav_on_inner(tv);
+            const uint32_t want = __ballot_sync(FULL, inner);
+            const uint32_t parked = __ballot_sync(FULL, !inner && tv.cur != TRAV_DONE);
+            if (want == 0u || __popc(want) < __popc(parked)) break;
+            if (inner) trav_node_step<COUNT>(sc, r, tv, stack, stride, cnt);
+        }
+        // ---- leaves ----
+        if (!trav_on_inner(tv) && tv.cur != TRAV_DONE) trav_leaf_step<COUNT, SPH64>(sc, r, tv, stack, stride, cnt);
+        if (has_ray && tv.cur == TRAV_DONE) {
+            hits[my_i] = make_float2(tv.tbest, __uint_as_float(tv.best));
+            has_ray = false;
+        }
     }
     if (COUNT) {
         uint32_t a = cnt.nodes, p = cnt.prims;
@@ -189,19 +229,13 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
 
 template <bool COUNT, bool SPH64>
 __global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DCounters* __restrict__ c, QueueSet q, int cur) {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
-    // [smem_nodes * 64 B top-of-tree nodes][stack_entries * blockDim.x * 4 B traversal stacks]
-    DNodeHalf* s_nodes = reinterpret_cast<DNodeHalf*>(smem_raw);
-    uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem_raw + (size_t)sc.smem_nodes * 64u);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // [stack_entries * blockDim.x * 4 B traversal stacks]
+    uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem_raw);
     __shared__ uint32_t s_cursor;
     if (threadIdx.x == 0) s_cursor = 0;
-    if (sc.smem_nodes) {
-        const float4* src = reinterpret_cast<const float4*>(sc.nodes);
-        float4* dst = reinterpret_cast<float4*>(s_nodes);
-        for (uint32_t i = threadIdx.x; i < sc.smem_nodes * 4u; i += blockDim.x) dst[i] = __ldg(src + i);
-    }
     __syncthreads();
-    phase_extend<COUNT, SPH64>(sc, c, q, cur, s_nodes, s_stack, &s_cursor);
+    phase_extend<COUNT, SPH64>(sc, c, q, cur, s_stack, &s_cursor);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -375,8 +409,7 @@ __global__ void __launch_bounds__(kBlock, SPH64 ? 6 : 8) k_shade(DScene sc, Rend
 template <bool EXACT_TILES, bool COUNT, bool SPH64>
 __device__ __forceinline__ bool wavefront_iteration(const DScene& sc, const RenderConst& rc, DCounters* __restrict__ c,
                                                     const QueueSet& q, int cur, float4* __restrict__ accum,
-                                                    const DNodeHalf* s_nodes, uint32_t* s_stack, uint32_t* s_u32,
-                                                    unsigned long long* s_u64) {
+                                                    uint32_t* s_stack, uint32_t* s_u32, unsigned long long* s_u64) {
     // s_u64[1..3]: cycles spent in generate / extend / shade, s_u64[4]: iterations (thread 0 only)
     long long t0 = 0;
     if (threadIdx.x == 0) t0 = clock64();
@@ -392,7 +425,7 @@ __device__ __forceinline__ bool wavefront_iteration(const DScene& sc, const Rend
     }
     __syncthreads();
     if (n == 0) return false;  // nothing live and no path left for this block
-    phase_extend<COUNT, SPH64>(sc, c, q, cur, s_nodes, s_stack, &s_u32[2]);
+    phase_extend<COUNT, SPH64>(sc, c, q, cur, s_stack, &s_u32[2]);
     __syncthreads();
     if (threadIdx.x == 0) {
         s_u32[2] = 0;
@@ -413,20 +446,14 @@ __device__ __forceinline__ bool wavefront_iteration(const DScene& sc, const Rend
 template <bool EXACT_TILES, bool COUNT, bool SPH64>
 __global__ void __launch_bounds__(kBlock, SPH64 ? 6 : 8) k_wavefront(DScene sc, RenderConst rc, DCounters* __restrict__ c,
                                                                       QueueSet q, float4* __restrict__ accum) {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
-    DNodeHalf* s_nodes = reinterpret_cast<DNodeHalf*>(smem_raw);
-    uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem_raw + (size_t)sc.smem_nodes * 64u);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem_raw);
     __shared__ uint32_t s_u32[4];
     __shared__ unsigned long long s_u64[5];
     if (threadIdx.x < 5) s_u64[threadIdx.x] = 0;
-    if (sc.smem_nodes) {
-        const float4* src = reinterpret_cast<const float4*>(sc.nodes);
-        float4* dst = reinterpret_cast<float4*>(s_nodes);
-        for (uint32_t i = threadIdx.x; i < sc.smem_nodes * 4u; i += blockDim.x) dst[i] = __ldg(src + i);
-    }
     __syncthreads();
     for (int cur = 0;; cur ^= 1)
-        if (!wavefront_iteration<EXACT_TILES, COUNT, SPH64>(sc, rc, c, q, cur, accum, s_nodes, s_stack, s_u32, s_u64)) break;
+        if (!wavefront_iteration<EXACT_TILES, COUNT, SPH64>(sc, rc, c, q, cur, accum, s_stack, s_u32, s_u64)) break;
     if (threadIdx.x == 0) {
         atomicMax(&c->iterations, s_u64[4]);
         atomicAdd(&c->cyc_generate, s_u64[1]);
@@ -465,21 +492,14 @@ __global__ void k_resolve(const float4* __restrict__ accum, float* __restrict__ 
 __global__ void __launch_bounds__(kBlock) k_intersect32(DScene sc, const float4* __restrict__ ray_o,
                                                          const float4* __restrict__ ray_d, uint32_t n,
                                                          int32_t* __restrict__ obj_id, float* __restrict__ t_out) {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
-    DNodeHalf* s_nodes = reinterpret_cast<DNodeHalf*>(smem_raw);
-    uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem_raw + (size_t)sc.smem_nodes * 64u);
-    if (sc.smem_nodes) {
-        const float4* src = reinterpret_cast<const float4*>(sc.nodes);
-        float4* dst = reinterpret_cast<float4*>(s_nodes);
-        for (uint32_t i = threadIdx.x; i < sc.smem_nodes * 4u; i += blockDim.x) dst[i] = __ldg(src + i);
-        __syncthreads();
-    }
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem_raw);
     TravCounters cnt{0, 0};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 o4 = ray_o[i], d4 = ray_d[i];
         float t;
         uint32_t prim;
-        closest_hit<false, false>(sc, s_nodes, xyz(o4), xyz(d4), RRS_NO_PRIM, nullptr, s_stack + threadIdx.x, blockDim.x, t, prim, cnt);
+        closest_hit<false, false>(sc, xyz(o4), xyz(d4), RRS_NO_PRIM, nullptr, s_stack + threadIdx.x, blockDim.x, t, prim, cnt);
         if (prim == RRS_NO_PRIM) {
             obj_id[i] = -1;
             t_out[i] = INFINITY;
@@ -519,7 +539,7 @@ __global__ void k_rng_probe(uint64_t seed, uint32_t pixel, uint32_t sample, uint
 // host side
 // ---------------------------------------------------------------------------------------
 static size_t extend_smem_bytes(const DScene& d) {
-    return (size_t)d.smem_nodes * 64u + (size_t)d.stack_entries * kBlock * sizeof(uint32_t);
+    return (size_t)d.stack_entries * kBlock * sizeof(uint32_t);
 }
 
 static void free_queues(Wavefront& w) {

@@ -7,6 +7,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "wavefront.cuh"
 
 using namespace rrs;
@@ -177,6 +179,7 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
             q.b = make_float4((float)p.v[3], (float)p.v[4], faxis, fobj);
             q.c = make_float4(0.f, 0.f, 0.f, femi);
         }
+        q.pad = make_float4(0.f, 0.f, 0.f, 0.f);
         hp[i] = q;
     }
     std::vector<DMat> hm(desc->n_materials);
@@ -210,16 +213,28 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
     static_assert(sizeof(RrsNodeF64) == 128, "RrsNodeF64 must be 128 bytes");
     if (rc == RRS_OK) rc = upload(&s.prims, hp.data(), hp.size(), err);
     {
-        // an RRS_REF_EMPTY child must fail the slab test by itself (the traversal does not look at the
-        // reference before testing the box): give it the inverted infinite box whatever the caller stored
-        std::vector<RrsNode> hn(desc->nodes, desc->nodes + desc->n_nodes);
-        for (RrsNode& nd : hn) {
+        // device nodes: fp16 boxes rounded outward, one half2 (lo, hi) word per axis (device_types.cuh).
+        // An RRS_REF_EMPTY child must fail the slab test by itself (the traversal does not look at the
+        // reference before testing the box): it gets the inverted infinite box whatever the caller stored.
+        auto pack = [](float lo, float hi) -> uint32_t {
+            __half hl = __float2half_rd(lo), hh = __float2half_ru(hi);  // overflow -> +-inf: still conservative
+            uint16_t bl, bh;
+            std::memcpy(&bl, &hl, 2);
+            std::memcpy(&bh, &hh, 2);
+            return (uint32_t)bl | ((uint32_t)bh << 16);
+        };
+        std::vector<DNode16> hn(desc->n_nodes);
+        for (uint32_t i = 0; i < desc->n_nodes; ++i) {
+            const RrsNode& nd = desc->nodes[i];
+            DNode16& q = hn[i];
             for (int k = 0; k < 3; ++k) {
-                if (nd.ref0 == RRS_REF_EMPTY) { nd.lo0[k] = INFINITY; nd.hi0[k] = -INFINITY; }
-                if (nd.ref1 == RRS_REF_EMPTY) { nd.lo1[k] = INFINITY; nd.hi1[k] = -INFINITY; }
+                q.w[k] = nd.ref0 == RRS_REF_EMPTY ? pack(INFINITY, -INFINITY) : pack(nd.lo0[k], nd.hi0[k]);
+                q.w[3 + k] = nd.ref1 == RRS_REF_EMPTY ? pack(INFINITY, -INFINITY) : pack(nd.lo1[k], nd.hi1[k]);
             }
+            q.w[6] = nd.ref0;
+            q.w[7] = nd.ref1;
         }
-        if (rc == RRS_OK) rc = upload(reinterpret_cast<RrsNode**>(&s.nodes), hn.data(), hn.size(), err);
+        if (rc == RRS_OK) rc = upload(&s.nodes, hn.data(), hn.size(), err);
     }
     if (rc == RRS_OK) rc = upload(&s.mats, hm.data(), hm.size(), err);
     if (rc == RRS_OK) rc = upload(&s.emis, he.data(), he.size(), err);
@@ -250,9 +265,17 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
     s.d.sphere64 = s.sphere64;
     s.d.stack_entries = std::max<uint32_t>(desc->max_depth + 3, 4);  // + the TRAV_DONE sentinel
     s.d.has_triangles = has_triangles ? 1u : 0u;
+    {
+        // children of the reference root lie inside its box, so its own slab test (the virtual root's
+        // only job) can be skipped whenever the root is an inner node
+        const RrsNode& vr = desc->nodes[0];
+        s.d.root = (vr.ref1 == RRS_REF_EMPTY && vr.ref0 != RRS_REF_EMPTY && !(vr.ref0 & RRS_REF_LEAF)) ? vr.ref0 : 0u;
+    }
     // rays of a deep tree differ widely in length: refill early; a tiny scene amortises the fetch over more lanes
     s.d.refill_lanes = desc->max_depth > 6 ? 4u : 12u;
+    s.d.tune = 1u;
     if (const char* e = std::getenv("RRS_REFILL_LANES")) s.d.refill_lanes = std::min(32, std::max(1, std::atoi(e)));
+    if (const char* e = std::getenv("RRS_TUNE")) s.d.tune = (uint32_t)std::atoi(e);
     *out = sc;
     return RRS_OK;
 }

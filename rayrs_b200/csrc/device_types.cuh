@@ -10,15 +10,17 @@ namespace rrs {
 // ---------------------------------------------------------------------------------------
 // HBM layout
 // ---------------------------------------------------------------------------------------
-// Primitive record, 48 B, three float4 so that it is fetched with 128-bit loads.
+// Primitive record, 64 B = two 32-byte halves, each fetched by ONE 256-bit load (a 48-byte record read
+// as 3 x 128 bit cost three L1 wavefronts per lane; the L1 data pipe is the busiest unit of the
+// traversal, profiles/r01d_c4_batched_metrics.csv).
 //   meta = type | material << 2          (a.w)
 //   triangle : a = (p1, meta)  b = (p2, obj_id)  c = (p3, emission)
 //   sphere   : a = (centre, meta) b = (r^2, index into sphere64, -, obj_id) c = (-, -, -, emission)
 //   plane    : a = (pos, umin, umax, meta) b = (vmin, vmax, axis, obj_id) c = (-, -, -, emission)
-struct DPrim {
-    float4 a, b, c;
+struct __align__(32) DPrim {
+    float4 a, b, c, pad;
 };
-static_assert(sizeof(DPrim) == 48, "DPrim must be 48 bytes");
+static_assert(sizeof(DPrim) == 64, "DPrim must be 64 bytes");
 
 // Material record, 48 B.
 //   m0 = (color rgb, tag)
@@ -28,12 +30,16 @@ struct DMat {
     float4 m0, m1, m2;
 };
 
-// 64-byte node as two 32-byte halves (each fetched by one 256-bit load):
-//   h0 = lo0.xyz hi0.xyz lo1.xy          h1 = lo1.z hi1.xyz ref0 ref1 flags pad
-// which is exactly the memory image of RrsNode.
-struct __align__(32) DNodeHalf {
-    float f[8];
+// 32-byte node: the whole binary node — both children's boxes and references — in ONE 256-bit load
+// (LDG.E.ENL2.256).  Boxes are fp16, rounded outward from the fp32 boxes of RrsNode (lo down, hi up;
+// out-of-range values become +-inf), so the test stays conservative: a looser box costs a few extra
+// node visits near the leaves, never a wrong hit.  Each axis is one half2 word (lo, hi), which lets the
+// traversal pick near/far planes with a single PRMT per axis instead of two selects.
+//   w[0..2] = child 0 (lo.x,hi.x) (lo.y,hi.y) (lo.z,hi.z)   w[3..5] = child 1   w[6] = ref0   w[7] = ref1
+struct __align__(32) DNode16 {
+    uint32_t w[8];
 };
+static_assert(sizeof(DNode16) == 32, "DNode16 must be 32 bytes");
 
 #define RRS_NO_PRIM 0xFFFFFFFFu
 // origin word of a ray: primitive index (28 bits) | RRS_ORG64 when the ray also carries an f64 origin
@@ -100,7 +106,7 @@ __device__ __forceinline__ float4 rng_uniforms(uint64_t seed, uint32_t pixel, ui
 // ---------------------------------------------------------------------------------------
 struct DScene {
     const DPrim* prims;
-    const DNodeHalf* nodes;  // 2 halves per node
+    const DNode16* nodes;
     const DMat* mats;
     const float4* emis;      // (strength*color, -)
     const float4* hdri;      // RGBA f32 texels
@@ -112,8 +118,10 @@ struct DScene {
     // transmissive material — see "sphere re-entry" in intersect.cuh
     const double4* sphere64;
     uint32_t stack_entries;  // per-thread traversal stack size (entries, including the sentinel)
-    uint32_t has_triangles;  // 0: no triangle in the scene (the per-ray shear setup is skipped)
+    uint32_t has_triangles;  // 0: no triangle in the scene (the per-leaf shear setup is skipped)
+    uint32_t root;           // node the traversal starts at (the virtual root's only child when that is an inner node)
     uint32_t refill_lanes;   // extend refills a warp with new rays once this many lanes are idle
+    uint32_t tune;           // development switches (bit0: prefetch a leaf run when a lane parks on it)
 };
 
 struct DCamera {

@@ -4,14 +4,21 @@
 //   Triangle::intersect geometry.rs:359-375     leaf filter t>tmin && t<tmax  bvh.rs:404-413
 //   closest hit = smallest t, ties -> first leaf in DFS order (bvh.rs:50-72,395-399)
 #pragma once
+#include <cuda_fp16.h>
+
 #include "device_types.cuh"
 
 namespace rrs {
 
-// 256-bit read-only load (LDG.E.ENL2.256.CONSTANT on sm_100a): one instruction per node half.
-__device__ __forceinline__ void ldg256(const DNodeHalf* p, float (&v)[8]) {
+// 256-bit read-only loads (LDG.E.ENL2.256.CONSTANT on sm_100a): one instruction per node / primitive half.
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                  : "l"(p));
 }
 
@@ -193,7 +200,7 @@ struct TravCounters {
 
 struct RayK {
     float3 o, d, idir;
-    RayProj proj;          // only initialised when the scene holds triangles
+    uint32_t selx, sely, selz;  // PRMT selectors: (near, far) = (lo, hi) or (hi, lo) by the sign of 1/d
     uint32_t origin_prim;  // primitive the ray was spawned on, RRS_NO_PRIM for camera rays
     const double* org64;   // f64 origin carried with the ray (transmissive spheres), or nullptr
 };
@@ -213,39 +220,45 @@ __device__ __forceinline__ void trav_begin(const DScene& sc, float3 o, float3 d,
     r.idir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     r.origin_prim = origin_word == RRS_NO_PRIM ? RRS_NO_PRIM : (origin_word & RRS_PRIM_MASK);
     r.org64 = (SPH64 && origin_word != RRS_NO_PRIM && (origin_word & RRS_ORG64)) ? org64 : nullptr;
-    if (sc.has_triangles) r.proj = make_proj(d);
+    r.selx = r.idir.x < 0.f ? 0x1032u : 0x3210u;
+    r.sely = r.idir.y < 0.f ? 0x1032u : 0x3210u;
+    r.selz = r.idir.z < 0.f ? 0x1032u : 0x3210u;
     stack[0] = TRAV_DONE;
-    tv.cur = 0;  // virtual root
+    tv.cur = sc.root;
     tv.sp = 1;
     tv.tbest = sc.tmax;
     tv.best = RRS_NO_PRIM;
 }
 
 __device__ __forceinline__ bool trav_on_inner(const Trav& tv) { return (int32_t)tv.cur >= 0; }
+__device__ __forceinline__ __half2 u32_as_half2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
 
 // One inner node: both child boxes from one 2 x 256-bit fetch, near child first, far child pushed.
 template <bool COUNT>
 __device__ __forceinline__ void trav_node_step(const DScene& sc, const RayK& r, Trav& tv, uint32_t* stack, int stride,
                                                TravCounters& cnt) {
-    float h0[8], h1[8];
-    ldg256(sc.nodes + 2 * tv.cur, h0);
-    ldg256(sc.nodes + 2 * tv.cur + 1, h1);
+    uint32_t w[8];
+    ldg256(sc.nodes + tv.cur, w);
     if (COUNT) cnt.nodes++;
     const float3 o = r.o, idir = r.idir;
-    const bool neg_x = idir.x < 0.f, neg_y = idir.y < 0.f, neg_z = idir.z < 0.f;
-    const uint32_t ref0 = __float_as_uint(h1[4]), ref1 = __float_as_uint(h1[5]);
-    // child 0: lo = h0[0..2], hi = h0[3..5]; child 1: lo = h0[6],h0[7],h1[0], hi = h1[1..3]
+    const uint32_t ref0 = w[6], ref1 = w[7];
     // Slab test as geometry.rs:458-513 writes it: the near/far plane is chosen by the sign of
     // 1/d (not by min/max of the two products), and max/min drop NaNs — so a ray lying in a
     // face plane of the box (0 * inf = NaN) is simply not constrained by that axis.
-    float ax0 = ((neg_x ? h0[3] : h0[0]) - o.x) * idir.x, ax1 = ((neg_x ? h0[0] : h0[3]) - o.x) * idir.x;
-    float ay0 = ((neg_y ? h0[4] : h0[1]) - o.y) * idir.y, ay1 = ((neg_y ? h0[1] : h0[4]) - o.y) * idir.y;
-    float az0 = ((neg_z ? h0[5] : h0[2]) - o.z) * idir.z, az1 = ((neg_z ? h0[2] : h0[5]) - o.z) * idir.z;
+    const float2 ax = __half22float2(u32_as_half2(__byte_perm(w[0], 0u, r.selx)));  // (near, far) planes
+    const float2 ay = __half22float2(u32_as_half2(__byte_perm(w[1], 0u, r.sely)));
+    const float2 az = __half22float2(u32_as_half2(__byte_perm(w[2], 0u, r.selz)));
+    const float2 bx = __half22float2(u32_as_half2(__byte_perm(w[3], 0u, r.selx)));
+    const float2 by = __half22float2(u32_as_half2(__byte_perm(w[4], 0u, r.sely)));
+    const float2 bz = __half22float2(u32_as_half2(__byte_perm(w[5], 0u, r.selz)));
+    float ax0 = (ax.x - o.x) * idir.x, ax1 = (ax.y - o.x) * idir.x;
+    float ay0 = (ay.x - o.y) * idir.y, ay1 = (ay.y - o.y) * idir.y;
+    float az0 = (az.x - o.z) * idir.z, az1 = (az.y - o.z) * idir.z;
     float n0 = fmaxf(fmaxf(ax0, ay0), fmaxf(az0, sc.tmin));
     float f0 = fminf(fminf(ax1, ay1), fminf(az1, tv.tbest));
-    float bx0 = ((neg_x ? h1[1] : h0[6]) - o.x) * idir.x, bx1 = ((neg_x ? h0[6] : h1[1]) - o.x) * idir.x;
-    float by0 = ((neg_y ? h1[2] : h0[7]) - o.y) * idir.y, by1 = ((neg_y ? h0[7] : h1[2]) - o.y) * idir.y;
-    float bz0 = ((neg_z ? h1[3] : h1[0]) - o.z) * idir.z, bz1 = ((neg_z ? h1[0] : h1[3]) - o.z) * idir.z;
+    float bx0 = (bx.x - o.x) * idir.x, bx1 = (bx.y - o.x) * idir.x;
+    float by0 = (by.x - o.y) * idir.y, by1 = (by.y - o.y) * idir.y;
+    float bz0 = (bz.x - o.z) * idir.z, bz1 = (bz.y - o.z) * idir.z;
     float n1 = fmaxf(fmaxf(bx0, by0), fmaxf(bz0, sc.tmin));
     float f1 = fminf(fminf(bx1, by1), fminf(bz1, tv.tbest));
     // conservative acceptance: fp32 slab arithmetic is good to a few ulp, boxes are rounded
@@ -272,18 +285,22 @@ __device__ __forceinline__ void trav_leaf_step(const DScene& sc, const RayK& r, 
                                                TravCounters& cnt) {
     const uint32_t first = tv.cur & 0x0FFFFFFFu;
     const uint32_t count = ((tv.cur >> 28) & 7u) + 1u;
+    // the shear rows are rebuilt per leaf visit (~3.5 per ray) instead of living in 6 registers for the
+    // whole traversal (~30 node steps per ray)
+    RayProj proj;
+    if (sc.has_triangles) proj = make_proj(r.d);
     for (uint32_t k = 0; k < count; ++k) {
         const uint32_t pi = first + k;
-        const float4* pp = reinterpret_cast<const float4*>(sc.prims + pi);
-        float4 a = __ldg(pp), b = __ldg(pp + 1);
+        float4 a, b, c, pad;
+        ldg256(sc.prims + pi, a, b);
+        ldg256(reinterpret_cast<const char*>(sc.prims + pi) + 32, c, pad);
         const uint32_t type = prim_type(a);
         float t;
         bool hit;
         if (COUNT) cnt.prims++;
         if (type == RRS_TRIANGLE) {
             if (pi == r.origin_prim) continue;  // planar primitive cannot re-hit itself
-            float4 c = __ldg(pp + 2);
-            hit = hit_triangle(a, b, c, r.o, r.d, r.proj, t);
+            hit = hit_triangle(a, b, c, r.o, r.d, proj, t);
         } else if (type == RRS_SPHERE) {
             if (SPH64 && pi == r.origin_prim && r.org64 != nullptr) {
                 // re-entry: the reference's f64 arithmetic on the f64 hit point, then the

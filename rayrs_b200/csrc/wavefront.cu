@@ -205,7 +205,10 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
             const uint32_t want = __ballot_sync(FULL, inner);
             const uint32_t parked = __ballot_sync(FULL, !inner && tv.cur != TRAV_DONE);
             if (want == 0u || __popc(want) < __popc(parked)) break;
-            if (inner) trav_node_step<COUNT>(sc, r, tv, stack, stride, cnt);
+            if (inner) {
+                trav_node_step<COUNT>(sc, r, tv, stack, stride, cnt);
+                for (uint32_t k = 1; k < ((sc.tune >> 4) & 15u) && trav_on_inner(tv); ++k) trav_node_step<COUNT>(sc, r, tv, stack, stride, cnt);
+            }
         }
         // ---- leaves ----
         if (!trav_on_inner(tv) && tv.cur != TRAV_DONE) trav_leaf_step<COUNT, SPH64>(sc, r, tv, stack, stride, cnt);

@@ -58,7 +58,7 @@ struct SceneImpl {
     DScene d{};
     // owned device allocations
     DPrim* prims = nullptr;
-    DNodeHalf* nodes = nullptr;
+    DNode16* nodes = nullptr;
     DMat* mats = nullptr;
     float4* emis = nullptr;
     float4* hdri = nullptr;

@@ -266,6 +266,33 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
     s.d.stack_entries = std::max<uint32_t>(desc->max_depth + 3, 4);  // + the TRAV_DONE sentinel
     s.d.has_triangles = has_triangles ? 1u : 0u;
     {
+        // primitives the traversal can reach (leaf runs below live nodes), for the small-scene path
+        std::vector<uint32_t> reach;
+        std::vector<uint32_t> todo{0u};
+        bool small = true;
+        while (!todo.empty() && small) {
+            const RrsNode& nd = desc->nodes[todo.back()];
+            todo.pop_back();
+            for (uint32_t r : {nd.ref0, nd.ref1}) {
+                if (r == RRS_REF_EMPTY) continue;
+                if (r & RRS_REF_LEAF) {
+                    for (uint32_t k = 0; k <= ((r >> 28) & 7u); ++k) reach.push_back((r & 0x0FFFFFFFu) + k);
+                } else {
+                    todo.push_back(r);
+                }
+            }
+            small = reach.size() <= RRS_BRUTE_MAX && todo.size() <= 64;
+        }
+        std::sort(reach.begin(), reach.end());
+        reach.erase(std::unique(reach.begin(), reach.end()), reach.end());
+        s.d.brute_count = 0;
+        const char* e = std::getenv("RRS_NO_BRUTE");
+        if (small && !reach.empty() && !(e && std::atoi(e))) {
+            s.d.brute_count = (uint32_t)reach.size();
+            for (size_t k = 0; k < reach.size(); ++k) s.d.brute_prim[k] = reach[k];
+        }
+    }
+    {
         // children of the reference root lie inside its box, so its own slab test (the virtual root's
         // only job) can be skipped whenever the root is an inner node
         const RrsNode& vr = desc->nodes[0];

@@ -104,6 +104,8 @@ __device__ __forceinline__ float4 rng_uniforms(uint64_t seed, uint32_t pixel, ui
 // ---------------------------------------------------------------------------------------
 // Scene as the kernels see it
 // ---------------------------------------------------------------------------------------
+#define RRS_BRUTE_MAX 8
+
 struct DScene {
     const DPrim* prims;
     const DNode16* nodes;
@@ -120,6 +122,8 @@ struct DScene {
     uint32_t stack_entries;  // per-thread traversal stack size (entries, including the sentinel)
     uint32_t has_triangles;  // 0: no triangle in the scene (the per-leaf shear setup is skipped)
     uint32_t root;           // node the traversal starts at (the virtual root's only child when that is an inner node)
+    uint32_t brute_count;    // > 0: that many reachable primitives in total -> no BVH, test them all (intersect.cuh)
+    uint32_t brute_prim[8];  // their indices, ascending (DFS order); RRS_BRUTE_MAX entries
     uint32_t refill_lanes;   // extend refills a warp with new rays once this many lanes are idle
     uint32_t tune;           // development switches (bit0: prefetch a leaf run when a lane parks on it)
 };

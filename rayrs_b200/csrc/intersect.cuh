@@ -279,6 +279,41 @@ __device__ __forceinline__ void trav_node_step(const DScene& sc, const RayK& r, 
     }
 }
 
+// One primitive against the ray; RayIntersection::update (bvh.rs:50-72) on a hit.
+template <bool SPH64>
+__device__ __forceinline__ void test_prim(const DScene& sc, uint32_t pi, float4 a, float4 b, float4 c, float3 o, float3 d,
+                                          const RayProj& proj, uint32_t origin_prim, const double* org64, float& tbest,
+                                          uint32_t& best) {
+    const uint32_t type = prim_type(a);
+    float t;
+    bool hit;
+    if (type == RRS_TRIANGLE) {
+        if (pi == origin_prim) return;  // planar primitive cannot re-hit itself
+        hit = hit_triangle(a, b, c, o, d, proj, t);
+    } else if (type == RRS_SPHERE) {
+        if (SPH64 && pi == origin_prim && org64 != nullptr) {
+            // re-entry: the reference's f64 arithmetic on the f64 hit point, then the
+            // leaf filter of bvh.rs:404-413 in f64
+            double t64;
+            double4 s64 = sc.sphere64[__float_as_uint(b.y)];
+            hit = sphere_intersect64(s64, org64[0], org64[1], org64[2], (double)d.x, (double)d.y, (double)d.z, t64) &&
+                  t64 > sc.tmin64 && t64 < sc.tmax64;
+            t = (float)t64;
+        } else {
+            hit = hit_sphere(a, b, o, d, pi == origin_prim, t);
+        }
+    } else {
+        if (pi == origin_prim) return;
+        hit = hit_plane(a, b, o, d, t);
+    }
+    // leaf filter + RayIntersection::update: strictly smaller t wins; equal t keeps
+    // the lower DFS index (ordered traversal may meet them in either order)
+    if (hit && t > sc.tmin && (t < tbest || (t == tbest && best != RRS_NO_PRIM && pi < best))) {
+        tbest = t;
+        best = pi;
+    }
+}
+
 // One leaf run (1..4 primitives, DFS order), then pop.
 template <bool COUNT, bool SPH64>
 __device__ __forceinline__ void trav_leaf_step(const DScene& sc, const RayK& r, Trav& tv, uint32_t* stack, int stride,
@@ -294,38 +329,43 @@ __device__ __forceinline__ void trav_leaf_step(const DScene& sc, const RayK& r, 
         float4 a, b, c, pad;
         ldg256(sc.prims + pi, a, b);
         ldg256(reinterpret_cast<const char*>(sc.prims + pi) + 32, c, pad);
-        const uint32_t type = prim_type(a);
-        float t;
-        bool hit;
         if (COUNT) cnt.prims++;
-        if (type == RRS_TRIANGLE) {
-            if (pi == r.origin_prim) continue;  // planar primitive cannot re-hit itself
-            hit = hit_triangle(a, b, c, r.o, r.d, proj, t);
-        } else if (type == RRS_SPHERE) {
-            if (SPH64 && pi == r.origin_prim && r.org64 != nullptr) {
-                // re-entry: the reference's f64 arithmetic on the f64 hit point, then the
-                // leaf filter of bvh.rs:404-413 in f64
-                double t64;
-                double4 s64 = sc.sphere64[__float_as_uint(b.y)];
-                hit = sphere_intersect64(s64, r.org64[0], r.org64[1], r.org64[2], (double)r.d.x, (double)r.d.y, (double)r.d.z, t64) &&
-                      t64 > sc.tmin64 && t64 < sc.tmax64;
-                t = (float)t64;
-            } else {
-                hit = hit_sphere(a, b, r.o, r.d, pi == r.origin_prim, t);
-            }
-        } else {
-            if (pi == r.origin_prim) continue;
-            hit = hit_plane(a, b, r.o, r.d, t);
-        }
-        // leaf filter + RayIntersection::update: strictly smaller t wins; equal t keeps
-        // the lower DFS index (ordered traversal may meet them in either order)
-        if (hit && t > sc.tmin && (t < tv.tbest || (t == tv.tbest && tv.best != RRS_NO_PRIM && pi < tv.best))) {
-            tv.tbest = t;
-            tv.best = pi;
-        }
+        test_prim<SPH64>(sc, pi, a, b, c, r.o, r.d, proj, r.origin_prim, r.org64, tv.tbest, tv.best);
     }
     --tv.sp;
     tv.cur = stack[tv.sp * stride];
+}
+
+// Small scenes (<= RRS_BRUTE_MAX reachable primitives, every sphere-series configuration): the BVH is
+// pure overhead — its two or three node steps cost as much as the tests they save and de-synchronise
+// the lanes.  All reachable primitives are tested instead, in DFS order, from a copy staged in shared
+// memory (one broadcast LDS per record, no stack, no divergence: every lane runs the same loop).  Same
+// result as the traversal: a box never rejects a ray that hits a primitive inside it, and primitives
+// under a dead node are not in the list.
+template <bool COUNT, bool SPH64>
+__device__ __forceinline__ void closest_hit_brute(const DScene& sc, const DPrim* __restrict__ s_prims, float3 o, float3 d,
+                                                  uint32_t origin_word, const double* __restrict__ org64, float& tbest,
+                                                  uint32_t& best, TravCounters& cnt) {
+    const uint32_t origin_prim = origin_word == RRS_NO_PRIM ? RRS_NO_PRIM : (origin_word & RRS_PRIM_MASK);
+    const double* o64 = (SPH64 && origin_word != RRS_NO_PRIM && (origin_word & RRS_ORG64)) ? org64 : nullptr;
+    RayProj proj;
+    if (sc.has_triangles) proj = make_proj(d);
+    tbest = sc.tmax;
+    best = RRS_NO_PRIM;
+    for (uint32_t k = 0; k < sc.brute_count; ++k) {
+        const DPrim& p = s_prims[k];
+        if (COUNT) cnt.prims++;
+        test_prim<SPH64>(sc, sc.brute_prim[k], p.a, p.b, p.c, o, d, proj, origin_prim, o64, tbest, best);
+    }
+}
+
+// block-wide copy of the brute-force list into shared memory (call before the first __syncthreads)
+__device__ __forceinline__ void stage_brute_prims(const DScene& sc, DPrim* s_prims) {
+    const uint32_t n4 = sc.brute_count * 4u;
+    for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) {
+        const float4* src = reinterpret_cast<const float4*>(sc.prims + sc.brute_prim[i >> 2]) + (i & 3u);
+        reinterpret_cast<float4*>(s_prims)[i] = __ldg(src);
+    }
 }
 
 // Per-thread traversal to completion (parity probes; the render path batches the steps per warp).

@@ -154,9 +154,24 @@ __global__ void __launch_bounds__(kBlock) k_generate(RenderConst rc, DCounters* 
 //            active on the 1M-triangle scene: profiles/r01c_c4_fused_metrics.csv);
 //   nodes    inner-node steps while at least as many lanes want one as are parked on a leaf;
 //   leaf     all parked lanes test their leaf run together, pop, and the cycle repeats.
+template <bool COUNT>
+__device__ __forceinline__ void flush_trav_counters(DCounters* __restrict__ c, const TravCounters& cnt) {
+    if (COUNT) {
+        uint32_t a = cnt.nodes, p = cnt.prims;
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+            p += __shfl_xor_sync(0xFFFFFFFFu, p, o);
+        }
+        if (lane_id() == 0) {
+            atomicAdd(&c->nodes_visited, (unsigned long long)a);
+            atomicAdd(&c->prims_tested, (unsigned long long)p);
+        }
+    }
+}
+
 template <bool COUNT, bool SPH64>
 __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __restrict__ c, const QueueSet& q, int cur,
-                                             uint32_t* s_stack, uint32_t* s_cursor) {
+                                             uint32_t* s_stack, const DPrim* s_prims, uint32_t* s_cursor) {
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t b = blockIdx.x;
     const uint32_t n = q.count[(size_t)cur * q.regions + b];
@@ -166,6 +181,27 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
     const float4* __restrict__ ray_o = q.ray_o + off;
     const float4* __restrict__ ray_d = q.ray_d + off;
     float2* __restrict__ hits = q.hits + roff;
+    if (sc.brute_count) {
+        // small scene: every lane runs the same loop over the staged primitives, 32 rays per fetch
+        TravCounters cnt{0, 0};
+        for (;;) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(s_cursor, 32u);
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= n) break;
+            const uint32_t i = base + lane;
+            if (i < n) {
+                float4 o4 = ray_o[i], d4 = ray_d[i];
+                const double* o64 = (SPH64 && q.org64) ? q.org64 + 3 * (off + i) : nullptr;
+                float t;
+                uint32_t prim;
+                closest_hit_brute<COUNT, SPH64>(sc, s_prims, xyz(o4), xyz(d4), __float_as_uint(o4.w), o64, t, prim, cnt);
+                hits[i] = make_float2(t, __uint_as_float(prim));
+            }
+        }
+        flush_trav_counters<COUNT>(c, cnt);
+        return;
+    }
     uint32_t* stack = s_stack + threadIdx.x;
     const int stride = blockDim.x;
     TravCounters cnt{0, 0};
@@ -217,17 +253,7 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
             has_ray = false;
         }
     }
-    if (COUNT) {
-        uint32_t a = cnt.nodes, p = cnt.prims;
-        for (int o = 16; o > 0; o >>= 1) {
-            a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
-            p += __shfl_xor_sync(0xFFFFFFFFu, p, o);
-        }
-        if (lane == 0) {
-            atomicAdd(&c->nodes_visited, (unsigned long long)a);
-            atomicAdd(&c->prims_tested, (unsigned long long)p);
-        }
-    }
+    flush_trav_counters<COUNT>(c, cnt);
 }
 
 template <bool COUNT, bool SPH64>
@@ -235,10 +261,12 @@ __global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DCounters* __restr
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // [stack_entries * blockDim.x * 4 B traversal stacks]
     uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem_raw);
+    __shared__ DPrim s_prims[RRS_BRUTE_MAX];
     __shared__ uint32_t s_cursor;
     if (threadIdx.x == 0) s_cursor = 0;
+    stage_brute_prims(sc, s_prims);
     __syncthreads();
-    phase_extend<COUNT, SPH64>(sc, c, q, cur, s_stack, &s_cursor);
+    phase_extend<COUNT, SPH64>(sc, c, q, cur, s_stack, s_prims, &s_cursor);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -412,7 +440,8 @@ __global__ void __launch_bounds__(kBlock, SPH64 ? 6 : 8) k_shade(DScene sc, Rend
 template <bool EXACT_TILES, bool COUNT, bool SPH64>
 __device__ __forceinline__ bool wavefront_iteration(const DScene& sc, const RenderConst& rc, DCounters* __restrict__ c,
                                                     const QueueSet& q, int cur, float4* __restrict__ accum,
-                                                    uint32_t* s_stack, uint32_t* s_u32, unsigned long long* s_u64) {
+                                                    uint32_t* s_stack, const DPrim* s_prims, uint32_t* s_u32,
+                                                    unsigned long long* s_u64) {
     // s_u64[1..3]: cycles spent in generate / extend / shade, s_u64[4]: iterations (thread 0 only)
     long long t0 = 0;
     if (threadIdx.x == 0) t0 = clock64();
@@ -428,7 +457,7 @@ __device__ __forceinline__ bool wavefront_iteration(const DScene& sc, const Rend
     }
     __syncthreads();
     if (n == 0) return false;  // nothing live and no path left for this block
-    phase_extend<COUNT, SPH64>(sc, c, q, cur, s_stack, &s_u32[2]);
+    phase_extend<COUNT, SPH64>(sc, c, q, cur, s_stack, s_prims, &s_u32[2]);
     __syncthreads();
     if (threadIdx.x == 0) {
         s_u32[2] = 0;
@@ -451,12 +480,14 @@ __global__ void __launch_bounds__(kBlock, SPH64 ? 6 : 8) k_wavefront(DScene sc, 
                                                                       QueueSet q, float4* __restrict__ accum) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem_raw);
+    __shared__ DPrim s_prims[RRS_BRUTE_MAX];
     __shared__ uint32_t s_u32[4];
     __shared__ unsigned long long s_u64[5];
     if (threadIdx.x < 5) s_u64[threadIdx.x] = 0;
+    stage_brute_prims(sc, s_prims);
     __syncthreads();
     for (int cur = 0;; cur ^= 1)
-        if (!wavefront_iteration<EXACT_TILES, COUNT, SPH64>(sc, rc, c, q, cur, accum, s_stack, s_u32, s_u64)) break;
+        if (!wavefront_iteration<EXACT_TILES, COUNT, SPH64>(sc, rc, c, q, cur, accum, s_stack, s_prims, s_u32, s_u64)) break;
     if (threadIdx.x == 0) {
         atomicMax(&c->iterations, s_u64[4]);
         atomicAdd(&c->cyc_generate, s_u64[1]);
@@ -497,12 +528,18 @@ __global__ void __launch_bounds__(kBlock) k_intersect32(DScene sc, const float4*
                                                          int32_t* __restrict__ obj_id, float* __restrict__ t_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem_raw);
+    __shared__ DPrim s_prims[RRS_BRUTE_MAX];
+    stage_brute_prims(sc, s_prims);
+    __syncthreads();
     TravCounters cnt{0, 0};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 o4 = ray_o[i], d4 = ray_d[i];
         float t;
         uint32_t prim;
-        closest_hit<false, false>(sc, xyz(o4), xyz(d4), RRS_NO_PRIM, nullptr, s_stack + threadIdx.x, blockDim.x, t, prim, cnt);
+        if (sc.brute_count)
+            closest_hit_brute<false, false>(sc, s_prims, xyz(o4), xyz(d4), RRS_NO_PRIM, nullptr, t, prim, cnt);
+        else
+            closest_hit<false, false>(sc, xyz(o4), xyz(d4), RRS_NO_PRIM, nullptr, s_stack + threadIdx.x, blockDim.x, t, prim, cnt);
         if (prim == RRS_NO_PRIM) {
             obj_id[i] = -1;
             t_out[i] = INFINITY;

@@ -243,7 +243,7 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
             if (want == 0u || __popc(want) < __popc(parked)) break;
             if (inner) {
                 trav_node_step<COUNT>(sc, r, tv, stack, stride, cnt);
-                for (uint32_t k = 1; k < ((sc.tune >> 4) & 15u) && trav_on_inner(tv); ++k) trav_node_step<COUNT>(sc, r, tv, stack, stride, cnt);
+                for (uint32_t k = 1; k < sc.node_steps && trav_on_inner(tv); ++k) trav_node_step<COUNT>(sc, r, tv, stack, stride, cnt);
             }
         }
         // ---- leaves ----

@@ -8,9 +8,12 @@
 //       triangle (2): p1 xyz, p2 xyz, p3 xyz
 //   materials n x 12 doubles [tag, color rgb, alpha, ior, fresnel kind, r0/spec rgb, -, -]
 //   emissions n x 4 doubles  [strength, color rgb]
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
+#include "mesh_io.hpp"
 #include "rayrs_host.hpp"
 
 using namespace rayrs;
@@ -117,6 +120,65 @@ int rrh_camera_new(const double* origin, const double* up, const double* lookat,
         Camera c(Vec3(origin[0], origin[1], origin[2]), Vec3(up[0], up[1], up[2]), Vec3(lookat[0], lookat[1], lookat[2]), fov,
                  width, height, ppi);
         *out = c.derived();
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// ---- mesh files (mesh_io.hpp) ----
+// kind 0 = PLY (load_ply_file), 1 = OBJ (load_obj_file); returns n x 9 doubles (p1, p2, p3), free with rrh_free
+double* rrh_load_mesh(const char* path, int kind, uint64_t* n_tris) {
+    try {
+        std::vector<Triangle> t = kind == 0 ? load_ply_file(path) : load_obj_file(path);
+        double* out = static_cast<double*>(std::malloc(sizeof(double) * 9 * std::max<size_t>(t.size(), 1)));
+        for (size_t i = 0; i < t.size(); ++i) {
+            const Vec3* p[3] = {&t[i].p1, &t[i].p2, &t[i].p3};
+            for (int k = 0; k < 3; ++k) {
+                out[9 * i + 3 * k] = p[k]->x;
+                out[9 * i + 3 * k + 1] = p[k]->y;
+                out[9 * i + 3 * k + 2] = p[k]->z;
+            }
+        }
+        *n_tris = t.size();
+        return out;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+void rrh_free(void* p) { std::free(p); }
+
+// format 0 = ascii, 1 = binary_big_endian, 2 = binary_little_endian
+int rrh_write_ply(const char* path, const float* xyz, uint64_t n_vertices, const int32_t* faces, uint64_t n_faces, int format) {
+    try {
+        ply::write_ply(path, std::vector<float>(xyz, xyz + 3 * n_vertices), std::vector<int32_t>(faces, faces + 3 * n_faces),
+                       (ply::PlyFormat)format);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// Header of an in-memory PLY as text, one line per item (tests):
+//   "format <ascii|binary_big_endian|binary_little_endian> <version>", "comment <line>",
+//   "element <name> <length>", "property <type#> <name>", "list <lentype#> <elemtype#> <name>"
+int rrh_ply_describe(const char* bytes, uint64_t n, char* out, uint64_t cap) {
+    try {
+        ply::Ply p = ply::Ply::parse(std::string(bytes, bytes + n));
+        static const char* fmt[] = {"ascii", "binary_big_endian", "binary_little_endian"};
+        std::string s = std::string("format ") + fmt[(int)p.header.format] + " " + p.header.version + "\n";
+        for (const std::string& c : p.header.comments) s += c + "\n";
+        for (const ply::PlyElement& e : p.header.elements) {
+            s += "element " + e.name + " " + std::to_string(e.length) + "\n";
+            for (const ply::PlyProperty& pr : e.properties)
+                s += pr.is_list ? "list " + std::to_string((int)pr.lentype) + " " + std::to_string((int)pr.typ) + " " + pr.name + "\n"
+                                : "property " + std::to_string((int)pr.typ) + " " + pr.name + "\n";
+        }
+        if (s.size() + 1 > cap) throw Panic("rrh_ply_describe: buffer too small");
+        std::memcpy(out, s.c_str(), s.size() + 1);
         return 0;
     } catch (const std::exception& e) {
         g_err = e.what();

@@ -108,6 +108,8 @@ struct Object {
                         Emission emission);
     static Object triangle(Vec3 p1, Vec3 p2, Vec3 p3, Material mat, Emission emission);
     static std::vector<Object> box_geom(Vec3 lower_left, Vec3 upper_right, Material mat, Emission emission);
+    // lib.rs:407-415: one object per triangle of a loaded mesh (mesh_io.hpp), all with the same material
+    static std::vector<Object> from_triangles(const std::vector<struct Triangle>& tris, Material mat, Emission emission);
     AxisAlignedBoundingBox bbox() const { return geom.bbox(); }
 };
 

@@ -11,6 +11,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Callable
 
+import os
+
 import numpy as np
 
 from .api import Axis, BvhHeuristic, Camera, Emission, Fresnel, Image, Material, Object, Scene, build_tables
@@ -202,6 +204,23 @@ def mesh_triangles(vertices: np.ndarray, faces: np.ndarray) -> np.ndarray:
     return vertices.astype(np.float64)[faces]
 
 
+def mesh_via_ply(vertices: np.ndarray, faces: np.ndarray, tag: str) -> np.ndarray:
+    """The BASELINE mesh configurations name a PLY mesh: write the synthetic mesh as binary-LE PLY
+    (float32 xyz, uchar-count int32 faces) and read it back through the host PLY loader — the path a
+    rayrs user's mesh takes (file -> load_ply_file -> Object::from_triangles)."""
+    import tempfile
+    from pathlib import Path
+    from . import mesh
+    d = Path(tempfile.gettempdir()) / "rayrs_b200_meshes"
+    d.mkdir(exist_ok=True)
+    path = d / f"{tag}_{os.getpid()}.ply"
+    mesh.write_ply(path, vertices, faces)
+    try:
+        return mesh.load_ply_file(path)
+    finally:
+        path.unlink(missing_ok=True)
+
+
 COPPER = dict(color=(1, 1, 1), alpha=0.05, r0=(0.722, 0.451, 0.2))  # test_scenes.rs:154-159
 
 
@@ -211,7 +230,7 @@ def copper_torus(nu=1000, nv=500, width_px=1920, height_px=1080, heuristic: BvhH
     w, h = film(width_px, height_px)
     mat = Material.cook_torrance(COPPER["color"], COPPER["alpha"], Fresnel.schlick_metallic(COPPER["r0"]))
     verts, faces = torus_mesh(nu, nv)
-    objects = [_floor(), Object.from_triangles(mesh_triangles(verts, faces), mat, Emission.Dark())]
+    objects = [_floor(), Object.from_triangles(mesh_via_ply(verts, faces, f"torus_{nu}x{nv}"), mat, Emission.Dark())]
     cam = dict(origin=(0.0, 5.0, 10.0), up=(0.0, 1.0, 0.0), lookat=(0.0, 1.0, 0.0), fov=50.0, width=w, height=h, ppi=PPI)
     return SceneSpec(f"copper_torus_{2 * nu * nv}", cam, objects, heuristic or BvhHeuristic.Sah(1000))
 
@@ -230,7 +249,7 @@ def mixed_scene(nu=2000, nv=1000, width_px=3840, height_px=2160, heuristic: BvhH
     ]
     copper = Material.cook_torrance(COPPER["color"], COPPER["alpha"], Fresnel.schlick_metallic(COPPER["r0"]))
     verts, faces = torus_mesh(nu, nv, center=(0.0, 1.7, -4.0))
-    extra = [Object.from_triangles(mesh_triangles(verts, faces), copper, Emission.Dark())]
+    extra = [Object.from_triangles(mesh_via_ply(verts, faces, f"torus_{nu}x{nv}_back"), copper, Emission.Dark())]
     spec = _multiple_spheres(f"mixed_{2 * nu * nv}", mats, width_px, height_px, extra=extra)
     if heuristic:
         spec.heuristic = heuristic

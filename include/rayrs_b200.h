@@ -220,6 +220,15 @@ int rrs_render_accumulate(RrsScene* scene, const RrsCamera* camera, const RrsRen
 int rrs_resolve(RrsScene* scene, const void* d_sum_rgba, uint32_t width, uint32_t height, uint32_t spp_total,
                 float* out_rgb, int out_is_device, void* cuda_stream);
 
+/* Output stage on the device — Image::to_raw_bytes (image.rs:193-222) fused with the division by
+ * spp_total: d_sum_rgba (device, float4 per pixel) -> out_rgb8 (device or host per `out_is_device`),
+ * 3 bytes per pixel = (255.99 * clip(mean, 0, 1)^gamma) as u8, evaluated in f64 like the reference
+ * (a NaN component clips to 1, as f64::min/max do).  census3, if not NULL, receives the three counters
+ * the reference prints: [clamped (> 1), NaN, negative] pixels.  The HDR export of main.rs:113-121
+ * (Image::pixels_f32, image.rs:224-229) is what rrs_resolve already returns.  Synchronous. */
+int rrs_to_raw_bytes(RrsScene* scene, const void* d_sum_rgba, uint32_t width, uint32_t height, uint32_t spp_total,
+                     double gamma, uint8_t* out_rgb8, int out_is_device, void* cuda_stream, uint64_t* census3);
+
 /* Closest hit for a batch of rays — Bvh::intersect (bvh.rs:212-214) with the scene's
  * (t_min, t_max).  obj_id[i] = RrsPrim.obj_id of the hit or -1; t[i] = distance or +inf.
  * precision 32: the production fp32 traversal (ordered, t-pruned).

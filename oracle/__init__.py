@@ -231,3 +231,19 @@ def rng_uniforms(seed, pixel, sample, slot, mode=RNG_MATCHED) -> np.ndarray:
     out = np.zeros(4)
     lib().orc_rng_uniforms(seed, pixel, sample, slot, mode, out.ctypes.data)
     return out
+
+
+def to_raw_bytes(image: np.ndarray, gamma: float = 1.0 / 2.2):
+    """Image::to_raw_bytes, rayrs-lib/src/image.rs:193-222, restated in numpy f64: per pixel the three censuses
+    the reference prints (clamped > 1, NaN, negative), then clip(0, 1) (min then max, both dropping NaN like
+    f64::min/max, vecmath.rs:389-397), powf(gamma), and (255.99 * x) as u8 (Rust's saturating float cast).
+    Returns (H x W x 3 uint8, {clamped, nan, negative})."""
+    v = np.asarray(image, dtype=np.float64)
+    nan = np.isnan(v).any(axis=-1)
+    with np.errstate(invalid="ignore"):
+        neg = (v < 0.0).any(axis=-1)
+        bright = (v > 1.0).any(axis=-1)
+        c = np.fmax(np.fmin(v, 1.0), 0.0)
+        q = 255.99 * np.power(c, gamma)
+    out = np.clip(np.nan_to_num(q, nan=0.0), 0.0, 255.0).astype(np.uint8)  # truncation toward zero
+    return out, {"clamped": int(bright.sum()), "nan": int(nan.sum()), "negative": int(neg.sum())}

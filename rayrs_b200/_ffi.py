@@ -85,6 +85,8 @@ CUDA_SYMBOLS = {
     "rrs_render": (C.c_int, [C.c_void_p, C.POINTER(RrsCamera), C.POINTER(RrsRenderParams), C.c_void_p]),
     "rrs_render_accumulate": (C.c_int, [C.c_void_p, C.POINTER(RrsCamera), C.POINTER(RrsRenderParams), C.c_void_p, C.c_void_p]),
     "rrs_resolve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p]),
+    "rrs_to_raw_bytes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_void_p, C.c_int,
+                                    C.c_void_p, C.c_void_p]),
     "rrs_intersect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]),
     "rrs_material_evaluate": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "rrs_background": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -386,3 +386,21 @@ def resolve(scene: Scene, d_sum_ptr: int, width: int, height: int, spp_total: in
     scene._need_gpu()
     _ffi.check(_ffi.cuda_lib().rrs_resolve(scene.handle, C.c_void_p(d_sum_ptr), width, height, spp_total,
                                            C.c_void_p(out_ptr), int(out_is_device), C.c_void_p(stream_ptr)))
+
+
+def to_raw_bytes(scene: Scene, d_sum_ptr: int, width: int, height: int, spp_total: int, gamma: float = 1.0 / 2.2,
+                 out_ptr: int = 0, stream_ptr: int = 0):
+    """Image::to_raw_bytes (image.rs:193-222) on the device, fused with the division by spp.  With out_ptr == 0
+    returns (H x W x 3 uint8 host array, {clamped, nan, negative} pixel counts); otherwise writes the bytes to the
+    DEVICE buffer at out_ptr and returns (None, counts)."""
+    scene._need_gpu()
+    census = (C.c_uint64 * 3)()
+    host = None
+    if out_ptr == 0:
+        host = np.empty((height, width, 3), dtype=np.uint8)
+        ptr, on_device = host.ctypes.data, 0
+    else:
+        ptr, on_device = out_ptr, 1
+    _ffi.check(_ffi.cuda_lib().rrs_to_raw_bytes(scene.handle, C.c_void_p(d_sum_ptr), width, height, spp_total, float(gamma),
+                                                C.c_void_p(ptr), on_device, C.c_void_p(stream_ptr), census))
+    return host, {"clamped": int(census[0]), "nan": int(census[1]), "negative": int(census[2])}

@@ -67,7 +67,7 @@ def build_cuda(force: bool = False) -> Path:
         objs.append(obj)
         if not force and _newer(obj, [src] + headers):
             continue
-        _run([nvcc] + NVCC_FLAGS + EXTRA.get(src.name, []) + ["-c", str(src), "-o", str(obj)],
+        _run([nvcc] + NVCC_FLAGS + EXTRA.get(src.name, []) + os.environ.get("RRS_NVCC_EXTRA", "").split() + ["-c", str(src), "-o", str(obj)],
              log=BUILD / (src.stem + ".ptxas.log"))
     if force or not _newer(CUDA_LIB, objs):
         _run([nvcc] + GENCODE + ["-shared", "-o", str(CUDA_LIB)] + [str(o) for o in objs])

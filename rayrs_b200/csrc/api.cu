@@ -337,6 +337,15 @@ int rrs_resolve(RrsScene* scene, const void* d_sum_rgba, uint32_t width, uint32_
     return rc == RRS_OK ? rc : fail(rc, err);
 }
 
+int rrs_to_raw_bytes(RrsScene* scene, const void* d_sum_rgba, uint32_t width, uint32_t height, uint32_t spp_total,
+                     double gamma, uint8_t* out_rgb8, int out_is_device, void* cuda_stream, uint64_t* census3) {
+    if (!scene) return fail(RRS_ERR_INVALID, "null scene");
+    std::string err;
+    int rc = wf_to_raw_bytes(&scene->impl, static_cast<const float4*>(d_sum_rgba), width, height, spp_total, gamma, out_rgb8,
+                             out_is_device != 0, static_cast<cudaStream_t>(cuda_stream), census3, err);
+    return rc == RRS_OK ? rc : fail(rc, err);
+}
+
 int rrs_render(RrsScene* scene, const RrsCamera* camera, const RrsRenderParams* params, float* out_rgb) {
     if (!scene || !camera || !params || !out_rgb) return fail(RRS_ERR_INVALID, "null argument");
     SceneImpl& s = scene->impl;

@@ -25,6 +25,12 @@
 namespace rrs {
 
 static constexpr int kBlock = 128;  // threads per block of the persistent kernels
+#ifndef RRS_BLOCKS_PER_SM
+#define RRS_BLOCKS_PER_SM 8
+#endif
+#ifndef RRS_BLOCKS_PER_SM_F64
+#define RRS_BLOCKS_PER_SM_F64 6
+#endif
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
@@ -418,7 +424,7 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
 }
 
 template <bool SPH64>
-__global__ void __launch_bounds__(kBlock, SPH64 ? 6 : 8) k_shade(DScene sc, RenderConst rc, DCounters* __restrict__ c,
+__global__ void __launch_bounds__(kBlock, SPH64 ? RRS_BLOCKS_PER_SM_F64 : RRS_BLOCKS_PER_SM) k_shade(DScene sc, RenderConst rc, DCounters* __restrict__ c,
                                                                   QueueSet q, int cur, float4* __restrict__ accum) {
     __shared__ uint32_t s_cursor, s_out;
     if (threadIdx.x == 0) {
@@ -476,7 +482,7 @@ __device__ __forceinline__ bool wavefront_iteration(const DScene& sc, const Rend
 }
 
 template <bool EXACT_TILES, bool COUNT, bool SPH64>
-__global__ void __launch_bounds__(kBlock, SPH64 ? 6 : 8) k_wavefront(DScene sc, RenderConst rc, DCounters* __restrict__ c,
+__global__ void __launch_bounds__(kBlock, SPH64 ? RRS_BLOCKS_PER_SM_F64 : RRS_BLOCKS_PER_SM) k_wavefront(DScene sc, RenderConst rc, DCounters* __restrict__ c,
                                                                       QueueSet q, float4* __restrict__ accum) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem_raw);
@@ -517,6 +523,41 @@ __global__ void k_resolve(const float4* __restrict__ accum, float* __restrict__ 
     if ((threadIdx.x & 31) == 0 && (nan_cnt | neg_cnt)) {
         atomicAdd(census + 0, (unsigned long long)nan_cnt);
         atomicAdd(census + 1, (unsigned long long)neg_cnt);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// output stage: Image::to_raw_bytes (image.rs:193-222) fused with the division by spp.  f64 like the
+// reference — it runs once per image, and the byte a pixel quantises to must not depend on fp32 pow.
+// ---------------------------------------------------------------------------------------
+__global__ void k_to_raw_bytes(const float4* __restrict__ accum, uint8_t* __restrict__ out, uint32_t npix, double inv_spp,
+                               double gamma, unsigned long long* __restrict__ census) {
+    uint32_t bright = 0, nan_cnt = 0, neg_cnt = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        const float4 a = accum[i];
+        // the f32 mean is the pixel value the host would hold (rrs_resolve); widen it like `val` in the reference
+        const double v[3] = {(double)(a.x * (float)inv_spp), (double)(a.y * (float)inv_spp), (double)(a.z * (float)inv_spp)};
+        if (isnan(v[0]) || isnan(v[1]) || isnan(v[2])) nan_cnt++;
+        if (v[0] < 0. || v[1] < 0. || v[2] < 0.) neg_cnt++;
+        if (v[0] > 1. || v[1] > 1. || v[2] > 1.) bright++;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            // Vector::clip vecmath.rs:389-397: x.min(1).max(0); f64::min drops a NaN operand, so NaN clips to 1.
+            // Spelled out: nvcc folds fmax(fmin(x, 1), 0) into a form that lets the NaN through.
+            double c = isnan(v[k]) ? 1. : (v[k] < 0. ? 0. : (v[k] > 1. ? 1. : v[k]));
+            double q = 255.99 * pow(c, gamma);
+            out[3 * (size_t)i + k] = (uint8_t)(q < 0. ? 0. : (q > 255. ? 255. : q));  // Rust `as u8` saturates
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        bright += __shfl_xor_sync(0xFFFFFFFFu, bright, o);
+        nan_cnt += __shfl_xor_sync(0xFFFFFFFFu, nan_cnt, o);
+        neg_cnt += __shfl_xor_sync(0xFFFFFFFFu, neg_cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0 && (bright | nan_cnt | neg_cnt)) {
+        atomicAdd(census + 0, (unsigned long long)bright);
+        atomicAdd(census + 1, (unsigned long long)nan_cnt);
+        atomicAdd(census + 2, (unsigned long long)neg_cnt);
     }
 }
 
@@ -839,6 +880,30 @@ int wf_resolve(SceneImpl* s, const float4* d_accum, uint32_t w, uint32_t h, uint
     s->stats.nan_pixels = s->h_census[0];
     s->stats.negative_pixels = s->h_census[1];
     s->stats.kernel_launches += 1;
+    return RRS_OK;
+}
+
+int wf_to_raw_bytes(SceneImpl* s, const float4* d_accum, uint32_t w, uint32_t h, uint32_t spp_total, double gamma,
+                    uint8_t* out, bool out_is_device, cudaStream_t stream, uint64_t* census3, std::string& err) {
+    if (!d_accum || !out || spp_total == 0) { err = "bad to_raw_bytes argument"; return RRS_ERR_INVALID; }
+    RRS_CUDA_CHECK(cudaSetDevice(s->device), err);
+    const uint32_t npix = w * h;
+    const size_t bytes = 3 * (size_t)npix;
+    unsigned long long* d_census = nullptr;
+    uint8_t* d_out = out;
+    RRS_CUDA_CHECK(cudaMalloc(&d_census, 3 * sizeof(unsigned long long)), err);
+    RRS_CUDA_CHECK(cudaMemsetAsync(d_census, 0, 3 * sizeof(unsigned long long), stream), err);
+    if (!out_is_device) RRS_CUDA_CHECK(cudaMalloc(&d_out, bytes), err);
+    int grid = std::min<uint32_t>((npix + 255) / 256, (uint32_t)s->num_sms * 8u);
+    k_to_raw_bytes<<<grid, 256, 0, stream>>>(d_accum, d_out, npix, 1.0 / (double)spp_total, gamma, d_census);
+    RRS_CUDA_CHECK(cudaGetLastError(), err);
+    unsigned long long hc[3] = {0, 0, 0};
+    if (!out_is_device) RRS_CUDA_CHECK(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, stream), err);
+    RRS_CUDA_CHECK(cudaMemcpyAsync(hc, d_census, sizeof(hc), cudaMemcpyDeviceToHost, stream), err);
+    RRS_CUDA_CHECK(cudaStreamSynchronize(stream), err);
+    if (!out_is_device) cudaFree(d_out);
+    cudaFree(d_census);
+    if (census3) { census3[0] = hc[0]; census3[1] = hc[1]; census3[2] = hc[2]; }
     return RRS_OK;
 }
 

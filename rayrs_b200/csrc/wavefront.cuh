@@ -85,6 +85,8 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
                          cudaStream_t stream, std::string& err);
 int wf_resolve(SceneImpl* s, const float4* d_accum, uint32_t w, uint32_t h, uint32_t spp_total, float* out,
                bool out_is_device, cudaStream_t stream, std::string& err);
+int wf_to_raw_bytes(SceneImpl* s, const float4* d_accum, uint32_t w, uint32_t h, uint32_t spp_total, double gamma,
+                    uint8_t* out, bool out_is_device, cudaStream_t stream, uint64_t* census3, std::string& err);
 int wf_intersect32(SceneImpl* s, const RrsRay* rays, size_t n, int32_t* obj_id, double* t, std::string& err);
 int wf_material_evaluate(SceneImpl* s, uint32_t material, const double* nv, const double* u, size_t n, float* out,
                          std::string& err);

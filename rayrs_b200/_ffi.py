@@ -20,6 +20,8 @@ RRS_REF_EMPTY = 0xFFFFFFFF
 RRS_FLAG_COUNT_TRAVERSAL = 1
 RRS_FLAG_TIME_PHASES = 2
 RRS_FLAG_SPLIT_KERNELS = 4
+RRS_FLAG_FORCE_QUEUES = 8
+RRS_FLAG_FORCE_PATHLOOP = 16
 
 
 class RrsPrim(C.Structure):

@@ -70,6 +70,32 @@ __global__ void k_plan(DCounters* c) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Camera::generate_primary_ray (lib.rs:202-210) for padded path index p.  Paths are numbered
+// sample-major over 8x4 pixel tiles (one tile per 32 consecutive indices), so a warp that takes 32
+// consecutive indices starts coherent.
+// ---------------------------------------------------------------------------------------
+template <bool EXACT_TILES>
+__device__ __forceinline__ bool primary_ray(const RenderConst& rc, unsigned long long p, uint32_t& pixel, uint32_t& sample,
+                                            float3& d) {
+    const uint32_t s_local = (uint32_t)(p / rc.npix_pad);
+    const uint32_t pq = (uint32_t)(p - (unsigned long long)s_local * rc.npix_pad);
+    const uint32_t tile = pq >> 5, l = pq & 31u;
+    const uint32_t ty = tile / rc.tiles_x, tx = tile - ty * rc.tiles_x;
+    const uint32_t col = tx * 8u + (l & 7u);
+    const uint32_t row = ty * 4u + (l >> 3);
+    if (!EXACT_TILES && !(col < rc.cam.W && row < rc.cam.H)) return false;
+    pixel = row * rc.cam.W + col;
+    sample = rc.sample_offset + s_local;
+    float4 u = rng_uniforms(rc.seed, pixel, sample, 0u);
+    // rayrs/src/main.rs:71-76: camera indices are (H - row, W - col)   
+    float fi = (float)(rc.cam.H - row), fj = (float)(rc.cam.W - col);
+    float x = (fj + u.x) * rc.cam.inv_ppc - rc.cam.half_w;
+    float y = (fi + u.y) * rc.cam.inv_ppc - rc.cam.half_h;
+    d = add3(add3(rc.cam.z, scale3(rc.cam.e_x, x)), scale3(rc.cam.e_y, y));
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------
 // generate: refill stripe b behind its survivors with new primary rays
 // ---------------------------------------------------------------------------------------
 template <bool EXACT_TILES>
@@ -104,17 +130,9 @@ __device__ __forceinline__ void phase_generate(const RenderConst& rc, DCounters*
     const uint32_t got_pad = (got + 31u) & ~31u;
     for (uint32_t k = threadIdx.x; k < got_pad; k += blockDim.x) {
         bool valid = k < got;
-        uint32_t row = 0, col = 0, s_local = 0;
-        if (valid) {
-            unsigned long long p = first + k;
-            s_local = (uint32_t)(p / rc.npix_pad);
-            uint32_t pq = (uint32_t)(p - (unsigned long long)s_local * rc.npix_pad);
-            uint32_t tile = pq >> 5, l = pq & 31u;
-            uint32_t ty = tile / rc.tiles_x, tx = tile - ty * rc.tiles_x;
-            col = tx * 8u + (l & 7u);
-            row = ty * 4u + (l >> 3);
-            if (!EXACT_TILES) valid = col < rc.cam.W && row < rc.cam.H;
-        }
+        uint32_t pixel = 0, sample = 0;
+        float3 d = f3(0.f, 0.f, 0.f);
+        if (valid) valid = primary_ray<EXACT_TILES>(rc, first + k, pixel, sample, d);
         uint32_t slot;
         if (EXACT_TILES) {
             slot = n0 + k;
@@ -126,14 +144,6 @@ __device__ __forceinline__ void phase_generate(const RenderConst& rc, DCounters*
             slot = base + __popc(ballot & ((1u << lane) - 1u));
         }
         if (!valid) continue;
-        uint32_t pixel = row * rc.cam.W + col;
-        uint32_t sample = rc.sample_offset + s_local;
-        float4 u = rng_uniforms(rc.seed, pixel, sample, 0u);
-        // rayrs/src/main.rs:71-76: camera indices are (H - row, W - col)   
-        float fi = (float)(rc.cam.H - row), fj = (float)(rc.cam.W - col);
-        float x = (fj + u.x) * rc.cam.inv_ppc - rc.cam.half_w;
-        float y = (fi + u.y) * rc.cam.inv_ppc - rc.cam.half_h;
-        float3 d = add3(add3(rc.cam.z, scale3(rc.cam.e_x, x)), scale3(rc.cam.e_y, y));
         ray_o[slot] = make_float4(rc.cam.origin.x, rc.cam.origin.y, rc.cam.origin.z, __uint_as_float(RRS_NO_PRIM));
         ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
         state[slot] = make_float4(1.f, 1.f, 1.f, __uint_as_float(sample << 8));
@@ -276,6 +286,117 @@ __global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DCounters* __restr
 }
 
 // ---------------------------------------------------------------------------------------
+// One path vertex: Material::evaluate + emission + Russian roulette (lib.rs:532-551) for a ray that hit
+// `prim` at distance t.  Shared by the queue-based shade phase and the register-resident path loop.
+// ---------------------------------------------------------------------------------------
+struct NextRay {
+    bool alive, carry64;
+    float4 no, nd, ns;           // origin + origin word, direction + pixel, throughput + (sample << 8 | bounce)
+    double p64x, p64y, p64z;     // f64 hit point (transmissive spheres)
+};
+
+template <bool SPH64>
+__device__ __forceinline__ NextRay shade_hit(const DScene& sc, const RenderConst& rc, float4* __restrict__ accum, float2 h,
+                                             float4 o4, float4 d4, float4 st, const double* o64_in) {
+    NextRay nr;
+    nr.alive = false;
+    nr.carry64 = false;
+    nr.p64x = nr.p64y = nr.p64z = 0.;
+    bool& alive = nr.alive;
+    bool& carry64 = nr.carry64;
+    float4 &no = nr.no, &nd = nr.nd, &ns = nr.ns;
+    double &p64x = nr.p64x, &p64y = nr.p64y, &p64z = nr.p64z;
+    uint32_t prim = __float_as_uint(h.y);
+    uint32_t pixel = __float_as_uint(d4.w);
+    uint32_t sb = __float_as_uint(st.w);
+    uint32_t bounce = sb & 0xFFu, sample = sb >> 8;
+    float3 thr = xyz(st);
+    float3 o = xyz(o4), d = xyz(d4);
+    const float4* pp = reinterpret_cast<const float4*>(sc.prims + prim);
+    float4 a = __ldg(pp);
+    const float4* mp = reinterpret_cast<const float4*>(sc.mats + prim_material(a));
+    DMat m;
+    m.m0 = __ldg(mp);
+    float3 pos, nrm;
+    const uint32_t mtag = __float_as_uint(m.m0.w);
+    const bool transmissive = mtag == RRS_MAT_REFRACT || mtag == RRS_MAT_GLASS ||
+                              mtag == RRS_MAT_COOK_TORRANCE_REFRACT || mtag == RRS_MAT_COOK_TORRANCE_GLASS;
+    if (SPH64 && sc.sphere64 != nullptr && prim_type(a) == RRS_SPHERE && transmissive) {
+        // hit point on a transmissive sphere in the reference's f64 arithmetic
+        // (intersect.cuh, "sphere re-entry"): Sphere::intersect, Ray::point, Sphere::normal
+        const uint32_t ow = __float_as_uint(o4.w);
+        double ox = o.x, oy = o.y, oz = o.z;
+        if (ow != RRS_NO_PRIM && (ow & RRS_ORG64) && o64_in) {
+            ox = o64_in[0]; oy = o64_in[1]; oz = o64_in[2];
+        }
+        double dx = d.x, dy = d.y, dz = d.z;
+        if (ow == RRS_NO_PRIM) {
+            // primary ray: Camera::generate_primary_ray (lib.rs:202-210) in f64.  The loss
+            // probability of the re-entry quirk depends on the f64 rounding of the FIRST hit,
+            // and an fp32-exact direction makes that arithmetic atypically exact (measured:
+            // 81 % instead of 71 % for the outer spheres), so the direction is rebuilt here.
+            const RrsCamera& c64 = rc.cam64;
+            uint32_t row = pixel / rc.cam.W, col = pixel - row * rc.cam.W;
+            float4 u0 = rng_uniforms(rc.seed, pixel, sample, 0u);
+            double fj = (double)(rc.cam.W - col), fi = (double)(rc.cam.H - row), ppc = (double)c64.ppc;
+            double x = __dsub_rn(__ddiv_rn(__dadd_rn(fj, (double)u0.x), ppc), __ddiv_rn(c64.width, 2.));
+            double y = __dsub_rn(__ddiv_rn(__dadd_rn(fi, (double)u0.y), ppc), __ddiv_rn(c64.height, 2.));
+            dx = __dadd_rn(__dadd_rn(c64.z_scaled[0], __dmul_rn(x, c64.e_x[0])), __dmul_rn(y, c64.e_y[0]));
+            dy = __dadd_rn(__dadd_rn(c64.z_scaled[1], __dmul_rn(x, c64.e_x[1])), __dmul_rn(y, c64.e_y[1]));
+            dz = __dadd_rn(__dadd_rn(c64.z_scaled[2], __dmul_rn(x, c64.e_x[2])), __dmul_rn(y, c64.e_y[2]));
+            ox = c64.origin[0]; oy = c64.origin[1]; oz = c64.origin[2];
+        }
+        double4 s64 = sc.sphere64[__float_as_uint(__ldg(pp + 1).y)];
+        double t64;
+        bool ok = sphere_intersect64(s64, ox, oy, oz, dx, dy, dz, t64);
+        if (!ok || fabs(t64 - (double)h.x) > 1e-3 * (double)h.x) t64 = (double)h.x;  // rim: keep the fp32 root
+        p64x = __dadd_rn(ox, __dmul_rn(dx, t64));
+        p64y = __dadd_rn(oy, __dmul_rn(dy, t64));
+        p64z = __dadd_rn(oz, __dmul_rn(dz, t64));
+        double nx = __dsub_rn(p64x, s64.x), ny = __dsub_rn(p64y, s64.y), nz = __dsub_rn(p64z, s64.z);
+        double inv = 1. / sqrt(dot64(nx, ny, nz, nx, ny, nz));
+        nrm = f3((float)(nx * inv), (float)(ny * inv), (float)(nz * inv));
+        pos = f3((float)p64x, (float)p64y, (float)p64z);
+        carry64 = true;
+    } else {
+        pos = madd3(d, h.x, o);  // Ray::point lib.rs:41-43
+        nrm = prim_normal(sc.prims, prim, a, pos);
+    }
+    float3 view = normalize3(neg3(d));
+    float4 u = rng_uniforms(rc.seed, pixel, sample, bounce + 1u);
+    m.m1 = __ldg(mp + 1);
+    m.m2 = __ldg(mp + 2);
+    ScatterOut so = material_evaluate(m, nrm, view, u.x, u.y, u.z);
+    bool finished = true;
+    if (so.scatter) {
+        // lib.rs:533-547
+        int emi = __float_as_int(__ldg(pp + 2).w);
+        if (emi >= 0) {
+            float4 e = __ldg(sc.emis + emi);
+            atomicAdd(accum + pixel, make_float4(thr.x * e.x, thr.y * e.y, thr.z * e.z, 0.f));
+        }
+        thr = mul3(thr, so.color);
+        float p = fmaxf(fmaxf(thr.x, thr.y), thr.z);
+        if (!(u.w > p) && bounce + 1u < rc.max_bounces) {
+            thr = f3(thr.x / p, thr.y / p, thr.z / p);
+            finished = false;
+            alive = true;
+            no = make_float4(pos.x, pos.y, pos.z, __uint_as_float(carry64 ? (prim | RRS_ORG64) : prim));
+            nd = make_float4(so.dir.x, so.dir.y, so.dir.z, d4.w);
+            ns = make_float4(thr.x, thr.y, thr.z, __uint_as_float((sample << 8) | (bounce + 1u)));
+        }
+    }
+    if (finished) atomicAdd(accum + pixel, make_float4(0.f, 0.f, 0.f, 1.f));
+    return nr;
+}
+
+// lib.rs:552-556: light + throughput * background(direction)
+__device__ __forceinline__ void shade_miss(const DScene& sc, float4* __restrict__ accum, float4 d4, float4 st) {
+    float3 bg = background(sc, xyz(d4));
+    atomicAdd(accum + __float_as_uint(d4.w), make_float4(st.x * bg.x, st.y * bg.y, st.z * bg.z, 1.f));
+}
+
+// ---------------------------------------------------------------------------------------
 // shade: Material::evaluate + Russian roulette + background for stripe b of queue `cur`;
 // survivors are compacted into stripe b of the other queue
 // ---------------------------------------------------------------------------------------
@@ -301,101 +422,20 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= n) break;
         uint32_t i = base + lane;
-        bool alive = false, carry64 = false;
-        float4 no, nd, ns;
-        double p64x = 0., p64y = 0., p64z = 0.;
+        NextRay nr;
+        nr.alive = false;
+        nr.carry64 = false;
         if (i < n) {
             float2 h = hits[i];
             float4 o4 = ray_o[i], d4 = ray_d[i], st = state[i];
-            uint32_t prim = __float_as_uint(h.y);
-            uint32_t pixel = __float_as_uint(d4.w);
-            uint32_t sb = __float_as_uint(st.w);
-            uint32_t bounce = sb & 0xFFu, sample = sb >> 8;
-            float3 thr = xyz(st);
-            float3 o = xyz(o4), d = xyz(d4);
-            if (prim == RRS_NO_PRIM) {
-                // lib.rs:552-556: light + throughput * background(direction)
-                float3 bg = background(sc, d);
-                atomicAdd(accum + pixel, make_float4(thr.x * bg.x, thr.y * bg.y, thr.z * bg.z, 1.f));
+            if (__float_as_uint(h.y) == RRS_NO_PRIM) {
+                shade_miss(sc, accum, d4, st);
             } else {
-                const float4* pp = reinterpret_cast<const float4*>(sc.prims + prim);
-                float4 a = __ldg(pp);
-                const float4* mp = reinterpret_cast<const float4*>(sc.mats + prim_material(a));
-                DMat m;
-                m.m0 = __ldg(mp);
-                float3 pos, nrm;
-                const uint32_t mtag = __float_as_uint(m.m0.w);
-                const bool transmissive = mtag == RRS_MAT_REFRACT || mtag == RRS_MAT_GLASS ||
-                                          mtag == RRS_MAT_COOK_TORRANCE_REFRACT || mtag == RRS_MAT_COOK_TORRANCE_GLASS;
-                if (SPH64 && sc.sphere64 != nullptr && prim_type(a) == RRS_SPHERE && transmissive) {
-                    // hit point on a transmissive sphere in the reference's f64 arithmetic
-                    // (intersect.cuh, "sphere re-entry"): Sphere::intersect, Ray::point, Sphere::normal
-                    const uint32_t ow = __float_as_uint(o4.w);
-                    double ox = o.x, oy = o.y, oz = o.z;
-                    if (ow != RRS_NO_PRIM && (ow & RRS_ORG64) && q.org64) {
-                        const double* o64 = q.org64 + 3 * (off + i);
-                        ox = o64[0]; oy = o64[1]; oz = o64[2];
-                    }
-                    double dx = d.x, dy = d.y, dz = d.z;
-                    if (ow == RRS_NO_PRIM) {
-                        // primary ray: Camera::generate_primary_ray (lib.rs:202-210) in f64.  The loss
-                        // probability of the re-entry quirk depends on the f64 rounding of the FIRST hit,
-                        // and an fp32-exact direction makes that arithmetic atypically exact (measured:
-                        // 81 % instead of 71 % for the outer spheres), so the direction is rebuilt here.
-                        const RrsCamera& c64 = rc.cam64;
-                        uint32_t row = pixel / rc.cam.W, col = pixel - row * rc.cam.W;
-                        float4 u0 = rng_uniforms(rc.seed, pixel, sample, 0u);
-                        double fj = (double)(rc.cam.W - col), fi = (double)(rc.cam.H - row), ppc = (double)c64.ppc;
-                        double x = __dsub_rn(__ddiv_rn(__dadd_rn(fj, (double)u0.x), ppc), __ddiv_rn(c64.width, 2.));
-                        double y = __dsub_rn(__ddiv_rn(__dadd_rn(fi, (double)u0.y), ppc), __ddiv_rn(c64.height, 2.));
-                        dx = __dadd_rn(__dadd_rn(c64.z_scaled[0], __dmul_rn(x, c64.e_x[0])), __dmul_rn(y, c64.e_y[0]));
-                        dy = __dadd_rn(__dadd_rn(c64.z_scaled[1], __dmul_rn(x, c64.e_x[1])), __dmul_rn(y, c64.e_y[1]));
-                        dz = __dadd_rn(__dadd_rn(c64.z_scaled[2], __dmul_rn(x, c64.e_x[2])), __dmul_rn(y, c64.e_y[2]));
-                        ox = c64.origin[0]; oy = c64.origin[1]; oz = c64.origin[2];
-                    }
-                    double4 s64 = sc.sphere64[__float_as_uint(__ldg(pp + 1).y)];
-                    double t64;
-                    bool ok = sphere_intersect64(s64, ox, oy, oz, dx, dy, dz, t64);
-                    if (!ok || fabs(t64 - (double)h.x) > 1e-3 * (double)h.x) t64 = (double)h.x;  // rim: keep the fp32 root
-                    p64x = __dadd_rn(ox, __dmul_rn(dx, t64));
-                    p64y = __dadd_rn(oy, __dmul_rn(dy, t64));
-                    p64z = __dadd_rn(oz, __dmul_rn(dz, t64));
-                    double nx = __dsub_rn(p64x, s64.x), ny = __dsub_rn(p64y, s64.y), nz = __dsub_rn(p64z, s64.z);
-                    double inv = 1. / sqrt(dot64(nx, ny, nz, nx, ny, nz));
-                    nrm = f3((float)(nx * inv), (float)(ny * inv), (float)(nz * inv));
-                    pos = f3((float)p64x, (float)p64y, (float)p64z);
-                    carry64 = true;
-                } else {
-                    pos = madd3(d, h.x, o);  // Ray::point lib.rs:41-43
-                    nrm = prim_normal(sc.prims, prim, a, pos);
-                }
-                float3 view = normalize3(neg3(d));
-                float4 u = rng_uniforms(rc.seed, pixel, sample, bounce + 1u);
-                m.m1 = __ldg(mp + 1);
-                m.m2 = __ldg(mp + 2);
-                ScatterOut so = material_evaluate(m, nrm, view, u.x, u.y, u.z);
-                bool finished = true;
-                if (so.scatter) {
-                    // lib.rs:533-547
-                    int emi = __float_as_int(__ldg(pp + 2).w);
-                    if (emi >= 0) {
-                        float4 e = __ldg(sc.emis + emi);
-                        atomicAdd(accum + pixel, make_float4(thr.x * e.x, thr.y * e.y, thr.z * e.z, 0.f));
-                    }
-                    thr = mul3(thr, so.color);
-                    float p = fmaxf(fmaxf(thr.x, thr.y), thr.z);
-                    if (!(u.w > p) && bounce + 1u < rc.max_bounces) {
-                        thr = f3(thr.x / p, thr.y / p, thr.z / p);
-                        finished = false;
-                        alive = true;
-                        no = make_float4(pos.x, pos.y, pos.z, __uint_as_float(carry64 ? (prim | RRS_ORG64) : prim));
-                        nd = make_float4(so.dir.x, so.dir.y, so.dir.z, d4.w);
-                        ns = make_float4(thr.x, thr.y, thr.z, __uint_as_float((sample << 8) | (bounce + 1u)));
-                    }
-                }
-                if (finished) atomicAdd(accum + pixel, make_float4(0.f, 0.f, 0.f, 1.f));
+                const double* o64 = (SPH64 && q.org64) ? q.org64 + 3 * (off + i) : nullptr;
+                nr = shade_hit<SPH64>(sc, rc, accum, h, o4, d4, st, o64);
             }
         }
+        const bool alive = nr.alive;
         // queue compaction: survivors of this warp take consecutive slots of the stripe
         uint32_t ballot = __ballot_sync(0xFFFFFFFFu, alive);
         if (ballot) {
@@ -404,12 +444,12 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
             obase = __shfl_sync(0xFFFFFFFFu, obase, 0);
             if (alive) {
                 uint32_t slot = obase + __popc(ballot & ((1u << lane) - 1u));
-                out_o[slot] = no;
-                out_d[slot] = nd;
-                out_state[slot] = ns;
-                if (SPH64 && carry64 && q.org64) {
+                out_o[slot] = nr.no;
+                out_d[slot] = nr.nd;
+                out_state[slot] = nr.ns;
+                if (SPH64 && nr.carry64 && q.org64) {
                     double* o64 = q.org64 + 3 * (ooff + slot);
-                    o64[0] = p64x; o64[1] = p64y; o64[2] = p64z;
+                    o64[0] = nr.p64x; o64[1] = nr.p64y; o64[2] = nr.p64z;
                 }
             }
         }
@@ -500,6 +540,104 @@ __global__ void __launch_bounds__(kBlock, SPH64 ? RRS_BLOCKS_PER_SM_F64 : RRS_BL
         atomicAdd(&c->cyc_extend, s_u64[2]);
         atomicAdd(&c->cyc_shade, s_u64[3]);
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Register-resident path loop for small scenes (brute_count > 0: every sphere-series configuration).
+// When the whole scene sits in 512 bytes of shared memory and a closest-hit query is a fixed 8-primitive
+// loop, the HBM queues buy nothing: there is no long, divergent traversal to separate from shading, yet
+// every ray still paid a 48-byte write, an 88-byte read-back, a hit record and two compaction passes
+// (170 B/ray of DRAM traffic and ~45 % of DRAM bandwidth on the sphere series,
+// profiles/r01b_c2_fused_metrics.csv).  Here a lane keeps ITS path in registers — generate, intersect,
+// shade, next bounce — and takes a new path index the moment its path ends (path regeneration), so the
+// warp stays full without any queue.  Same paths as the wavefront form (the RNG is keyed by pixel,
+// sample and bounce), same accumulator, same census.  Warps claim path indices in chunks of 1024 from the
+// global cursor (one global atomic per chunk) and hand them to their dead lanes by ballot/popc.
+// ---------------------------------------------------------------------------------------
+template <bool EXACT_TILES, bool COUNT, bool SPH64>
+__global__ void __launch_bounds__(kBlock, SPH64 ? RRS_BLOCKS_PER_SM_F64 : RRS_BLOCKS_PER_SM)
+k_pathloop(DScene sc, RenderConst rc, DCounters* __restrict__ c, float4* __restrict__ accum) {
+    const uint32_t FULL = 0xFFFFFFFFu;
+    __shared__ DPrim s_prims[RRS_BRUTE_MAX];
+    stage_brute_prims(sc, s_prims);
+    __syncthreads();
+    const uint32_t lane = lane_id();
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const unsigned long long total = c->total_paths;
+    unsigned long long w_next = 0, w_end = 0;  // this warp's claimed path range (warp-uniform)
+    bool exhausted = false;                    // the global cursor has run past the end (warp-uniform)
+    bool alive = false;
+    float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = o4, st = o4;
+    double o64[3] = {0., 0., 0.};
+    TravCounters cnt{0, 0};
+    unsigned long long rays = 0, iters = 0;
+    for (;;) {
+        // ---- regenerate: dead lanes take the next path indices of the warp's range ----
+        uint32_t dead = __ballot_sync(FULL, !alive);
+        if (dead && !exhausted) {
+            if (w_next >= w_end) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&c->next_path, 1024ull);
+                base = __shfl_sync(FULL, base, 0);
+                w_next = base;
+                w_end = base + 1024ull < total ? base + 1024ull : total;
+                if (base >= total) {
+                    exhausted = true;
+                    w_end = w_next = 0;
+                }
+            }
+            if (!exhausted) {
+                const unsigned long long p = w_next + (unsigned long long)__popc(dead & lt_mask);
+                if (!alive && p < w_end) {
+                    uint32_t pixel = 0, sample = 0;
+                    float3 d;
+                    if (primary_ray<EXACT_TILES>(rc, p, pixel, sample, d)) {
+                        o4 = make_float4(rc.cam.origin.x, rc.cam.origin.y, rc.cam.origin.z, __uint_as_float(RRS_NO_PRIM));
+                        d4 = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
+                        st = make_float4(1.f, 1.f, 1.f, __uint_as_float(sample << 8));
+                        alive = true;
+                    }
+                }
+                w_next += (unsigned long long)__popc(dead);
+                if (w_next > w_end) w_next = w_end;
+            }
+        }
+        if (__ballot_sync(FULL, alive) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        ++iters;
+        if (alive) {
+            // ---- extend ----
+            float2 h;
+            uint32_t prim;
+            closest_hit_brute<COUNT, SPH64>(sc, s_prims, xyz(o4), xyz(d4), __float_as_uint(o4.w), SPH64 ? o64 : nullptr, h.x, prim, cnt);
+            h.y = __uint_as_float(prim);
+            ++rays;
+            // ---- shade ----
+            if (prim == RRS_NO_PRIM) {
+                shade_miss(sc, accum, d4, st);
+                alive = false;
+            } else {
+                NextRay nr = shade_hit<SPH64>(sc, rc, accum, h, o4, d4, st, SPH64 ? o64 : nullptr);
+                alive = nr.alive;
+                if (alive) {
+                    o4 = nr.no;
+                    d4 = nr.nd;
+                    st = nr.ns;
+                    if (SPH64 && nr.carry64) {
+                        o64[0] = nr.p64x; o64[1] = nr.p64y; o64[2] = nr.p64z;
+                    }
+                }
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(FULL, rays, o);
+    if (lane == 0) {
+        atomicAdd(&c->rays, rays);
+        atomicMax(&c->iterations, iters);
+    }
+    flush_trav_counters<COUNT>(c, cnt);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -695,6 +833,16 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     const bool sph64 = s->sphere64 != nullptr;
     auto extend_fn = sph64 ? (count ? k_extend<true, true> : k_extend<false, true>) : (count ? k_extend<true, false> : k_extend<false, false>);
     auto shade_fn = sph64 ? k_shade<true> : k_shade<false>;
+    typedef void (*PathFn)(DScene, RenderConst, DCounters*, float4*);
+    PathFn path_fn;
+    {
+        const int sel = (exact_tiles ? 4 : 0) | (count ? 2 : 0) | (sph64 ? 1 : 0);
+        static const PathFn ptable[8] = {k_pathloop<false, false, false>, k_pathloop<false, false, true>,
+                                         k_pathloop<false, true, false>,  k_pathloop<false, true, true>,
+                                         k_pathloop<true, false, false>,  k_pathloop<true, false, true>,
+                                         k_pathloop<true, true, false>,   k_pathloop<true, true, true>};
+        path_fn = ptable[sel];
+    }
     typedef void (*FusedFn)(DScene, RenderConst, DCounters*, QueueSet, float4*);
     FusedFn fused_fn;
     {
@@ -766,7 +914,20 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     uint64_t launches = 0, iters = 0;
     std::vector<size_t> phase_ev;  // indices of per-iteration event groups
     const bool split = (p->flags & RRS_FLAG_SPLIT_KERNELS) != 0;
-    if (!split) {
+    // measured (gpurun_out/sweep_pathloop.log): +16 % on the opaque sphere series, but -10 % on the frosted-glass
+    // series, whose f64 re-entry arithmetic diverges harder inside one long-lived loop than in the queued shade phase
+    const bool want_pathloop = (p->flags & RRS_FLAG_FORCE_PATHLOOP) || !sph64;
+    const bool pathloop = !split && s->d.brute_count > 0 && want_pathloop && !(p->flags & RRS_FLAG_FORCE_QUEUES);
+    if (pathloop) {
+        // small scene: register-resident paths, no queues (k_pathloop)
+        int occ_path = 0;
+        RRS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_path, path_fn, kBlock, 0), err);
+        path_fn<<<(uint32_t)s->num_sms * (uint32_t)std::max(occ_path, 1), kBlock, 0, stream>>>(s->d, rc, w.counters, d_accum);
+        launches = 1;
+        RRS_CUDA_CHECK(cudaGetLastError(), err);
+        RRS_CUDA_CHECK(cudaMemcpyAsync(w.h_counters, w.counters, sizeof(DCounters), cudaMemcpyDeviceToHost, stream), err);
+        RRS_CUDA_CHECK(cudaStreamSynchronize(stream), err);
+    } else if (!split) {
         // one persistent launch for the whole render
         fused_fn<<<regions, kBlock, smem, stream>>>(s->d, rc, w.counters, q, d_accum);
         launches = 1;

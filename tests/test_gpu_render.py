@@ -133,12 +133,14 @@ def test_shapes_queues_and_limits(hdri_small):
     assert relrmse(base, ref) < 5e-3
     rays0 = sc.stats()["rays"]
     for q in (1024, 4096, 1 << 16):
-        for flags in (0, api._ffi.RRS_FLAG_SPLIT_KERNELS, api._ffi.RRS_FLAG_SPLIT_KERNELS | api._ffi.RRS_FLAG_TIME_PHASES):
+        for flags in (0, api._ffi.RRS_FLAG_FORCE_QUEUES, api._ffi.RRS_FLAG_SPLIT_KERNELS,
+                      api._ffi.RRS_FLAG_SPLIT_KERNELS | api._ffi.RRS_FLAG_TIME_PHASES):
             img = api.render_gpu(cam, sc, 40, 50, queue_capacity=q, flags=flags).astype(np.float64)
             st = sc.stats()
             assert st["rays"] == rays0                      # the set of paths does not depend on queue size / kernel form
             assert np.allclose(img, base, rtol=2e-5, atol=1e-6)  # only the fp32 summation order differs
-            assert st["kernel_launches"] == (2 if flags == 0 else st["kernel_launches"])  # fused: 1 render + 1 resolve
+            if flags in (0, api._ffi.RRS_FLAG_FORCE_QUEUES):
+                assert st["kernel_launches"] == 2  # path loop / fused wavefront: 1 render + 1 resolve
     # depth limits: max_bounces = 1 traces exactly one ray per path; 0 renders black (lib.rs:525,559)
     for mb in (1, 2, 3):
         img = api.render_gpu(cam, sc, 8, mb).astype(np.float64)
@@ -191,3 +193,25 @@ def test_sample_split_accumulate_and_census(hdri_small):
     ref, _ = osc.render(cam.derived17(), W, H, spp)
     assert relrmse(a[..., :3] / spp, ref) < 5e-3
     sc.close()
+
+
+def test_path_loop_and_queues_trace_the_same_paths(hdri_small):
+    """Small scenes render with the register-resident path loop (k_pathloop), transmissive ones with the queued
+    wavefront kernel by default; both forms must trace the same set of paths (same ray count) and agree up to the
+    fp32 summation order."""
+    F = api._ffi
+    for builder, a, b in ((lambda: scenes.cook_torrance_spheres_plastic(120, 48), 0, F.RRS_FLAG_FORCE_QUEUES),
+                          (lambda: scenes.diffuse_single_sphere(96, 64), 0, F.RRS_FLAG_FORCE_QUEUES),
+                          (lambda: scenes.cook_torrance_spheres_frosted_glass(120, 40), F.RRS_FLAG_FORCE_PATHLOOP, 0),
+                          (lambda: scenes.glass_single_sphere(96, 64), F.RRS_FLAG_FORCE_PATHLOOP, F.RRS_FLAG_FORCE_QUEUES)):
+        spec = builder()
+        sc = spec.scene(hdri_small, with_f64=False)
+        cam = spec.camera()
+        img_a = api.render_gpu(cam, sc, 24, 50, flags=a).astype(np.float64)
+        st_a = sc.stats()
+        img_b = api.render_gpu(cam, sc, 24, 50, flags=b).astype(np.float64)
+        st_b = sc.stats()
+        assert st_a["rays"] == st_b["rays"] and st_a["paths"] == st_b["paths"]
+        assert st_a["kernel_launches"] == st_b["kernel_launches"] == 2
+        assert np.allclose(img_a, img_b, rtol=2e-5, atol=1e-6)
+        sc.close()

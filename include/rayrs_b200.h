@@ -190,7 +190,12 @@ typedef struct RrsStats {
     double generate_ms;
     uint64_t nodes_visited;   /* only with RRS_FLAG_COUNT_TRAVERSAL */
     uint64_t prims_tested;
+    uint64_t kernel_form;     /* RRS_FORM_*: which render kernel the last render used */
 } RrsStats;
+
+#define RRS_FORM_WAVEFRONT 0u /* fused persistent wavefront kernel, ray/hit queues in HBM (k_wavefront) */
+#define RRS_FORM_SPLIT 1u     /* one generate/extend/shade launch per iteration (RRS_FLAG_SPLIT_KERNELS) */
+#define RRS_FORM_PATHLOOP 2u  /* small scene: register-resident path loop, no queues (k_pathloop) */
 
 #define RRS_FLAG_COUNT_TRAVERSAL 1u /* count nodes/primitives touched (slower; for the bytes/ray model) */
 #define RRS_FLAG_TIME_PHASES 2u     /* split kernels only: CUDA-event time every phase launch */

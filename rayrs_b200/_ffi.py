@@ -77,7 +77,11 @@ class RrsStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("iterations", C.c_uint64), ("nan_pixels", C.c_uint64), ("negative_pixels", C.c_uint64),
                 ("device_ms", C.c_double), ("extend_ms", C.c_double), ("shade_ms", C.c_double),
-                ("generate_ms", C.c_double), ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64)]
+                ("generate_ms", C.c_double), ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64),
+                ("kernel_form", C.c_uint64)]
+
+
+RRS_FORM_WAVEFRONT, RRS_FORM_SPLIT, RRS_FORM_PATHLOOP = 0, 1, 2
 
 
 # every symbol include/rayrs_b200.h declares: (name, restype, argtypes)

@@ -978,6 +978,7 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     st.kernel_launches = launches;
     st.iterations = iters;
     st.device_ms = ms;
+    st.kernel_form = pathloop ? RRS_FORM_PATHLOOP : (split ? RRS_FORM_SPLIT : RRS_FORM_WAVEFRONT);
     st.nodes_visited = w.h_counters->nodes_visited;
     st.prims_tested = w.h_counters->prims_tested;
     st.generate_ms = st.extend_ms = st.shade_ms = 0.;

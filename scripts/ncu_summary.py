@@ -90,11 +90,41 @@ def metrics(rep: Path, out_csv: Path, out_stalls: Path):
     print(out_stalls.read_text())
 
 
+def update_model(metrics_csv: Path, key: str):
+    """Copy the measured per-launch DRAM traffic and the pipe / issue evidence of the profiled kernel into
+    profiles/bytes_per_ray.json[key]["ncu"], where bench.py picks up roofline.traffic."""
+    import json
+    rows = {r[0]: r for r in csv.reader(metrics_csv.open())}
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def mean(name, scale=False):
+        r = rows[name]
+        vals = [float(x) for x in r[2:]]
+        return (sum(vals) / len(vals)) * (unit[r[1]] if scale else 1.0)
+    model_path = ROOT / "profiles" / "bytes_per_ray.json"
+    model = json.loads(model_path.read_text())
+    model[key]["ncu"] = {
+        "dram_bytes_per_launch": mean("dram__bytes_read.sum", True) + mean("dram__bytes_write.sum", True),
+        "kernel": rows["metric"][2].strip('"'),
+        "launch_ms_under_ncu": mean("gpu__time_duration.sum"),
+        "issue_active_pct": mean("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        "alu_pipe_pct": mean("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+        "fma_pipe_pct": mean("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+        "xu_pipe_pct": mean("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+        "lanes_per_instruction": mean("smsp__thread_inst_executed_per_inst_executed.ratio"),
+        "dram_pct_of_peak": mean("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+        "source": f"profiles/{metrics_csv.name}",
+    }
+    model_path.write_text(json.dumps(model, indent=1) + "\n")
+    print("updated", model_path, key, model[key]["ncu"])
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("tag")
     ap.add_argument("--launches", default=str(ROOT / "gpurun_out" / "launches.csv"))
     ap.add_argument("--rep", default=str(ROOT / "gpurun_out" / "prof.ncu-rep"))
+    ap.add_argument("--model-key", default="", help="c1..c5: also record the capture in profiles/bytes_per_ray.json")
     a = ap.parse_args()
     prof = ROOT / "profiles"
     prof.mkdir(exist_ok=True)
@@ -102,3 +132,5 @@ if __name__ == "__main__":
         launches(Path(a.launches), prof / f"{a.tag}_launches.csv")
     if Path(a.rep).exists():
         metrics(Path(a.rep), prof / f"{a.tag}_metrics.csv", prof / f"{a.tag}_stalls.txt")
+        if a.model_key:
+            update_model(prof / f"{a.tag}_metrics.csv", a.model_key)

@@ -38,6 +38,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_ffi.RrsPrim) == 88
     assert C.sizeof(_ffi.RrsRay) == 48
     assert C.sizeof(_ffi.RrsMaterial) == 72
+    assert C.sizeof(_ffi.RrsStats) == 104
 
 
 def test_abi_version_and_error_channel():

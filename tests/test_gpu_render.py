@@ -212,6 +212,7 @@ def test_path_loop_and_queues_trace_the_same_paths(hdri_small):
         img_b = api.render_gpu(cam, sc, 24, 50, flags=b).astype(np.float64)
         st_b = sc.stats()
         assert st_a["rays"] == st_b["rays"] and st_a["paths"] == st_b["paths"]
+        assert {st_a["kernel_form"], st_b["kernel_form"]} == {F.RRS_FORM_PATHLOOP, F.RRS_FORM_WAVEFRONT}
         assert st_a["kernel_launches"] == st_b["kernel_launches"] == 2
         assert np.allclose(img_a, img_b, rtol=2e-5, atol=1e-6)
         sc.close()

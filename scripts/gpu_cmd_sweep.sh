@@ -1,2 +1,1 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python scripts/gpu_dev.py c3 | grep -v "scene build"
+python -m pytest tests/test_gpu_render.py -m gpu -x -q -s -k "full_size_config" 2>&1 | tail -25

@@ -49,9 +49,16 @@ SCENES = {
 }
 
 
+# sphere scenes take the brute-force small-scene path by default; "+bvh" runs the same scene through the
+# BVH traversal (RRS_NO_BRUTE is read at scene creation), which is what a ninth primitive would switch on
+SCENES.update({k + "+bvh": v for k, v in list(SCENES.items()) if k in ("diffuse_single_sphere", "spheres_metallic", "material_test")})
+
+
 @pytest.mark.parametrize("name", sorted(SCENES))
-def test_ids_and_t_against_oracle(name, hdri_small):
+def test_ids_and_t_against_oracle(name, hdri_small, monkeypatch):
     spec = SCENES[name]()
+    if name.endswith("+bvh"):
+        monkeypatch.setenv("RRS_NO_BRUTE", "1")
     sc = spec.scene(hdri_small)
     osc = oracle.OracleScene(spec.tables(), hdri_small.pixels, heuristic=(spec.heuristic.kind, spec.heuristic.splits), build_mode=1)
     rays = fixed_ray_set(spec, osc, N_RAYS)

@@ -216,3 +216,74 @@ def test_path_loop_and_queues_trace_the_same_paths(hdri_small):
         assert st_a["kernel_launches"] == st_b["kernel_launches"] == 2
         assert np.allclose(img_a, img_b, rtol=2e-5, atol=1e-6)
         sc.close()
+
+
+def _block_mean_with_f8_shift(img, k):
+    """Average k x k blocks of a full-size image so that block (r, c) covers the film area of pixel (r, c) of the
+    same view rendered k times smaller.  The camera index of pixel row r is H - r, so low-res
+    row r_lo corresponds to full-size rows k*r_lo - (k-1) .. k*r_lo (and the same for columns)."""
+    H, W, _ = img.shape
+    pad = np.zeros((H + k - 1, W + k - 1, 3))
+    pad[k - 1:, k - 1:] = img
+    return pad[: H, : W].reshape(H // k, k, W // k, k, 3).mean(axis=(1, 3))
+
+
+FULL = {
+    # key: (block size for the low-resolution oracle comparison, oracle spp, spp override (0 = the config's))
+    "c2": (16, 192, 0),
+    "c3": (24, 192, 0),
+    "c4": (24, 96, 0),
+    "c5": (48, 64, 64),   # 4K, 4M triangles: full resolution and scene, 64 of the 4096 spp (the rest only repeats the same kernel)
+}
+
+
+@pytest.mark.parametrize("key", sorted(FULL))
+def test_full_size_config_properties(key, native_built):
+    """BASELINE configurations at their full resolution / scene size, where the oracle cannot follow ray by ray:
+    size-independent properties instead — every pixel terminates exactly spp paths (census), no NaN / negative
+    pixel, two disjoint sample halves add up to the one-shot render (linearity in samples, GPU-count independence),
+    and the block-averaged image equals the oracle's render of the same view at 1/k resolution within its noise."""
+    import torch
+    k, ospp, spp_over = FULL[key]
+    cfg = scenes.CONFIGS[key]
+    spp = spp_over or cfg.spp
+    hdri = scenes.synthetic_hdri(2048, 1024)
+    W, H = cfg.width, cfg.height
+    stream = torch.cuda.current_stream().cuda_stream
+    for spec in cfg.specs():
+        sc = spec.scene(hdri, with_f64=False)
+        cam = spec.camera()
+        one = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+        api.render_accumulate(cam, sc, spp, cfg.max_bounces, one.data_ptr(), stream, spp_total=spp)
+        st = sc.stats()
+        two = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+        h1 = spp // 2
+        api.render_accumulate(cam, sc, h1, cfg.max_bounces, two.data_ptr(), stream, sample_offset=0, spp_total=spp)
+        rays_two = sc.stats()["rays"]
+        api.render_accumulate(cam, sc, spp - h1, cfg.max_bounces, two.data_ptr(), stream, sample_offset=h1, spp_total=spp)
+        rays_two += sc.stats()["rays"]
+        torch.cuda.synchronize()
+        assert bool((one[..., 3] == float(spp)).all()) and bool((two[..., 3] == float(spp)).all())   # census
+        assert st["paths"] == W * H * spp and rays_two == st["rays"]                                # same set of paths
+        assert bool(torch.isfinite(one).all()) and bool((one >= 0).all())
+        assert torch.allclose(one[..., :3], two[..., :3], rtol=5e-5, atol=1e-4 * spp)                # fp32 summation order only
+        img = (one[..., :3] / spp).cpu().numpy().astype(np.float64)
+        # the same view at 1/k resolution by the oracle (F9: the field of view does not depend on the film size)
+        lw, lh = scenes.film(W // k, H // k)
+        lo = type(spec)(spec.name, dict(spec.camera_args, width=lw, height=lh), spec.objects, spec.heuristic)
+        lcam = lo.camera()
+        assert (lcam.x_pixels(), lcam.y_pixels()) == (W // k, H // k)
+        osc = oracle.OracleScene(spec.tables(), hdri.pixels, heuristic=(spec.heuristic.kind, spec.heuristic.splits), build_mode=1)
+        A, _ = osc.render(lcam.derived17(), W // k, H // k, ospp, max_bounces=cfg.max_bounces, seed=11, rng_mode=oracle.RNG_WIDE)
+        B, _ = osc.render(lcam.derived17(), W // k, H // k, ospp, max_bounces=cfg.max_bounces, seed=12, rng_mode=oracle.RNG_WIDE)
+        G = _block_mean_with_f8_shift(img, k)
+        inner = (slice(1, None), slice(1, None))   # the first block row / column is cut by the shift
+        e0, eg = relrmse(A[inner], B[inner]), relrmse(G[inner], A[inner])
+        # G is nearly noise-free (k*k*spp samples per block): its distance to A is A's own noise, e0 / sqrt(2)
+        assert eg <= 0.85 * e0, (key, spec.name, eg, e0)
+        m_g, m_o = G[inner].mean(), 0.5 * (A[inner].mean() + B[inner].mean())
+        assert abs(m_g - m_o) <= 0.01 * m_o, (m_g, m_o)
+        print(f"[{key} {spec.name}] {W}x{H} spp {spp}: census ok, halves == one-shot, rays {st['rays']:.3e} in {st['device_ms']:.1f} ms; "
+              f"block-mean vs oracle relRMSE {eg:.4f} (oracle noise {e0:.4f}), mean {m_g:.5f} vs {m_o:.5f}")
+        sc.close()
+        osc.close()

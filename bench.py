@@ -336,6 +336,14 @@ def run_ours(args):
             ncu = model.get("ncu", {})
             roof["traffic"] = ncu.get("dram_bytes_per_launch")
             roof["ncu"] = {k: v for k, v in ncu.items() if k != "dram_bytes_per_launch"} or None
+            if ncu.get("warp_instructions_per_launch") and clocks and clocks.get("sm_mhz"):
+                # the limit that actually binds: issue slots.  warp instructions per launch are a constant of the code
+                # and the workload (ncu capture of this command, profiles/); the launch time is measured live.
+                sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                peak_issue = sms * 4 * clocks["sm_mhz"] * 1e6          # 4 schedulers per SM, 1 warp instruction per cycle each
+                ach = ncu["warp_instructions_per_launch"] / (kms / n_launch * 1e-3)
+                roof["issue"] = {"bound": "issue slots", "achieved": ach / 1e9, "peak": peak_issue / 1e9, "unit": "Gwarp-inst/s",
+                                 "frac": ach / peak_issue, "warp_instructions_per_ray": ncu["warp_instructions_per_launch"] / (rays_rank0 / n_launch)}
             if kernel_form == 2:
                 roof["note"] = ("algorithmic bytes are SURVEY 8(d)'s wavefront model (node + primitive fetches + 144 B of queue "
                                 "state per ray).  k_pathloop keeps the path in registers and the <= 8 primitives in shared "

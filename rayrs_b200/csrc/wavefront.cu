@@ -554,6 +554,14 @@ __global__ void __launch_bounds__(kBlock, SPH64 ? RRS_BLOCKS_PER_SM_F64 : RRS_BL
 // sample and bounce), same accumulator, same census.  Warps claim path indices in chunks of 1024 from the
 // global cursor (one global atomic per chunk) and hand them to their dead lanes by ballot/popc.
 // ---------------------------------------------------------------------------------------
+// Lanes of a warp are at different stages of their paths, and the four stages cost very differently
+// (generate ~110 instructions, closest hit ~400, shade a hit ~450, shade a miss ~150).  Running all four
+// every iteration with whatever lanes need them executed 22 of 32 lanes per instruction
+// (profiles/r01g_c2_bench_metrics.csv).  Instead every lane carries its stage, and each iteration the warp
+// runs ONE stage — the one most lanes are waiting for (four ballots + popc); the other lanes keep their
+// state in registers and wait.  A stage's lane count only grows while it waits, so nothing starves.
+enum PathStage : uint32_t { ST_GEN = 0, ST_ISECT = 1, ST_HIT = 2, ST_MISS = 3, ST_DONE = 4 };
+
 template <bool EXACT_TILES, bool COUNT, bool SPH64>
 __global__ void __launch_bounds__(kBlock, SPH64 ? RRS_BLOCKS_PER_SM_F64 : RRS_BLOCKS_PER_SM)
 k_pathloop(DScene sc, RenderConst rc, DCounters* __restrict__ c, float4* __restrict__ accum) {
@@ -566,16 +574,52 @@ k_pathloop(DScene sc, RenderConst rc, DCounters* __restrict__ c, float4* __restr
     const unsigned long long total = c->total_paths;
     unsigned long long w_next = 0, w_end = 0;  // this warp's claimed path range (warp-uniform)
     bool exhausted = false;                    // the global cursor has run past the end (warp-uniform)
-    bool alive = false;
+    uint32_t stage = ST_GEN;
     float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = o4, st = o4;
+    float2 h = make_float2(0.f, 0.f);
     double o64[3] = {0., 0., 0.};
     TravCounters cnt{0, 0};
     unsigned long long rays = 0, iters = 0;
     for (;;) {
-        // ---- regenerate: dead lanes take the next path indices of the warp's range ----
-        uint32_t dead = __ballot_sync(FULL, !alive);
-        if (dead && !exhausted) {
-            if (w_next >= w_end) {
+        const uint32_t b_gen = __ballot_sync(FULL, stage == ST_GEN), b_is = __ballot_sync(FULL, stage == ST_ISECT);
+        const uint32_t b_hit = __ballot_sync(FULL, stage == ST_HIT), b_miss = __ballot_sync(FULL, stage == ST_MISS);
+        if ((b_gen | b_is | b_hit | b_miss) == 0u) break;
+        const int n_gen = __popc(b_gen), n_is = __popc(b_is), n_hit = __popc(b_hit), n_miss = __popc(b_miss);
+        ++iters;
+        if (n_is >= n_gen && n_is >= n_hit && n_is >= n_miss) {
+            // ---- extend: closest hit over the staged primitives ----
+            if (stage == ST_ISECT) {
+                uint32_t prim;
+                closest_hit_brute<COUNT, SPH64>(sc, s_prims, xyz(o4), xyz(d4), __float_as_uint(o4.w), SPH64 ? o64 : nullptr, h.x, prim, cnt);
+                h.y = __uint_as_float(prim);
+                ++rays;
+                stage = prim == RRS_NO_PRIM ? ST_MISS : ST_HIT;
+            }
+        } else if (n_hit >= n_gen && n_hit >= n_miss) {
+            // ---- shade a hit: Material::evaluate, emission, Russian roulette ----
+            if (stage == ST_HIT) {
+                NextRay nr = shade_hit<SPH64>(sc, rc, accum, h, o4, d4, st, SPH64 ? o64 : nullptr);
+                if (nr.alive) {
+                    o4 = nr.no;
+                    d4 = nr.nd;
+                    st = nr.ns;
+                    if (SPH64 && nr.carry64) {
+                        o64[0] = nr.p64x; o64[1] = nr.p64y; o64[2] = nr.p64z;
+                    }
+                    stage = ST_ISECT;
+                } else {
+                    stage = ST_GEN;
+                }
+            }
+        } else if (n_miss >= n_gen) {
+            // ---- shade a miss: background ----
+            if (stage == ST_MISS) {
+                shade_miss(sc, accum, d4, st);
+                stage = ST_GEN;
+            }
+        } else {
+            // ---- generate: waiting lanes take the next path indices of the warp's range ----
+            if (w_next >= w_end && !exhausted) {
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(&c->next_path, 1024ull);
                 base = __shfl_sync(FULL, base, 0);
@@ -586,49 +630,22 @@ k_pathloop(DScene sc, RenderConst rc, DCounters* __restrict__ c, float4* __restr
                     w_end = w_next = 0;
                 }
             }
-            if (!exhausted) {
-                const unsigned long long p = w_next + (unsigned long long)__popc(dead & lt_mask);
-                if (!alive && p < w_end) {
+            if (exhausted) {
+                if (stage == ST_GEN) stage = ST_DONE;
+            } else {
+                const unsigned long long p = w_next + (unsigned long long)__popc(b_gen & lt_mask);
+                if (stage == ST_GEN && p < w_end) {
                     uint32_t pixel = 0, sample = 0;
                     float3 d;
                     if (primary_ray<EXACT_TILES>(rc, p, pixel, sample, d)) {
                         o4 = make_float4(rc.cam.origin.x, rc.cam.origin.y, rc.cam.origin.z, __uint_as_float(RRS_NO_PRIM));
                         d4 = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
                         st = make_float4(1.f, 1.f, 1.f, __uint_as_float(sample << 8));
-                        alive = true;
+                        stage = ST_ISECT;
                     }
                 }
-                w_next += (unsigned long long)__popc(dead);
+                w_next += (unsigned long long)n_gen;
                 if (w_next > w_end) w_next = w_end;
-            }
-        }
-        if (__ballot_sync(FULL, alive) == 0u) {
-            if (exhausted) break;
-            continue;
-        }
-        ++iters;
-        if (alive) {
-            // ---- extend ----
-            float2 h;
-            uint32_t prim;
-            closest_hit_brute<COUNT, SPH64>(sc, s_prims, xyz(o4), xyz(d4), __float_as_uint(o4.w), SPH64 ? o64 : nullptr, h.x, prim, cnt);
-            h.y = __uint_as_float(prim);
-            ++rays;
-            // ---- shade ----
-            if (prim == RRS_NO_PRIM) {
-                shade_miss(sc, accum, d4, st);
-                alive = false;
-            } else {
-                NextRay nr = shade_hit<SPH64>(sc, rc, accum, h, o4, d4, st, SPH64 ? o64 : nullptr);
-                alive = nr.alive;
-                if (alive) {
-                    o4 = nr.no;
-                    d4 = nr.nd;
-                    st = nr.ns;
-                    if (SPH64 && nr.carry64) {
-                        o64[0] = nr.p64x; o64[1] = nr.p64y; o64[2] = nr.p64z;
-                    }
-                }
             }
         }
     }

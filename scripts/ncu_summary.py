@@ -107,6 +107,7 @@ def update_model(metrics_csv: Path, key: str):
         "dram_bytes_per_launch": mean("dram__bytes_read.sum", True) + mean("dram__bytes_write.sum", True),
         "kernel": rows["metric"][2].strip('"'),
         "launch_ms_under_ncu": mean("gpu__time_duration.sum"),
+        "warp_instructions_per_launch": mean("smsp__inst_executed.sum"),
         "issue_active_pct": mean("smsp__issue_active.avg.pct_of_peak_sustained_active"),
         "alu_pipe_pct": mean("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
         "fma_pipe_pct": mean("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),

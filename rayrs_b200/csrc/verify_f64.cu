@@ -147,14 +147,14 @@ int vf_intersect64(SceneImpl* s, const RrsRay* rays, size_t n, int32_t* obj_id, 
     RRS_CUDA_CHECK(cudaSetDevice(s->device), err);
     if (!s->nodes_f64 || !s->prims_f64) { err = "scene was created without f64 nodes"; return RRS_ERR_INVALID; }
     if (n == 0) return RRS_OK;
-    RrsRay* d_r = nullptr;
-    int32_t* d_id = nullptr;
-    double* d_t = nullptr;
-    int* d_ovf = nullptr;
-    RRS_CUDA_CHECK(cudaMalloc(&d_r, sizeof(RrsRay) * n), err);
-    RRS_CUDA_CHECK(cudaMalloc(&d_id, sizeof(int32_t) * n), err);
-    RRS_CUDA_CHECK(cudaMalloc(&d_t, sizeof(double) * n), err);
-    RRS_CUDA_CHECK(cudaMalloc(&d_ovf, sizeof(int)), err);
+    DevBuf<RrsRay> d_r;
+    DevBuf<int32_t> d_id;
+    DevBuf<double> d_t;
+    DevBuf<int> d_ovf;
+    RRS_CUDA_CHECK(d_r.alloc(n), err);
+    RRS_CUDA_CHECK(d_id.alloc(n), err);
+    RRS_CUDA_CHECK(d_t.alloc(n), err);
+    RRS_CUDA_CHECK(d_ovf.alloc(1), err);
     RRS_CUDA_CHECK(cudaMemset(d_ovf, 0, sizeof(int)), err);
     RRS_CUDA_CHECK(cudaMemcpy(d_r, rays, sizeof(RrsRay) * n, cudaMemcpyHostToDevice), err);
     k_intersect64<<<(unsigned)((n + 63) / 64), 64>>>(s->prims_f64, s->nodes_f64, d_r, (uint32_t)n, s->tmin, s->tmax, d_id,
@@ -164,7 +164,6 @@ int vf_intersect64(SceneImpl* s, const RrsRay* rays, size_t n, int32_t* obj_id, 
     RRS_CUDA_CHECK(cudaMemcpy(&ovf, d_ovf, sizeof(int), cudaMemcpyDeviceToHost), err);
     RRS_CUDA_CHECK(cudaMemcpy(obj_id, d_id, sizeof(int32_t) * n, cudaMemcpyDeviceToHost), err);
     RRS_CUDA_CHECK(cudaMemcpy(t, d_t, sizeof(double) * n, cudaMemcpyDeviceToHost), err);
-    cudaFree(d_r); cudaFree(d_id); cudaFree(d_t); cudaFree(d_ovf);
     if (ovf) { err = "fp64 verification stack overflow"; return RRS_ERR_TOO_DEEP; }
     return RRS_OK;
 }

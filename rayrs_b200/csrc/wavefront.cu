@@ -1068,11 +1068,15 @@ int wf_to_raw_bytes(SceneImpl* s, const float4* d_accum, uint32_t w, uint32_t h,
     RRS_CUDA_CHECK(cudaSetDevice(s->device), err);
     const uint32_t npix = w * h;
     const size_t bytes = 3 * (size_t)npix;
-    unsigned long long* d_census = nullptr;
+    DevBuf<unsigned long long> d_census;
+    DevBuf<uint8_t> d_stage;
     uint8_t* d_out = out;
-    RRS_CUDA_CHECK(cudaMalloc(&d_census, 3 * sizeof(unsigned long long)), err);
+    RRS_CUDA_CHECK(d_census.alloc(3), err);
     RRS_CUDA_CHECK(cudaMemsetAsync(d_census, 0, 3 * sizeof(unsigned long long), stream), err);
-    if (!out_is_device) RRS_CUDA_CHECK(cudaMalloc(&d_out, bytes), err);
+    if (!out_is_device) {
+        RRS_CUDA_CHECK(d_stage.alloc(bytes), err);
+        d_out = d_stage;
+    }
     int grid = std::min<uint32_t>((npix + 255) / 256, (uint32_t)s->num_sms * 8u);
     k_to_raw_bytes<<<grid, 256, 0, stream>>>(d_accum, d_out, npix, 1.0 / (double)spp_total, gamma, d_census);
     RRS_CUDA_CHECK(cudaGetLastError(), err);
@@ -1080,8 +1084,6 @@ int wf_to_raw_bytes(SceneImpl* s, const float4* d_accum, uint32_t w, uint32_t h,
     if (!out_is_device) RRS_CUDA_CHECK(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, stream), err);
     RRS_CUDA_CHECK(cudaMemcpyAsync(hc, d_census, sizeof(hc), cudaMemcpyDeviceToHost, stream), err);
     RRS_CUDA_CHECK(cudaStreamSynchronize(stream), err);
-    if (!out_is_device) cudaFree(d_out);
-    cudaFree(d_census);
     if (census3) { census3[0] = hc[0]; census3[1] = hc[1]; census3[2] = hc[2]; }
     return RRS_OK;
 }
@@ -1095,13 +1097,13 @@ int wf_intersect32(SceneImpl* s, const RrsRay* rays, size_t n, int32_t* obj_id, 
         ho[i] = make_float4((float)rays[i].origin[0], (float)rays[i].origin[1], (float)rays[i].origin[2], 0.f);
         hd[i] = make_float4((float)rays[i].direction[0], (float)rays[i].direction[1], (float)rays[i].direction[2], 0.f);
     }
-    float4 *d_o = nullptr, *d_d = nullptr;
-    int32_t* d_id = nullptr;
-    float* d_t = nullptr;
-    RRS_CUDA_CHECK(cudaMalloc(&d_o, sizeof(float4) * n), err);
-    RRS_CUDA_CHECK(cudaMalloc(&d_d, sizeof(float4) * n), err);
-    RRS_CUDA_CHECK(cudaMalloc(&d_id, sizeof(int32_t) * n), err);
-    RRS_CUDA_CHECK(cudaMalloc(&d_t, sizeof(float) * n), err);
+    DevBuf<float4> d_o, d_d;
+    DevBuf<int32_t> d_id;
+    DevBuf<float> d_t;
+    RRS_CUDA_CHECK(d_o.alloc(n), err);
+    RRS_CUDA_CHECK(d_d.alloc(n), err);
+    RRS_CUDA_CHECK(d_id.alloc(n), err);
+    RRS_CUDA_CHECK(d_t.alloc(n), err);
     RRS_CUDA_CHECK(cudaMemcpy(d_o, ho.data(), sizeof(float4) * n, cudaMemcpyHostToDevice), err);
     RRS_CUDA_CHECK(cudaMemcpy(d_d, hd.data(), sizeof(float4) * n, cudaMemcpyHostToDevice), err);
     size_t smem = extend_smem_bytes(s->d);
@@ -1113,7 +1115,6 @@ int wf_intersect32(SceneImpl* s, const RrsRay* rays, size_t n, int32_t* obj_id, 
     RRS_CUDA_CHECK(cudaMemcpy(obj_id, d_id, sizeof(int32_t) * n, cudaMemcpyDeviceToHost), err);
     RRS_CUDA_CHECK(cudaMemcpy(ht.data(), d_t, sizeof(float) * n, cudaMemcpyDeviceToHost), err);
     for (size_t i = 0; i < n; ++i) t[i] = (double)ht[i];
-    cudaFree(d_o); cudaFree(d_d); cudaFree(d_id); cudaFree(d_t);
     return RRS_OK;
 }
 
@@ -1127,16 +1128,15 @@ int wf_material_evaluate(SceneImpl* s, uint32_t material, const double* nv, cons
     std::vector<float> hnv(6 * n), hu(3 * n);
     for (size_t i = 0; i < 6 * n; ++i) hnv[i] = (float)nv[i];
     for (size_t i = 0; i < 3 * n; ++i) hu[i] = (float)u[i];
-    float *d_nv = nullptr, *d_u = nullptr, *d_out = nullptr;
-    RRS_CUDA_CHECK(cudaMalloc(&d_nv, sizeof(float) * 6 * n), err);
-    RRS_CUDA_CHECK(cudaMalloc(&d_u, sizeof(float) * 3 * n), err);
-    RRS_CUDA_CHECK(cudaMalloc(&d_out, sizeof(float) * 7 * n), err);
+    DevBuf<float> d_nv, d_u, d_out;
+    RRS_CUDA_CHECK(d_nv.alloc(6 * n), err);
+    RRS_CUDA_CHECK(d_u.alloc(3 * n), err);
+    RRS_CUDA_CHECK(d_out.alloc(7 * n), err);
     RRS_CUDA_CHECK(cudaMemcpy(d_nv, hnv.data(), sizeof(float) * 6 * n, cudaMemcpyHostToDevice), err);
     RRS_CUDA_CHECK(cudaMemcpy(d_u, hu.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice), err);
     k_material_probe<<<(unsigned)((n + 127) / 128), 128>>>(m, d_nv, d_u, (uint32_t)n, d_out);
     RRS_CUDA_CHECK(cudaGetLastError(), err);
     RRS_CUDA_CHECK(cudaMemcpy(out, d_out, sizeof(float) * 7 * n, cudaMemcpyDeviceToHost), err);
-    cudaFree(d_nv); cudaFree(d_u); cudaFree(d_out);
     return RRS_OK;
 }
 
@@ -1145,26 +1145,24 @@ int wf_background(SceneImpl* s, const double* dirs, size_t n, float* out, std::s
     if (n == 0) return RRS_OK;
     std::vector<float> hd(3 * n);
     for (size_t i = 0; i < 3 * n; ++i) hd[i] = (float)dirs[i];
-    float *d_d = nullptr, *d_out = nullptr;
-    RRS_CUDA_CHECK(cudaMalloc(&d_d, sizeof(float) * 3 * n), err);
-    RRS_CUDA_CHECK(cudaMalloc(&d_out, sizeof(float) * 3 * n), err);
+    DevBuf<float> d_d, d_out;
+    RRS_CUDA_CHECK(d_d.alloc(3 * n), err);
+    RRS_CUDA_CHECK(d_out.alloc(3 * n), err);
     RRS_CUDA_CHECK(cudaMemcpy(d_d, hd.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice), err);
     k_background_probe<<<(unsigned)((n + 127) / 128), 128>>>(s->d, d_d, (uint32_t)n, d_out);
     RRS_CUDA_CHECK(cudaGetLastError(), err);
     RRS_CUDA_CHECK(cudaMemcpy(out, d_out, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost), err);
-    cudaFree(d_d); cudaFree(d_out);
     return RRS_OK;
 }
 
 int wf_rng_uniforms(SceneImpl* s, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, float* out4,
                     std::string& err) {
     RRS_CUDA_CHECK(cudaSetDevice(s->device), err);
-    float* d = nullptr;
-    RRS_CUDA_CHECK(cudaMalloc(&d, 4 * sizeof(float)), err);
+    DevBuf<float> d;
+    RRS_CUDA_CHECK(d.alloc(4), err);
     k_rng_probe<<<1, 1>>>(seed, pixel, sample, slot, d);
     RRS_CUDA_CHECK(cudaGetLastError(), err);
     RRS_CUDA_CHECK(cudaMemcpy(out4, d, 4 * sizeof(float), cudaMemcpyDeviceToHost), err);
-    cudaFree(d);
     return RRS_OK;
 }
 

@@ -97,6 +97,19 @@ void wf_free(SceneImpl* s);
 // verify_f64.cu
 int vf_intersect64(SceneImpl* s, const RrsRay* rays, size_t n, int32_t* obj_id, double* t, std::string& err);
 
+// Scratch device allocation of one entry point: freed on every return path, including the early returns of
+// RRS_CUDA_CHECK.
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) { return cudaMalloc(&p, sizeof(T) * (count ? count : 1)); }
+    operator T*() const { return p; }
+};
+
 #define RRS_CUDA_CHECK(expr, errstr)                                                           \
     do {                                                                                       \
         cudaError_t _e = (expr);                                                               \

@@ -237,7 +237,9 @@ def run_ours(args):
                 launches += 1
         return rays, launches, ph
 
-    host_out = [np.empty((H, W, 3), dtype=np.float32) for _ in built]
+    # the caller's image buffers, page-locked (the library DMAs straight into a pinned destination)
+    host_pin = [torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True) for _ in built]
+    host_out = [t.numpy() for t in host_pin]
 
     def step_e2e():
         """public API with HOST buffers.  N == 1: rrs_render (h2d camera+params, d2h image).

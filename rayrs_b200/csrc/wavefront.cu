@@ -1036,8 +1036,12 @@ int wf_resolve(SceneImpl* s, const float4* d_accum, uint32_t w, uint32_t h, uint
     }
     RRS_CUDA_CHECK(cudaMemsetAsync(s->census, 0, 2 * sizeof(unsigned long long), stream), err);
     float* d_out = out;
+    bool direct = false;  // the caller's host buffer is page-locked: DMA straight into it
     if (!out_is_device) {
-        // persistent device image + pinned staging buffer: the host copy is one async D2H
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, out) == cudaSuccess) direct = at.type == cudaMemoryTypeHost;
+        cudaGetLastError();  // an unregistered pointer is not an error here
+        // persistent device image (+ pinned staging buffer for pageable destinations): the host copy is one async D2H
         if (s->resolve_bytes < bytes) {
             cudaFree(s->resolve_dev);
             if (s->resolve_pinned) cudaFreeHost(s->resolve_pinned);
@@ -1052,10 +1056,11 @@ int wf_resolve(SceneImpl* s, const float4* d_accum, uint32_t w, uint32_t h, uint
     }
     int grid = std::min<uint32_t>((npix + 255) / 256, (uint32_t)s->num_sms * 8u);
     k_resolve<<<grid, 256, 0, stream>>>(d_accum, d_out, npix, 1.0f / (float)spp_total, s->census);
-    if (!out_is_device) RRS_CUDA_CHECK(cudaMemcpyAsync(s->resolve_pinned, d_out, bytes, cudaMemcpyDeviceToHost, stream), err);
+    if (!out_is_device)
+        RRS_CUDA_CHECK(cudaMemcpyAsync(direct ? out : s->resolve_pinned, d_out, bytes, cudaMemcpyDeviceToHost, stream), err);
     RRS_CUDA_CHECK(cudaMemcpyAsync(s->h_census, s->census, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), err);
     RRS_CUDA_CHECK(cudaStreamSynchronize(stream), err);
-    if (!out_is_device) std::memcpy(out, s->resolve_pinned, bytes);
+    if (!out_is_device && !direct) std::memcpy(out, s->resolve_pinned, bytes);
     s->stats.nan_pixels = s->h_census[0];
     s->stats.negative_pixels = s->h_census[1];
     s->stats.kernel_launches += 1;

@@ -246,7 +246,10 @@ int rrs_intersect(RrsScene* scene, const RrsRay* rays, size_t n, int32_t* obj_id
 
 /* Material::evaluate (material.rs:91-109, pdf=None) for a batch: normal_view = n x 6 doubles
  * (unit normal, unit view), u = n x 3 uniforms in call order; out = n x 7 floats
- * [scatter flag, color rgb, direction xyz].  Parity probe for the shading kernels. */
+ * [scatter flag, color rgb, direction xyz].  Parity probe for the shading kernels.  The kernels carry two
+ * forms of the function (shared stages for mixed warps, one arm per variant for the small-scene path loop);
+ * `material | RRS_MATERIAL_FORM_CASES` probes the second. */
+#define RRS_MATERIAL_FORM_CASES 0x80000000u
 int rrs_material_evaluate(RrsScene* scene, uint32_t material, const double* normal_view, const double* u,
                           size_t n, float* out);
 

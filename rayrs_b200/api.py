@@ -321,12 +321,12 @@ class Scene:
                                                  int(precision)))
         return ids, t
 
-    def material_evaluate(self, material: int, normal_view: np.ndarray, u: np.ndarray) -> np.ndarray:
+    def material_evaluate(self, material: int, normal_view: np.ndarray, u: np.ndarray, cases_form: bool = False) -> np.ndarray:
         self._need_gpu()
         nv = np.ascontiguousarray(normal_view, dtype=np.float64).reshape(-1, 6)
         uu = np.ascontiguousarray(u, dtype=np.float64).reshape(-1, 3)
         out = np.zeros((nv.shape[0], 7), dtype=np.float32)
-        _ffi.check(_ffi.cuda_lib().rrs_material_evaluate(self.handle, int(material), nv.ctypes.data, uu.ctypes.data,
+        _ffi.check(_ffi.cuda_lib().rrs_material_evaluate(self.handle, int(material) | (0x80000000 if cases_form else 0), nv.ctypes.data, uu.ctypes.data,
                                                          nv.shape[0], out.ctypes.data))
         return out
 

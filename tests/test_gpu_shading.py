@@ -50,8 +50,9 @@ def _inputs(n, seed, both_sides):
     return nv, u
 
 
+@pytest.mark.parametrize("cases_form", [False, True], ids=["staged", "cases"])
 @pytest.mark.parametrize("name", sorted(MATERIALS))
-def test_material_evaluate_matches_oracle(name, scene):
+def test_material_evaluate_matches_oracle(name, scene, cases_form):
     mat = MATERIALS[name]
     idx = list(MATERIALS).index(name)
     assert scene.tables.mats.shape[0] == len(MATERIALS)
@@ -59,7 +60,7 @@ def test_material_evaluate_matches_oracle(name, scene):
     # view on both sides of the surface: transmissive materials see it from inside, and the
     # reflective ones must reproduce the reference's NoScatter / sign behaviour there
     nv, u = _inputs(n, 100 + idx, both_sides=True)
-    g = scene.material_evaluate(idx, nv, u).astype(np.float64)
+    g = scene.material_evaluate(idx, nv, u, cases_form=cases_form).astype(np.float64)
     o = oracle.material_evaluate(scene.tables.mats[idx], nv, u)
     flag_diff = g[:, 0] != o[:, 0]
     # scatter/no-scatter decisions differ only within fp32 noise of a decision boundary

@@ -320,17 +320,27 @@ __device__ __forceinline__ void trav_leaf_step(const DScene& sc, const RayK& r, 
                                                TravCounters& cnt) {
     const uint32_t first = tv.cur & 0x0FFFFFFFu;
     const uint32_t count = ((tv.cur >> 28) & 7u) + 1u;
+    // software-pipelined: the record of primitive k + 1 is in flight while primitive k is tested (the loads of a
+    // run are independent of the tests, but the loop-carried closest hit keeps the compiler from hoisting them)
+    float4 a, b, c, pad;
+    ldg256(sc.prims + first, a, b);
+    ldg256(reinterpret_cast<const char*>(sc.prims + first) + 32, c, pad);
     // the shear rows are rebuilt per leaf visit (~3.5 per ray) instead of living in 6 registers for the
-    // whole traversal (~30 node steps per ray)
+    // whole traversal (~30 node steps per ray); they overlap the first fetch
     RayProj proj;
     if (sc.has_triangles) proj = make_proj(r.d);
     for (uint32_t k = 0; k < count; ++k) {
         const uint32_t pi = first + k;
-        float4 a, b, c, pad;
-        ldg256(sc.prims + pi, a, b);
-        ldg256(reinterpret_cast<const char*>(sc.prims + pi) + 32, c, pad);
+        float4 na = a, nb = b, nc = c;
+        if (k + 1 < count) {
+            ldg256(sc.prims + pi + 1, na, nb);
+            ldg256(reinterpret_cast<const char*>(sc.prims + pi + 1) + 32, nc, pad);
+        }
         if (COUNT) cnt.prims++;
         test_prim<SPH64>(sc, pi, a, b, c, r.o, r.d, proj, r.origin_prim, r.org64, tv.tbest, tv.best);
+        a = na;
+        b = nb;
+        c = nc;
     }
     --tv.sp;
     tv.cur = stack[tv.sp * stride];

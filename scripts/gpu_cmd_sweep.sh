@@ -1,7 +1,3 @@
-cp rayrs_b200/librayrs_b200.so /tmp/orig.so
-for v in orig 7_6 7_5 8_5; do
-if [ $v = orig ]; then cp /tmp/orig.so rayrs_b200/librayrs_b200.so; else cp _variants/lib_$v.so rayrs_b200/librayrs_b200.so; fi
-python scripts/gpu_dev.py c2,c4 0 64 2>&1 | grep -v "scene build" | sed "s/^/v=$v /"
-python scripts/gpu_dev.py c3 0 64 2>&1 | grep -v "scene build" | sed "s/^/v=$v /"
-done | tee gpurun_out/sweep_occ2.log
-cp /tmp/orig.so rayrs_b200/librayrs_b200.so
+python -m pytest tests/test_gpu_intersect.py tests/test_golden.py -m gpu -x -q 2>&1 | tail -2
+python scripts/gpu_dev.py c4 | grep -v "scene build"
+python scripts/gpu_dev.py c5 0 16 | grep -v "scene build"

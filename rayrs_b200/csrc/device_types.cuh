@@ -5,6 +5,16 @@
 
 #include "../../include/rayrs_b200.h"
 
+// Bounds checks of our own (compute-sanitizer is closed on this GPU pool): built with -DRRS_DEBUG_CHECKS every
+// stack push, queue slot, node and primitive index is asserted on the device; the GPU test suite is run once
+// against that build (scripts/gpu_cmd_debugchecks.sh).  Compiled out otherwise.
+#ifdef RRS_DEBUG_CHECKS
+#include <cassert>
+#define RRS_CHECK(cond) assert(cond)
+#else
+#define RRS_CHECK(cond) ((void)0)
+#endif
+
 namespace rrs {
 
 // ---------------------------------------------------------------------------------------

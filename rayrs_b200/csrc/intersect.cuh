@@ -238,6 +238,7 @@ template <bool COUNT>
 __device__ __forceinline__ void trav_node_step(const DScene& sc, const RayK& r, Trav& tv, uint32_t* stack, int stride,
                                                TravCounters& cnt) {
     uint32_t w[8];
+    RRS_CHECK(tv.cur < sc.n_nodes);
     ldg256(sc.nodes + tv.cur, w);
     if (COUNT) cnt.nodes++;
     const float3 o = r.o, idir = r.idir;
@@ -268,12 +269,14 @@ __device__ __forceinline__ void trav_node_step(const DScene& sc, const RayK& r, 
     const bool go1 = n1 <= f1 * 1.000001f;
     if (go0 && go1) {
         const bool swap = n1 < n0;
+        RRS_CHECK(tv.sp < sc.stack_entries);
         stack[tv.sp * stride] = swap ? ref0 : ref1;
         ++tv.sp;
         tv.cur = swap ? ref1 : ref0;
     } else if (go0 || go1) {
         tv.cur = go0 ? ref0 : ref1;
     } else {
+        RRS_CHECK(tv.sp >= 1u);
         --tv.sp;
         tv.cur = stack[tv.sp * stride];
     }
@@ -323,6 +326,7 @@ __device__ __forceinline__ void trav_leaf_step(const DScene& sc, const RayK& r, 
     // software-pipelined: the record of primitive k + 1 is in flight while primitive k is tested (the loads of a
     // run are independent of the tests, but the loop-carried closest hit keeps the compiler from hoisting them)
     float4 a, b, c, pad;
+    RRS_CHECK(first + count <= sc.n_prims && tv.sp >= 1u);
     ldg256(sc.prims + first, a, b);
     ldg256(reinterpret_cast<const char*>(sc.prims + first) + 32, c, pad);
     // the shear rows are rebuilt per leaf visit (~3.5 per ray) instead of living in 6 registers for the

@@ -142,6 +142,7 @@ __device__ __forceinline__ void phase_generate(const RenderConst& rc, DCounters*
             slot = base + __popc(ballot & ((1u << lane) - 1u));
         }
         if (!valid) continue;
+        RRS_CHECK(slot < q.region_cap);
         ray_o[slot] = make_float4(rc.cam.origin.x, rc.cam.origin.y, rc.cam.origin.z, __uint_as_float(RRS_NO_PRIM));
         ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
         state[slot] = make_float4(1.f, 1.f, 1.f, __uint_as_float(sample << 8));
@@ -305,6 +306,7 @@ __device__ __forceinline__ NextRay shade_hit(const DScene& sc, const RenderConst
     double &p64x = nr.p64x, &p64y = nr.p64y, &p64z = nr.p64z;
     uint32_t prim = __float_as_uint(h.y);
     uint32_t pixel = __float_as_uint(d4.w);
+    RRS_CHECK(prim < sc.n_prims && pixel < rc.cam.W * rc.cam.H);
     uint32_t sb = __float_as_uint(st.w);
     uint32_t bounce = sb & 0xFFu, sample = sb >> 8;
     float3 thr = xyz(st);
@@ -443,6 +445,7 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
             obase = __shfl_sync(0xFFFFFFFFu, obase, 0);
             if (alive) {
                 uint32_t slot = obase + __popc(ballot & ((1u << lane) - 1u));
+                RRS_CHECK(slot < q.region_cap);
                 out_o[slot] = nr.no;
                 out_d[slot] = nr.nd;
                 out_state[slot] = nr.ns;

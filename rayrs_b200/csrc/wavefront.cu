@@ -29,7 +29,7 @@ static constexpr int kBlock = 128;  // threads per block of the persistent kerne
 #define RRS_BLOCKS_PER_SM 8
 #endif
 #ifndef RRS_BLOCKS_PER_SM_F64
-#define RRS_BLOCKS_PER_SM_F64 6
+#define RRS_BLOCKS_PER_SM_F64 7
 #endif
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }

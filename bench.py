@@ -346,15 +346,11 @@ def run_ours(args):
                 ach = ncu["warp_instructions_per_launch"] / (kms / n_launch * 1e-3)
                 roof["issue"] = {"bound": "issue slots", "achieved": ach / 1e9, "peak": peak_issue / 1e9, "unit": "Gwarp-inst/s",
                                  "frac": ach / peak_issue, "warp_instructions_per_ray": ncu["warp_instructions_per_launch"] / (rays_rank0 / n_launch)}
-            if kernel_form == 2:
-                roof["note"] = ("algorithmic bytes are SURVEY 8(d)'s wavefront model (node + primitive fetches + 144 B of queue "
-                                "state per ray).  k_pathloop keeps the path in registers and the <= 8 primitives in shared "
-                                "memory, so its measured DRAM traffic is ~0 and frac > 1 only says the kernel never touches HBM: "
-                                "it is FP32/ALU-issue bound (issue slots, pipe utilisation and lanes per instruction in "
-                                "roofline.ncu and profiles/)")
-            else:
-                roof["note"] = ("algorithmic bytes follow SURVEY 8(d) (queues counted as HBM traffic); node/primitive fetches are "
-                                "mostly L1/L2 hits, so the kernel is issue / L1-wavefront bound rather than HBM bound (profiles/)")
+            roof["note"] = ("algorithmic bytes follow SURVEY 8(d) (node + primitive fetches + 144 B of queue state per ray, all counted "
+                            "as HBM traffic).  Here the primitives sit in shared memory, the closest hit is fused into the shade phase "
+                            "(no hit queue, one read of the ray record) and part of the queue stripes stays in L2, so the measured DRAM "
+                            "traffic (roofline.traffic) is below the algorithmic figure and frac > 1 only says the kernel is not "
+                            "HBM-bound: it is issue-bound (roofline.issue, roofline.ncu, profiles/)")
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             import oracle  # cpu_baseline leg: the one place bench.py may execute oracle/

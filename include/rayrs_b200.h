@@ -201,9 +201,9 @@ typedef struct RrsStats {
 #define RRS_FLAG_TIME_PHASES 2u     /* split kernels only: CUDA-event time every phase launch */
 #define RRS_FLAG_SPLIT_KERNELS 4u   /* one generate/extend/shade launch per wavefront iteration instead of the
                                        single fused persistent kernel (per-phase profiling) */
-#define RRS_FLAG_FORCE_QUEUES 8u    /* small scenes: use the queue-based wavefront kernel instead of the
-                                       register-resident path loop (A/B measurements, tests) */
-#define RRS_FLAG_FORCE_PATHLOOP 16u /* small scenes with transmissive spheres: use the path loop anyway */
+#define RRS_FLAG_FORCE_QUEUES 8u    /* use the queue-based wavefront kernel (the default; kept for A/B scripts) */
+#define RRS_FLAG_FORCE_PATHLOOP 16u /* small scenes (<= 8 primitives): use the register-resident path loop
+                                       (k_pathloop) instead of the queued kernel (A/B measurements, tests) */
 
 typedef struct RrsScene RrsScene;
 

@@ -401,10 +401,14 @@ __device__ __forceinline__ void shade_miss(const DScene& sc, float4* __restrict_
 // shade: Material::evaluate + Russian roulette + background for stripe b of queue `cur`;
 // survivors are compacted into stripe b of the other queue
 // ---------------------------------------------------------------------------------------
-template <bool SPH64>
+// INLINE_HIT (small scenes in the queued kernel): the closest hit is found here, by brute force over the staged
+// primitives, instead of in a separate extend phase — a fixed 8-primitive loop has nothing to gain from being
+// batched on its own, and fusing it drops the hit queue and the second read of every ray record (48 of ~190 bytes
+// of DRAM traffic per ray on the frosted-glass series, profiles/r01j_c3_frosted_metrics.csv).
+template <bool SPH64, bool INLINE_HIT, bool COUNT>
 __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst& rc, DCounters* __restrict__ c,
                                             const QueueSet& q, int cur, float4* __restrict__ accum, uint32_t* s_cursor,
-                                            uint32_t* s_out) {
+                                            uint32_t* s_out, const DPrim* s_prims) {
     const uint32_t b = blockIdx.x;
     const uint32_t n = q.count[(size_t)cur * q.regions + b];
     const uint32_t lane = lane_id();
@@ -417,6 +421,7 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
     float4* __restrict__ out_o = q.ray_o + ooff;
     float4* __restrict__ out_d = q.ray_d + ooff;
     float4* __restrict__ out_state = q.state + ooff;
+    TravCounters tcnt{0, 0};
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(s_cursor, 32u);
@@ -427,12 +432,19 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
         nr.alive = false;
         nr.carry64 = false;
         if (i < n) {
-            float2 h = hits[i];
             float4 o4 = ray_o[i], d4 = ray_d[i], st = state[i];
+            const double* o64 = (SPH64 && q.org64) ? q.org64 + 3 * (off + i) : nullptr;
+            float2 h;
+            if (INLINE_HIT) {
+                uint32_t prim;
+                closest_hit_brute<COUNT, SPH64>(sc, s_prims, xyz(o4), xyz(d4), __float_as_uint(o4.w), o64, h.x, prim, tcnt);
+                h.y = __uint_as_float(prim);
+            } else {
+                h = hits[i];
+            }
             if (__float_as_uint(h.y) == RRS_NO_PRIM) {
                 shade_miss(sc, accum, d4, st);
             } else {
-                const double* o64 = (SPH64 && q.org64) ? q.org64 + 3 * (off + i) : nullptr;
                 nr = shade_hit<SPH64, true>(sc, rc, accum, h, o4, d4, st, o64);
             }
         }
@@ -456,6 +468,7 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
             }
         }
     }
+    if (INLINE_HIT) flush_trav_counters<COUNT>(c, tcnt);
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t survivors = *s_out;
@@ -474,7 +487,124 @@ __global__ void __launch_bounds__(kBlock, SPH64 ? RRS_BLOCKS_PER_SM_F64 : RRS_BL
         s_out = 0;
     }
     __syncthreads();
-    phase_shade<SPH64>(sc, rc, c, q, cur, accum, &s_cursor, &s_out);
+    phase_shade<SPH64, false, false>(sc, rc, c, q, cur, accum, &s_cursor, &s_out, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------
+// Small scenes (BRUTE): one pass per iteration.  The stripe's survivors are read from the queue; the slots behind
+// them are filled with NEW paths generated in registers (no queue write + read-back for primary rays); every ray
+// finds its closest hit by brute force over the staged primitives, is shaded, and only the survivors of this
+// bounce are written — compacted — into the other half of the stripe.  Per ray that leaves one 48-byte queue
+// write and one 48-byte read for the ~36 % of rays that continue, instead of generate-write / extend-read /
+// hit-write / shade-read (192 B of DRAM traffic per ray on the frosted-glass series, profiles/r01j_c3_frosted_*).
+// ---------------------------------------------------------------------------------------
+template <bool COUNT, bool SPH64>
+__device__ __forceinline__ bool small_scene_iteration(const DScene& sc, const RenderConst& rc, DCounters* __restrict__ c,
+                                                      const QueueSet& q, int cur, float4* __restrict__ accum,
+                                                      const DPrim* s_prims, uint32_t* s_u32, unsigned long long* s_u64) {
+    // s_u32: [0] new paths claimed, [1] rays traced, [2] work cursor, [3] append cursor; s_u64[0]: first new path index
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t b = blockIdx.x;
+    const uint32_t lane = lane_id();
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t n0 = q.count[(size_t)cur * q.regions + b];
+    if (threadIdx.x == 0) {
+        uint32_t need = q.region_cap - n0, got = 0;
+        unsigned long long base = 0;
+        if (need && c->next_path < c->total_paths) {  // one global atomic per block per iteration
+            base = atomicAdd(&c->next_path, (unsigned long long)need);
+            if (base < c->total_paths) {
+                unsigned long long left = c->total_paths - base;
+                got = left < need ? (uint32_t)left : need;
+            }
+        }
+        s_u64[0] = base;
+        s_u32[0] = got;
+        s_u32[1] = 0;
+        s_u32[2] = 0;
+        s_u32[3] = 0;
+    }
+    __syncthreads();
+    const uint32_t n = n0 + s_u32[0];
+    const unsigned long long first = s_u64[0];
+    if (n == 0) return false;  // nothing live and no path left for this block
+    const size_t roff = (size_t)b * q.region_cap;
+    const size_t off = (size_t)cur * q.capacity + roff, ooff = (size_t)(cur ^ 1) * q.capacity + roff;
+    const float4* __restrict__ ray_o = q.ray_o + off;
+    const float4* __restrict__ ray_d = q.ray_d + off;
+    const float4* __restrict__ state = q.state + off;
+    float4* __restrict__ out_o = q.ray_o + ooff;
+    float4* __restrict__ out_d = q.ray_d + ooff;
+    float4* __restrict__ out_state = q.state + ooff;
+    TravCounters tcnt{0, 0};
+    uint32_t traced = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&s_u32[2], 32u);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        NextRay nr;
+        nr.alive = false;
+        nr.carry64 = false;
+        bool valid = i < n;
+        float4 o4, d4, st;
+        const double* o64 = nullptr;
+        if (valid) {
+            if (i < n0) {  // a survivor of the previous bounce
+                o4 = ray_o[i];
+                d4 = ray_d[i];
+                st = state[i];
+                if (SPH64 && q.org64) o64 = q.org64 + 3 * (off + i);
+            } else {       // a new path: Camera::generate_primary_ray, straight into registers
+                uint32_t pixel = 0, sample = 0;
+                float3 d;
+                valid = primary_ray(rc, first + (i - n0), pixel, sample, d);
+                o4 = make_float4(rc.cam.origin.x, rc.cam.origin.y, rc.cam.origin.z, __uint_as_float(RRS_NO_PRIM));
+                d4 = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
+                st = make_float4(1.f, 1.f, 1.f, __uint_as_float(sample << 8));
+            }
+        }
+        if (valid) {
+            float2 h;
+            uint32_t prim;
+            closest_hit_brute<COUNT, SPH64>(sc, s_prims, xyz(o4), xyz(d4), __float_as_uint(o4.w), o64, h.x, prim, tcnt);
+            h.y = __uint_as_float(prim);
+            ++traced;
+            if (prim == RRS_NO_PRIM) shade_miss(sc, accum, d4, st);
+            else nr = shade_hit<SPH64, true>(sc, rc, accum, h, o4, d4, st, o64);
+        }
+        // queue compaction: survivors of this warp take consecutive slots of the stripe's other half
+        const uint32_t ballot = __ballot_sync(FULL, nr.alive);
+        if (ballot) {
+            uint32_t obase = 0;
+            if (lane == 0) obase = atomicAdd(&s_u32[3], (uint32_t)__popc(ballot));
+            obase = __shfl_sync(FULL, obase, 0);
+            if (nr.alive) {
+                const uint32_t slot = obase + __popc(ballot & lt_mask);
+                RRS_CHECK(slot < q.region_cap);
+                out_o[slot] = nr.no;
+                out_d[slot] = nr.nd;
+                out_state[slot] = nr.ns;
+                if (SPH64 && nr.carry64 && q.org64) {
+                    double* w64 = q.org64 + 3 * (ooff + slot);
+                    w64[0] = nr.p64x; w64[1] = nr.p64y; w64[2] = nr.p64z;
+                }
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) traced += __shfl_xor_sync(FULL, traced, o);
+    if (lane == 0 && traced) atomicAdd(&s_u32[1], traced);
+    flush_trav_counters<COUNT>(c, tcnt);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t survivors = s_u32[3];
+        q.count[(size_t)(cur ^ 1) * q.regions + b] = survivors;
+        if (s_u32[1]) atomicAdd(&c->rays, (unsigned long long)s_u32[1]);
+        s_u64[4] += 1;
+    }
+    __syncthreads();
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -505,16 +635,18 @@ __device__ __forceinline__ bool wavefront_iteration(const DScene& sc, const Rend
     }
     __syncthreads();
     if (n == 0) return false;  // nothing live and no path left for this block
-    phase_extend<BRUTE, COUNT, SPH64>(sc, c, q, cur, s_stack, s_prims, &s_u32[2]);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        s_u32[2] = 0;
-        long long t1 = clock64();
-        s_u64[2] += (unsigned long long)(t1 - t0);
-        t0 = t1;
+    if (!BRUTE) {
+        phase_extend<BRUTE, COUNT, SPH64>(sc, c, q, cur, s_stack, s_prims, &s_u32[2]);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_u32[2] = 0;
+            long long t1 = clock64();
+            s_u64[2] += (unsigned long long)(t1 - t0);
+            t0 = t1;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    phase_shade<SPH64>(sc, rc, c, q, cur, accum, &s_u32[2], &s_u32[3]);
+    phase_shade<SPH64, BRUTE, COUNT>(sc, rc, c, q, cur, accum, &s_u32[2], &s_u32[3], s_prims);
     __syncthreads();
     if (threadIdx.x == 0) {
         s_u64[3] += (unsigned long long)(clock64() - t0);
@@ -534,8 +666,11 @@ __global__ void __launch_bounds__(kBlock, SPH64 ? RRS_BLOCKS_PER_SM_F64 : RRS_BL
     if (threadIdx.x < 5) s_u64[threadIdx.x] = 0;
     stage_brute_prims(sc, s_prims);
     __syncthreads();
-    for (int cur = 0;; cur ^= 1)
-        if (!wavefront_iteration<BRUTE, COUNT, SPH64>(sc, rc, c, q, cur, accum, s_stack, s_prims, s_u32, s_u64)) break;
+    for (int cur = 0;; cur ^= 1) {
+        const bool more = BRUTE ? small_scene_iteration<COUNT, SPH64>(sc, rc, c, q, cur, accum, s_prims, s_u32, s_u64)
+                                : wavefront_iteration<BRUTE, COUNT, SPH64>(sc, rc, c, q, cur, accum, s_stack, s_prims, s_u32, s_u64);
+        if (!more) break;
+    }
     if (threadIdx.x == 0) {
         atomicMax(&c->iterations, s_u64[4]);
         atomicAdd(&c->cyc_generate, s_u64[1]);
@@ -934,9 +1069,11 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     uint64_t launches = 0, iters = 0;
     std::vector<size_t> phase_ev;  // indices of per-iteration event groups
     const bool split = (p->flags & RRS_FLAG_SPLIT_KERNELS) != 0;
-    // measured (gpurun_out/sweep_pathloop.log): +16 % on the opaque sphere series, but -10 % on the frosted-glass
-    // series, whose f64 re-entry arithmetic diverges harder inside one long-lived loop than in the queued shade phase
-    const bool want_pathloop = (p->flags & RRS_FLAG_FORCE_PATHLOOP) || !sph64;
+    // The register-resident path loop beat the queued kernel by 16 % while that still ran a separate extend phase
+    // (gpurun_out/sweep_pathloop.log); with the closest hit fused into the shade phase the queued kernel is as fast or
+    // faster on every small scene (plastic series +5 %, gpurun_out/sweep_pl_vs_q.log) — compaction gives it full warps
+    // every iteration — so the path loop is an option (RRS_FLAG_FORCE_PATHLOOP), not the default.
+    const bool want_pathloop = (p->flags & RRS_FLAG_FORCE_PATHLOOP) != 0;
     const bool pathloop = !split && brute && want_pathloop && !(p->flags & RRS_FLAG_FORCE_QUEUES);
     if (pathloop) {
         // small scene: register-resident paths, no queues (k_pathloop)

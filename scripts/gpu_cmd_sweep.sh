@@ -1,7 +1,3 @@
-cp rayrs_b200/librayrs_b200.so /tmp/orig.so
-for v in orig 8_8 8_7; do
-if [ $v = orig ]; then cp /tmp/orig.so rayrs_b200/librayrs_b200.so; else cp _variants/lib_$v.so rayrs_b200/librayrs_b200.so; fi
-python scripts/gpu_dev.py c5 0 16 2>&1 | grep -v "scene build" | sed "s/^/v=$v /"
-python scripts/gpu_dev.py c3 0 64 2>&1 | grep -v "scene build" | sed "s/^/v=$v /"
-done | tee gpurun_out/sweep_occ3.log
-cp /tmp/orig.so rayrs_b200/librayrs_b200.so
+python -m pytest tests -m gpu -x -q -k "not full_size" 2>&1 | tail -3
+python scripts/gpu_dev.py c1,c2,c3 | grep -v "scene build" | tee gpurun_out/sweep_smallfused.log
+python scripts/gpu_dev.py c2 262144,1048576,2097152,8388608 128 | grep -v "scene build" | tee -a gpurun_out/sweep_smallfused.log

@@ -140,7 +140,7 @@ def test_shapes_queues_and_limits(hdri_small):
             assert st["rays"] == rays0                      # the set of paths does not depend on queue size / kernel form
             assert np.allclose(img, base, rtol=2e-5, atol=1e-6)  # only the fp32 summation order differs
             if flags in (0, api._ffi.RRS_FLAG_FORCE_QUEUES):
-                assert st["kernel_launches"] == 2  # path loop / fused wavefront: 1 render + 1 resolve
+                assert st["kernel_launches"] == 2  # fused wavefront: 1 render + 1 resolve
     # depth limits: max_bounces = 1 traces exactly one ray per path; 0 renders black (lib.rs:525,559)
     for mb in (1, 2, 3):
         img = api.render_gpu(cam, sc, 8, mb).astype(np.float64)
@@ -196,11 +196,11 @@ def test_sample_split_accumulate_and_census(hdri_small):
 
 
 def test_path_loop_and_queues_trace_the_same_paths(hdri_small):
-    """Small scenes render with the register-resident path loop (k_pathloop), transmissive ones with the queued
-    wavefront kernel by default; both forms must trace the same set of paths and agree up to fp32 rounding."""
+    """Small scenes can render with the register-resident path loop (k_pathloop) instead of the queued wavefront
+    kernel; both forms must trace the same set of paths and agree up to fp32 rounding."""
     F = api._ffi
-    for builder, a, b in ((lambda: scenes.cook_torrance_spheres_plastic(120, 48), 0, F.RRS_FLAG_FORCE_QUEUES),
-                          (lambda: scenes.diffuse_single_sphere(96, 64), 0, F.RRS_FLAG_FORCE_QUEUES),
+    for builder, a, b in ((lambda: scenes.cook_torrance_spheres_plastic(120, 48), F.RRS_FLAG_FORCE_PATHLOOP, 0),
+                          (lambda: scenes.diffuse_single_sphere(96, 64), F.RRS_FLAG_FORCE_PATHLOOP, F.RRS_FLAG_FORCE_QUEUES),
                           (lambda: scenes.cook_torrance_spheres_frosted_glass(120, 40), F.RRS_FLAG_FORCE_PATHLOOP, 0),
                           (lambda: scenes.glass_single_sphere(96, 64), F.RRS_FLAG_FORCE_PATHLOOP, F.RRS_FLAG_FORCE_QUEUES),
                           # all nine Material variants: the path loop shades with material_evaluate_cases, the

@@ -76,10 +76,26 @@ __global__ void k_plan(DCounters* c) {
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ bool primary_ray(const RenderConst& rc, unsigned long long p, uint32_t& pixel, uint32_t& sample,
                                             float3& d) {
-    const uint32_t s_local = (uint32_t)(p / rc.npix_pad);
-    const uint32_t pq = (uint32_t)(p - (unsigned long long)s_local * rc.npix_pad);
+    // (sample, tile, lane) from the path index without 64-bit or 32-bit hardware division where the host could
+    // prove the multiply-high forms exact (rc.small_index): p < 2^32, and tiles * tiles_x < 2^32
+    uint32_t s_local, pq, ty;
+    if (rc.small_index) {
+        const uint32_t p32 = (uint32_t)p;
+        s_local = __umulhi(p32, rc.magic_npix);
+        pq = p32 - s_local * (uint32_t)rc.npix_pad;
+        if (pq >= (uint32_t)rc.npix_pad) {  // the magic quotient can be one short
+            pq -= (uint32_t)rc.npix_pad;
+            ++s_local;
+        }
+        ty = __umulhi(pq >> 5, rc.magic_tiles_x);
+        if ((pq >> 5) - ty * rc.tiles_x >= rc.tiles_x) ++ty;
+    } else {
+        s_local = (uint32_t)(p / rc.npix_pad);
+        pq = (uint32_t)(p - (unsigned long long)s_local * rc.npix_pad);
+        ty = (pq >> 5) / rc.tiles_x;
+    }
     const uint32_t tile = pq >> 5, l = pq & 31u;
-    const uint32_t ty = tile / rc.tiles_x, tx = tile - ty * rc.tiles_x;
+    const uint32_t tx = tile - ty * rc.tiles_x;
     const uint32_t col = tx * 8u + (l & 7u);
     const uint32_t row = ty * 4u + (l >> 3);
     if (!rc.exact_tiles && !(col < rc.cam.W && row < rc.cam.H)) return false;  // padded tile lane outside the image
@@ -1043,6 +1059,10 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     rc.tiles_y = (p->height + 3u) / 4u;
     rc.exact_tiles = exact_tiles ? 1u : 0u;
     rc.npix_pad = (unsigned long long)rc.tiles_x * rc.tiles_y * 32ull;
+    // floor(2^32 / d): __umulhi(n, magic) is floor(n / d) or one less for every n < 2^32 (corrected on the device)
+    rc.small_index = (rc.npix_pad * (unsigned long long)p->spp < (1ull << 32)) ? 1u : 0u;
+    rc.magic_npix = (uint32_t)std::min<unsigned long long>((1ull << 32) / rc.npix_pad, 0xFFFFFFFFull);
+    rc.magic_tiles_x = (uint32_t)std::min<unsigned long long>((1ull << 32) / rc.tiles_x, 0xFFFFFFFFull);
     rc.spp = p->spp;
     rc.sample_offset = p->sample_offset;
     rc.max_bounces = p->max_bounces;

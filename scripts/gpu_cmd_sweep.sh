@@ -1,3 +1,2 @@
 python -m pytest tests -m gpu -x -q -k "not full_size" 2>&1 | tail -3
-python scripts/gpu_dev.py c1,c2,c3 | grep -v "scene build" | tee gpurun_out/sweep_smallfused.log
-python scripts/gpu_dev.py c2 262144,1048576,2097152,8388608 128 | grep -v "scene build" | tee -a gpurun_out/sweep_smallfused.log
+python scripts/gpu_dev.py c1,c2,c3 | grep -v "scene build" | tee gpurun_out/sweep_micro.log

@@ -300,8 +300,6 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
     }
     // rays of a deep tree differ widely in length: refill early; a tiny scene amortises the fetch over more lanes
     s.d.refill_lanes = desc->max_depth > 6 ? 4u : 12u;
-    s.d.dev = 0u;
-    if (const char* e = std::getenv("RRS_DEV")) s.d.dev = (uint32_t)std::atoi(e);
     s.d.node_steps = 4u;  // measured best: 3-4 (gpurun_out/sweep_tune*.log)
     if (const char* e = std::getenv("RRS_REFILL_LANES")) s.d.refill_lanes = std::min(32, std::max(1, std::atoi(e)));
     if (const char* e = std::getenv("RRS_NODE_STEPS")) s.d.node_steps = std::min(15, std::max(1, std::atoi(e)));

@@ -135,7 +135,6 @@ struct DScene {
     uint32_t brute_count;    // > 0: that many reachable primitives in total -> no BVH, test them all (intersect.cuh)
     uint32_t brute_prim[8];  // their indices, ascending (DFS order); RRS_BRUTE_MAX entries
     uint32_t refill_lanes;   // extend refills a warp with new rays once this many lanes are idle
-    uint32_t dev;            // development knobs (only read when built with -DRRS_DEV_KNOBS)
     uint32_t node_steps;     // inner-node steps a lane may take per ballot round of the batched traversal
 };
 

@@ -289,7 +289,17 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
         const char* e = std::getenv("RRS_NO_BRUTE");
         if (small && !reach.empty() && !(e && std::atoi(e))) {
             s.d.brute_count = (uint32_t)reach.size();
-            for (size_t k = 0; k < reach.size(); ++k) s.d.brute_prim[k] = reach[k];
+            // grouped by type (spheres, planes, triangles), DFS order inside a group
+            std::stable_sort(reach.begin(), reach.end(), [&](uint32_t x, uint32_t y) {
+                auto rank = [&](uint32_t i) { return desc->prims[i].type == RRS_SPHERE ? 0 : (desc->prims[i].type == RRS_PLANE ? 1 : 2); };
+                return rank(x) < rank(y);
+            });
+            s.d.brute_spheres = s.d.brute_planes = 0;
+            for (size_t k = 0; k < reach.size(); ++k) {
+                s.d.brute_prim[k] = reach[k];
+                if (desc->prims[reach[k]].type == RRS_SPHERE) s.d.brute_spheres++;
+                else if (desc->prims[reach[k]].type == RRS_PLANE) s.d.brute_planes++;
+            }
         }
     }
     {

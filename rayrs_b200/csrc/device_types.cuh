@@ -133,7 +133,8 @@ struct DScene {
     uint32_t has_triangles;  // 0: no triangle in the scene (the per-leaf shear setup is skipped)
     uint32_t root;           // node the traversal starts at (the virtual root's only child when that is an inner node)
     uint32_t brute_count;    // > 0: that many reachable primitives in total -> no BVH, test them all (intersect.cuh)
-    uint32_t brute_prim[8];  // their indices, ascending (DFS order); RRS_BRUTE_MAX entries
+    uint32_t brute_prim[8];  // their indices: spheres, then planes, then triangles, DFS order inside a group
+    uint32_t brute_spheres, brute_planes;  // group sizes (triangles: the rest)
     uint32_t refill_lanes;   // extend refills a warp with new rays once this many lanes are idle
     uint32_t node_steps;     // inner-node steps a lane may take per ballot round of the batched traversal
 };

@@ -1,18 +1,22 @@
-// Wavefront path tracer for sm_100a: persistent generate / extend / shade kernels over ray and
-// hit queues in HBM.  Replaces the pixel x spp x bounce loops of rayrs/src/main.rs:61-94 and
+// Wavefront path tracer for sm_100a.  Replaces the pixel x spp x bounce loops of rayrs/src/main.rs:61-94 and
 // rayrs-lib/src/lib.rs:521-560.
 //
-// One iteration = plan -> generate -> extend -> shade:
-//   plan     (1 thread)  sizes the iteration on the device: how many survivors, how many new
-//                        paths fit into the queue (path regeneration keeps the queue full);
-//   generate             Camera::generate_primary_ray (lib.rs:202-210) for new paths, appended
-//                        behind the survivors with a warp-aggregated atomic;
-//   extend               closest hit per ray (intersect.cuh), persistent warps fetch 32-ray
-//                        batches from a global cursor;
-//   shade                Material::evaluate + Russian roulette + background; survivors are
-//                        compacted into the other queue (__ballot_sync/__popc + one atomicAdd
-//                        per warp); terminated paths add their radiance to the fp32 accumulator
-//                        with one 128-bit reduction.
+// A render is ONE launch of the persistent kernel k_wavefront.  Block b owns stripe b of the ray / state / hit
+// queues in HBM and loops until the global path cursor is exhausted and its stripe has drained:
+//   BVH form (k_wavefront<false,..>), per iteration of a block:
+//     generate   Camera::generate_primary_ray (lib.rs:202-210) for new paths, appended behind the stripe's
+//                survivors (path regeneration keeps the stripe full);
+//     extend     closest hit per ray (intersect.cuh): warp-batched traversal of the flattened reference BVH with
+//                dynamic ray fetch, traversal stacks in shared memory;
+//     shade      Material::evaluate + emission + Russian roulette + background (shade_hit / shade_miss); survivors
+//                are compacted into the other half of the stripe (__ballot_sync/__popc + one shared-memory
+//                atomicAdd per warp); terminated paths add their radiance to the fp32 accumulator with one
+//                128-bit reduction.
+//   small-scene form (k_wavefront<true,..>, <= 8 primitives): one fused pass per iteration
+//     (small_scene_iteration): survivors read from the queue, new paths generated in registers, closest hit by
+//     brute force over the primitives staged in shared memory, shading, compaction.
+// k_generate / k_extend / k_shade (+ k_plan) are the same phases as separate launches (RRS_FLAG_SPLIT_KERNELS, for
+// per-phase profiling); k_pathloop is the register-resident alternative for small scenes (RRS_FLAG_FORCE_PATHLOOP).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>

@@ -28,7 +28,10 @@
 
 namespace rrs {
 
-static constexpr int kBlock = 128;  // threads per block of the persistent kernels
+#ifndef RRS_BLOCK_THREADS
+#define RRS_BLOCK_THREADS 128
+#endif
+static constexpr int kBlock = RRS_BLOCK_THREADS;  // threads per block of the persistent kernels
 #ifndef RRS_BLOCKS_PER_SM
 #define RRS_BLOCKS_PER_SM 8
 #endif

@@ -1,2 +1,6 @@
-python -m pytest tests -m gpu -x -q -k "not full_size" 2>&1 | tail -3
-python scripts/gpu_dev.py c1,c2,c3 | grep -v "scene build" | tee gpurun_out/sweep_grouped.log
+cp rayrs_b200/librayrs_b200.so /tmp/orig.so
+for v in orig 256 64; do
+if [ $v = orig ]; then cp /tmp/orig.so rayrs_b200/librayrs_b200.so; else cp _variants/lib_$v.so rayrs_b200/librayrs_b200.so; fi
+python scripts/gpu_dev.py c2,c4 0 64 2>&1 | grep -v "scene build" | sed "s/^/block=$v /"
+done | tee gpurun_out/sweep_block.log
+cp /tmp/orig.so rayrs_b200/librayrs_b200.so

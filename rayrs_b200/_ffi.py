@@ -115,6 +115,7 @@ HOST_SYMBOLS = {
     "rrh_camera_new": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_uint32,
                                   C.POINTER(RrsCamera)]),
     "rrh_load_mesh": (C.c_void_p, [C.c_char_p, C.c_int, C.POINTER(C.c_uint64)]),
+    "rrh_load_obj_spheres": (C.c_void_p, [C.c_char_p, C.c_double, C.POINTER(C.c_uint64)]),
     "rrh_free": (None, [C.c_void_p]),
     "rrh_write_ply": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int]),
     "rrh_ply_describe": (C.c_int, [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]),

@@ -148,6 +148,23 @@ double* rrh_load_mesh(const char* path, int kind, uint64_t* n_tris) {
         return nullptr;
     }
 }
+// load_obj_file_spheres: returns n x 3 doubles (centres), free with rrh_free
+double* rrh_load_obj_spheres(const char* path, double radius, uint64_t* n) {
+    try {
+        std::vector<Sphere> sp = load_obj_file_spheres(path, radius);
+        double* out = static_cast<double*>(std::malloc(sizeof(double) * 3 * std::max<size_t>(sp.size(), 1)));
+        for (size_t i = 0; i < sp.size(); ++i) {
+            out[3 * i] = sp[i].origin.x;
+            out[3 * i + 1] = sp[i].origin.y;
+            out[3 * i + 2] = sp[i].origin.z;
+        }
+        *n = sp.size();
+        return out;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
 void rrh_free(void* p) { std::free(p); }
 
 // format 0 = ascii, 1 = binary_big_endian, 2 = binary_little_endian

@@ -382,6 +382,13 @@ std::vector<Object> Object::from_triangles(const std::vector<Triangle>& tris, Ma
     return out;
 }
 
+std::vector<Object> Object::from_spheres(const std::vector<Sphere>& spheres, Material mat, Emission emission) {
+    std::vector<Object> out;
+    out.reserve(spheres.size());
+    for (const Sphere& sp : spheres) out.push_back(Object::sphere(sp.radius, sp.origin, mat, emission));
+    return out;
+}
+
 std::vector<Triangle> load_ply_file(const std::string& filename) { return ply::Ply::load(filename).triangles(); }
 
 // wavefront_obj::load_obj_file (wavefront_obj.rs:15-44): "v x y z" and "f i j k" lines split on single
@@ -418,6 +425,29 @@ std::vector<Triangle> load_obj_file(const std::string& filename) {
         }
     }
     return triangles;
+}
+
+// wavefront_obj::load_obj_file_spheres (wavefront_obj.rs:46-66): one sphere of `radius` per "v x y z" line
+std::vector<Sphere> load_obj_file_spheres(const std::string& filename, double radius) {
+    std::ifstream f(filename);
+    if (!f) throw IoError(IoError::NotFound, "No such file or directory: " + filename);
+    std::vector<Sphere> spheres;
+    std::string text;
+    auto parse_f64 = [](const std::string& s) {
+        char* end = nullptr;
+        double v = std::strtod(s.c_str(), &end);
+        if (s.empty() || end != s.c_str() + s.size()) throw Panic("called `Result::unwrap()` on an `Err` value: ParseFloatError");
+        return v;
+    };
+    while (std::getline(f, text)) {
+        if (!text.empty() && text.back() == '\r') text.pop_back();
+        std::vector<std::string> v = ply::split_space(text);
+        if (v[0] == "v") {
+            if (v.size() < 4) throw Panic("index out of bounds");
+            spheres.push_back(Sphere{radius, Vec3(parse_f64(v[1]), parse_f64(v[2]), parse_f64(v[3]))});
+        }
+    }
+    return spheres;
 }
 
 }  // namespace rayrs

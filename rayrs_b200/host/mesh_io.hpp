@@ -27,9 +27,13 @@ struct IoError : std::runtime_error {
     IoError(Kind k, const std::string& msg) : std::runtime_error(msg), kind(k) {}
 };
 
-// geometry.rs:312-355 — what the loaders return; Object::from_triangles wraps them
+// geometry.rs:312-355 / 78-101 — what the loaders return; Object::from_triangles / from_spheres wrap them
 struct Triangle {
     Vec3 p1, p2, p3;
+};
+struct Sphere {
+    double radius;
+    Vec3 origin;
 };
 
 namespace ply {
@@ -108,5 +112,6 @@ void write_ply(const std::string& path, const std::vector<float>& xyz, const std
 
 std::vector<Triangle> load_ply_file(const std::string& filename);  // PLY twin of load_obj_file
 std::vector<Triangle> load_obj_file(const std::string& filename);  // wavefront_obj.rs:15-44
+std::vector<Sphere> load_obj_file_spheres(const std::string& filename, double radius);  // wavefront_obj.rs:46-66: a sphere per vertex
 
 }  // namespace rayrs

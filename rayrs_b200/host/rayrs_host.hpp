@@ -110,6 +110,8 @@ struct Object {
     static std::vector<Object> box_geom(Vec3 lower_left, Vec3 upper_right, Material mat, Emission emission);
     // lib.rs:407-415: one object per triangle of a loaded mesh (mesh_io.hpp), all with the same material
     static std::vector<Object> from_triangles(const std::vector<struct Triangle>& tris, Material mat, Emission emission);
+    // lib.rs:423-431: the same for spheres (e.g. one per vertex of a mesh, wavefront_obj::load_obj_file_spheres)
+    static std::vector<Object> from_spheres(const std::vector<struct Sphere>& spheres, Material mat, Emission emission);
     AxisAlignedBoundingBox bbox() const { return geom.bbox(); }
 };
 

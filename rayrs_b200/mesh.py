@@ -41,6 +41,21 @@ def load_obj_file(path) -> np.ndarray:
     return _load(path, 1)
 
 
+def load_obj_file_spheres(path) -> np.ndarray:
+    """wavefront_obj::load_obj_file_spheres: the (n, 3) vertex positions, one sphere centre each — hand them to
+    Object.from_spheres(centers, radius, mat)."""
+    lib = _ffi.host_lib()
+    n = C.c_uint64(0)
+    ptr = lib.rrh_load_obj_spheres(os.fsencode(str(path)), 1.0, C.byref(n))
+    if not ptr:
+        raise MeshError(lib.rrh_last_error().decode())
+    try:
+        out = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(max(n.value, 1) * 3,))[: n.value * 3].copy()
+    finally:
+        lib.rrh_free(ptr)
+    return out.reshape(-1, 3)
+
+
 def write_ply(path, vertices: np.ndarray, faces: np.ndarray, fmt: str = "binary_little_endian") -> None:
     """float32 xyz vertices + uchar-count int32 triangle faces."""
     v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)

@@ -163,3 +163,17 @@ def test_obj_loader_matches_reference_rules(tmp_path, native_built):
     p.write_text("v  0 0 0\n")  # double space -> empty field -> ParseFloatError in the reference
     with pytest.raises(mesh.MeshError, match="ParseFloatError"):
         mesh.load_obj_file(p)
+
+
+def test_obj_spheres_loader(tmp_path, native_built):
+    """wavefront_obj.rs:46-66: a sphere per 'v' line; faces and everything else ignored."""
+    from rayrs_b200.api import Material, Object, build_tables
+    p = tmp_path / "pts.obj"
+    p.write_text("v 0 0 0\nv 1 0 0.5\nf 1 2 1\nvn 0 0 1\nv -2 3 4\n")
+    c = mesh.load_obj_file_spheres(p)
+    assert np.array_equal(c, [[0, 0, 0], [1, 0, 0.5], [-2, 3, 4]])
+    rows = build_tables([Object.from_spheres(c, 0.25, Material.no_reflect())]).objs   # Object::from_spheres lib.rs:423-431
+    assert rows.shape[0] == 3 and (rows[:, 0] == 0).all() and (rows[:, 3] == 0.25).all() and np.array_equal(rows[:, 4:7], c)
+    p.write_text("v 0 0\n")
+    with pytest.raises(mesh.MeshError, match="index out of bounds"):
+        mesh.load_obj_file_spheres(p)

@@ -235,6 +235,17 @@ def copper_torus(nu=1000, nv=500, width_px=1920, height_px=1080, heuristic: BvhH
     return SceneSpec(f"copper_torus_{2 * nu * nv}", cam, objects, heuristic or BvhHeuristic.Sah(1000))
 
 
+def glass_torus(nu=200, nv=100, width_px=1920, height_px=1080, heuristic: BvhHeuristic | None = None) -> SceneSpec:
+    """glass_suzanne (test_scenes.rs:164-167): the obj_scene template with Glass(1, 1.45) on the mesh — refraction
+    through a closed triangle mesh (rays spawned on a triangle, travelling inside, leaving through another)."""
+    w, h = film(width_px, height_px)
+    mat = Material.glass((1, 1, 1), 1.45)
+    verts, faces = torus_mesh(nu, nv)
+    objects = [_floor(), Object.from_triangles(mesh_via_ply(verts, faces, f"torus_{nu}x{nv}_glass"), mat, Emission.Dark())]
+    cam = dict(origin=(0.0, 5.0, 10.0), up=(0.0, 1.0, 0.0), lookat=(0.0, 1.0, 0.0), fov=50.0, width=w, height=h, ppi=PPI)
+    return SceneSpec(f"glass_torus_{2 * nu * nv}", cam, objects, heuristic or BvhHeuristic.Sah(1000))
+
+
 def mixed_scene(nu=2000, nv=1000, width_px=3840, height_px=2160, heuristic: BvhHeuristic | None = None) -> SceneSpec:
     """Config 5: the seven spheres of multiple_spheres (test_scenes.rs:178-189) with the in-scope
     materials of material_test (:276-289), a synthetic torus behind the row, and the floor."""

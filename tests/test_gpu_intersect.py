@@ -46,6 +46,7 @@ SCENES = {
     "copper_torus_20k": lambda: scenes.copper_torus(100, 100, 256, 192),
     "copper_torus_20k_midpoint": lambda: scenes.copper_torus(100, 100, 256, 192, heuristic=BvhHeuristic.Midpoint()),
     "mixed_5k": lambda: scenes.mixed_scene(50, 50, 320, 180),
+    "glass_torus_5k": lambda: scenes.glass_torus(50, 50, 256, 192),
 }
 
 

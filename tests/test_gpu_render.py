@@ -63,6 +63,7 @@ DIELECTRIC = {
     "material_test": (lambda: scenes.material_test(280, 56), 64),
     "spheres_ct_refract": (lambda: scenes.cook_torrance_spheres_cook_torrance_refract(240, 80), 64),
     "mixed_small": (lambda: scenes.mixed_scene(40, 40, 240, 135), 48),
+    "glass_torus_3200": (lambda: scenes.glass_torus(40, 40, 192, 128), 48),   # glass_suzanne: a refractive triangle mesh
 }
 
 

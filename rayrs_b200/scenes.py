@@ -246,6 +246,23 @@ def glass_torus(nu=200, nv=100, width_px=1920, height_px=1080, heuristic: BvhHeu
     return SceneSpec(f"glass_torus_{2 * nu * nv}", cam, objects, heuristic or BvhHeuristic.Sah(1000))
 
 
+def emissive_room(width_px=240, height_px=160) -> SceneSpec:
+    """Not a reference scene (every shipped one is Emission::Dark, SURVEY.md F11): an emissive sphere and an emissive
+    panel light a Lambertian sphere, a plastic sphere and a box (Object::box_geom: planes on all six axis variants)
+    standing on the usual floor — exercises Emission::Emissive gathering (lib.rs:533-547, only in the Scatter arm)."""
+    w, h = film(width_px, height_px)
+    white = Material.lambertian_diffuse((0.8, 0.8, 0.8))
+    objects = [
+        _floor(),
+        Object.sphere(0.6, (-2.4, 0.6, 0.0), white, Emission.new(6.0, (1.0, 0.7, 0.4))),
+        Object.sphere(1.0, (0.0, 1.0, 0.0), white),
+        Object.sphere(0.8, (2.2, 0.8, 0.4), Material.plastic((0.2, 0.5, 0.8), (1, 1, 1), 0.1, 1.45)),
+        Object.plane(Axis.YRev, -1.5, 1.5, -1.5, 1.5, 4.0, Material.lambertian_diffuse((0.5, 0.5, 0.5)), Emission.new(3.0, (0.6, 0.8, 1.0))),
+    ] + Object.box_geom((-1.0, 0.0, 1.6), (-0.2, 0.9, 2.4), Material.cook_torrance((1, 1, 1), 0.2, Fresnel.schlick_metallic((0.9, 0.6, 0.3))))
+    cam = dict(origin=(0.0, 3.0, 9.0), up=(0.0, 1.0, 0.0), lookat=(0.0, 1.0, 0.0), fov=50.0, width=w, height=h, ppi=PPI)
+    return SceneSpec("emissive_room", cam, objects, BvhHeuristic.Sah(1000))
+
+
 def mixed_scene(nu=2000, nv=1000, width_px=3840, height_px=2160, heuristic: BvhHeuristic | None = None) -> SceneSpec:
     """Config 5: the seven spheres of multiple_spheres (test_scenes.rs:178-189) with the in-scope
     materials of material_test (:276-289), a synthetic torus behind the row, and the floor."""

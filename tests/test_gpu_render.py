@@ -29,6 +29,7 @@ OPAQUE = {
     "spheres_metallic": (lambda: scenes.cook_torrance_spheres_metallic(240, 96), 64, 50),
     "spheres_plastic": (lambda: scenes.cook_torrance_spheres_plastic(240, 96), 64, 50),
     "copper_torus_5k": (lambda: scenes.copper_torus(50, 50, 192, 128), 32, 50),
+    "emissive_room": (lambda: scenes.emissive_room(240, 160), 64, 50),   # Emission::Emissive + box_geom planes (11 primitives: BVH path)
 }
 
 

@@ -219,15 +219,14 @@ def run_ours(args):
         """inputs resident in HBM; returns (rays, launches, phase dict)"""
         rays = launches = 0
         ph = {"generate_ms": 0.0, "extend_ms": 0.0, "shade_ms": 0.0, "iterations": 0, "device_ms": 0.0, "kernel_form": 0}
-        flush.fill_(1)  # L2 flush between timed iterations (inside the region: ~0.1 ms)
-        launches += 1
+        flush.fill_(1)  # L2 flush between timed iterations (inside the region: ~0.1 ms); a torch kernel, not counted
         for k, (spec, sc, cam) in enumerate(built):
             acc[k].zero_()
             api.render_accumulate(cam, sc, spp, cfg.max_bounces, acc[k].data_ptr(), sptr, sample_offset=first,
                                   spp_total=spp_total, queue_capacity=args.queue, flags=flags)
             st = sc.stats()
             rays += st["rays"]
-            launches += st["kernel_launches"] + 1
+            launches += st["kernel_launches"]  # OUR kernels only (the render kernel); torch's zero_ / fill_ are not counted
             for key in ph:
                 ph[key] = st[key] if key == "kernel_form" else ph[key] + st[key]
             if world > 1:

@@ -375,3 +375,91 @@ def test_cook_torrance_glass_restatement(alpha):
             assert np.allclose(got[k, 4:7], l, rtol=0, atol=1e-11)
             assert np.allclose(got[k, 1:4], c, rtol=1e-8, atol=1e-13), (k, got[k, 1:4], c)
     assert len(kinds) == 4   # reflected and transmitted, from outside and from inside
+
+
+# ---- the whole path: main.rs:61-94 (pixel loop, F8 index mapping) -> generate_primary_ray -> radiance (lib.rs:521-560:
+#      closest hit with the leaf filter t > tmin && t < tmax, emission only in the Scatter arm, Russian roulette from
+#      bounce 0 with true division) -> Sphere / Plane intersect (geometry.rs:106-132, 229-271) -> background,
+#      as a pure-Python path tracer on the diffuse_single_sphere scene, consuming the oracle's counter-based uniforms
+def background_ref(px, W, H, d):
+    u = unit(d)
+    phi = np.arctan2(u[2], u[0]) + np.pi
+    theta = np.arccos(u[1])
+    x, y = phi / (2.0 * np.pi) * (W - 1), theta / np.pi * (H - 1)
+    xf, xc, yf, yc = np.floor(x), np.ceil(x), np.floor(y), np.ceil(y)
+    i, j = int(yf), int(xf)
+    return (px[i, j] * (xc - x) * (yc - y) + px[i + 1, j] * (xc - x) * (y - yf) + px[i, j + 1] * (x - xf) * (yc - y)
+            + px[i + 1, j + 1] * (x - xf) * (y - yf))
+
+
+def sphere_ref(radius2, c, o, d):
+    od = o - c
+    a, b, cc = d @ d, 2.0 * (d @ od), od @ od - radius2
+    desc = b * b - 4.0 * a * cc
+    if not desc > 0.0:
+        return None
+    t1, t2 = (-b - np.sqrt(desc)) / (2.0 * a), (-b + np.sqrt(desc)) / (2.0 * a)
+    if t1 < 0.0:
+        return None if t2 < 0.0 else t2
+    return t1
+
+
+def floor_ref(o, d):   # Plane(Axis::Y, -25..25, -25..25, pos 0): half-open ranges, any sign of t
+    if d[1] == 0.0:
+        return None
+    t = (0.0 - o[1]) / d[1]
+    p = o + t * d
+    return t if (-25.0 <= p[0] < 25.0 and -25.0 <= p[2] < 25.0) else None
+
+
+def test_whole_path_restatement():
+    W, H, spp, max_bounces, seed = 12, 8, 3, 8, 0x5EEDB200
+    hdri = scenes.synthetic_hdri(64, 32)
+    px = np.asarray(hdri.pixels, dtype=np.float64).reshape(32, 64, 3)
+    spec = scenes.diffuse_single_sphere(W, H)
+    osc = oracle.OracleScene(spec.tables(), hdri.pixels)
+    cam = spec.camera().derived17()
+    want, st = osc.render(cam, W, H, spp, max_bounces=max_bounces, seed=seed, nthreads=1)
+    origin, e_x, e_y, zs, width, height, ppc = cam[0:3], cam[3:6], cam[6:9], cam[9:12], cam[12], cam[13], cam[14]
+    tmin, tmax = 1e-6, 1e6
+    got = np.zeros((H, W, 3))
+    rays = 0
+    for row in range(H):
+        for col in range(W):
+            pixel = row * W + col
+            acc = np.zeros(3)
+            for s in range(spp):
+                u = oracle.rng_uniforms(seed, pixel, s, 0)
+                x = (float(W - col) + u[0]) / ppc - width / 2.0
+                y = (float(H - row) + u[1]) / ppc - height / 2.0
+                o, d = origin.copy(), zs + x * e_x + y * e_y
+                thr, light = np.ones(3), np.zeros(3)
+                for b in range(max_bounces):
+                    rays += 1
+                    best, which = None, None
+                    for name, t in (("floor", floor_ref(o, d)), ("sphere", sphere_ref(1.0, np.array([0.0, 1.0, 0.0]), o, d))):
+                        if t is not None and t > tmin and t < tmax and (best is None or t < best):
+                            best, which = t, name
+                    if best is None:
+                        light = light + thr * background_ref(px, 64, 32, d)
+                        break
+                    pos = o + best * d
+                    view = unit(-1.0 * d)
+                    uu = oracle.rng_uniforms(seed, pixel, s, b + 1)
+                    if which == "sphere":
+                        f, color, l = lambertian_ref(np.array([0.8, 0.8, 0.8]), unit(pos - np.array([0.0, 1.0, 0.0])), view, uu)
+                    else:
+                        f, color, l = cook_torrance_ref(np.ones(3), 0.5, np.array([0.8, 0.8, 0.8]), np.array([0.0, 1.0, 0.0]), view, uu)
+                    if not f:
+                        break
+                    thr = thr * color                       # Emission::Dark: nothing to gather
+                    p = max(thr)
+                    if uu[3] > p:
+                        break
+                    thr = thr / p
+                    o, d = pos, l
+                acc += light
+            got[row, col] = acc / spp
+    assert rays == st["rays"]
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-12), np.abs(got - want).max()
+    osc.close()

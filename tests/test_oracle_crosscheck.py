@@ -463,3 +463,64 @@ def test_whole_path_restatement():
     assert rays == st["rays"]
     assert np.allclose(got, want, rtol=1e-9, atol=1e-12), np.abs(got - want).max()
     osc.close()
+
+
+# ---- the three "next" arms: Reflect (material.rs:283-303), Refract (:305-337), CookTorranceRefract (:426-467)
+def test_reflect_refract_ct_refract_restatements():
+    rng = np.random.default_rng(21)
+    col = np.array([0.9, 0.8, 0.7])
+    mats = [Material.reflect(tuple(col)), Material.refract(tuple(col), 1.45), Material.cook_torrance_refract(tuple(col), 0.2, 1.45)]
+    rows = build_tables([Object.sphere(1.0, (3.0 * k, 0, 0), m) for k, m in enumerate(mats)]).mats
+    n_s = 3000
+    nrm = np.array([unit(x) for x in rng.normal(size=(n_s, 3))])
+    view = np.array([unit(x) for x in rng.normal(size=(n_s, 3))])
+    u = rng.random((n_s, 3))
+    nv = np.concatenate([nrm, view], axis=1)
+    got = [oracle.material_evaluate(r, nv, u) for r in rows]
+    scat = 0
+    for k in range(n_s):
+        n, v = nrm[k], view[k]
+        # Reflect: Dirac pdf (value 1), brdf = color / |n.l|
+        l = 2.0 * (v @ n) * n - v
+        assert got[0][k, 0] == 1.0 and np.allclose(got[0][k, 4:7], l, atol=1e-13)
+        assert np.allclose(got[0][k, 1:4], col / abs(n @ l) * (n @ l), rtol=1e-12)
+        # Refract
+        entering = n @ v > 0.0
+        nn = n if entering else -n
+        ratio = 1.0 / 1.45 if entering else 1.45
+        l = refract_ref(nn, v, ratio)
+        if l is None:
+            assert got[1][k, 0] == 0.0
+        else:
+            btdf = np.zeros(3) if l @ v > 0.0 else col / abs(nn @ l)
+            assert got[1][k, 0] == 1.0 and np.allclose(got[1][k, 4:7], l, atol=1e-13)
+            assert np.allclose(got[1][k, 1:4], btdf * abs(nn @ l), rtol=1e-12)
+        # CookTorranceRefract: half vector about the FLIPPED normal, flipped back for the exiting case
+        a2 = 0.2 * 0.2
+        e1, e2 = basis(nn)
+        phi = 2.0 * np.pi * u[k, 0]
+        tan2 = -a2 * np.log(1.0 - u[k, 1])
+        cost = 1.0 / np.sqrt(1.0 + tan2)
+        sint = np.sqrt(1.0 - cost * cost)
+        h = np.cos(phi) * sint * e1 + np.sin(phi) * sint * e2 + cost * nn
+        pdf = np.exp(-tan2 / a2) / (np.pi * a2 * (nn @ h) ** 4)
+        if not entering:
+            h = -h
+        l = refract_ref(h, v, ratio)
+        if l is None:
+            assert got[2][k, 0] == 0.0, k
+            continue
+        nl = nn @ l
+        if h @ v < 0.0 or nl > 0.0:
+            assert got[2][k, 0] == 0.0, k
+            continue
+        hl, hv = abs(h @ l), abs(h @ v)
+        dwh = hl / (ratio * hv + hl) ** 2
+        c = ct_btdf(col, a2, 1.45, nn, l, v, entering) * abs(nl) / (ratio * ratio) / (pdf * dwh)
+        if not c.any():
+            assert got[2][k, 0] == 0.0, k
+            continue
+        scat += 1
+        assert got[2][k, 0] == 1.0 and np.allclose(got[2][k, 4:7], l, atol=1e-11)
+        assert np.allclose(got[2][k, 1:4], c, rtol=1e-8, atol=1e-13), (k, got[2][k, 1:4], c)
+    assert scat > 200

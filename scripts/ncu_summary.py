@@ -90,7 +90,7 @@ def metrics(rep: Path, out_csv: Path, out_stalls: Path):
     print(out_stalls.read_text())
 
 
-def update_model(metrics_csv: Path, key: str):
+def update_model(metrics_csv: Path, key: str, captured_rays: float = 0.0):
     """Copy the measured per-launch DRAM traffic and the pipe / issue evidence of the profiled kernel into
     profiles/bytes_per_ray.json[key]["ncu"], where bench.py picks up roofline.traffic."""
     import json
@@ -116,6 +116,10 @@ def update_model(metrics_csv: Path, key: str):
         "dram_pct_of_peak": mean("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
         "source": f"profiles/{metrics_csv.name}",
     }
+    if captured_rays:
+        # the capture rendered fewer samples per pixel than the bench command: bench.py scales the per-launch
+        # counts (DRAM bytes, warp instructions) by rays of its launch / rays of the captured launch
+        model[key]["ncu"]["rays_per_launch_captured"] = captured_rays
     model_path.write_text(json.dumps(model, indent=1) + "\n")
     print("updated", model_path, key, model[key]["ncu"])
 
@@ -126,6 +130,8 @@ if __name__ == "__main__":
     ap.add_argument("--launches", default=str(ROOT / "gpurun_out" / "launches.csv"))
     ap.add_argument("--rep", default=str(ROOT / "gpurun_out" / "prof.ncu-rep"))
     ap.add_argument("--model-key", default="", help="c1..c5: also record the capture in profiles/bytes_per_ray.json")
+    ap.add_argument("--captured-rays", type=float, default=0.0,
+                    help="rays traced by the captured launch when it was not the bench command itself (reduced spp)")
     a = ap.parse_args()
     prof = ROOT / "profiles"
     prof.mkdir(exist_ok=True)
@@ -134,4 +140,4 @@ if __name__ == "__main__":
     if Path(a.rep).exists():
         metrics(Path(a.rep), prof / f"{a.tag}_metrics.csv", prof / f"{a.tag}_stalls.txt")
         if a.model_key:
-            update_model(prof / f"{a.tag}_metrics.csv", a.model_key)
+            update_model(prof / f"{a.tag}_metrics.csv", a.model_key, a.captured_rays)

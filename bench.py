@@ -171,7 +171,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": secs / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg.description, "cpu_threads": threads,
-                   "note": "restated reference (oracle port, g++ -O2 -ffp-contract=off), not the Rust binary: no Rust toolchain in the image"},
+                   "note": "restated reference (oracle port, g++ -O3 -ffp-contract=off), not the Rust binary: no Rust toolchain in the image"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -27,7 +27,7 @@
 // counter-based Philox4x32-10 stream keyed by (seed; pixel, sample, slot) so that
 // results are reproducible and can be sample-matched with the GPU backend.
 //
-// Build: see oracle/Makefile (g++ -O2 -ffp-contract=off: Rust never contracts a*b+c).
+// Build: see oracle/Makefile (g++ -O3 -ffp-contract=off: Rust never contracts a*b+c).
 
 #include <algorithm>
 #include <atomic>

@@ -15,7 +15,7 @@ from rayrs_b200.api import BvhHeuristic
 
 pytestmark = pytest.mark.gpu
 
-N_RAYS = 1 << 17
+N_RAYS = 1 << 20  # 2^20 rays per scene
 
 
 def fixed_ray_set(spec, osc, n, seed=7):

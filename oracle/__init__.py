@@ -39,6 +39,7 @@ def lib() -> C.CDLL:
         L.orc_tree_dump.argtypes = [vp, vp, u64, vp, u64]
         L.orc_intersect.argtypes = [vp, vp, u64, vp, vp, i32]
         L.orc_intersect_stable.argtypes = [vp, vp, u64, dbl, dbl, vp, i32]
+        L.orc_intersect_sensitivity.argtypes = [vp, vp, u64, dbl, dbl, vp, vp, i32]
         L.orc_camera_new.argtypes = [vp, vp, vp, dbl, dbl, dbl, u32, vp]
         L.orc_primary_rays.argtypes = [vp, u32, u32, vp, vp, vp, u64, u64, i32, vp]
         L.orc_render.argtypes = [vp, vp, u32, u32, u32, u32, u32, u64, i32, i32, vp, vp]
@@ -122,6 +123,16 @@ class OracleScene:
         lib().orc_intersect_stable(self._p, r.ctypes.data, r.shape[0], eps_dir, eps_org, st.ctypes.data,
                                    nthreads or hardware_threads())
         return st.astype(bool)
+
+    def intersect_sensitivity(self, rays, eps_dir=2e-6, eps_org=2e-5, nthreads=0):
+        """(stable, tchange): the stability probe plus the largest relative change of t over its 12 perturbed
+        rays — how well conditioned t is with respect to the ray (0 where not stable or a miss)."""
+        r = _d(rays).reshape(-1, 6)
+        st = np.zeros(r.shape[0], dtype=np.uint8)
+        tc = np.zeros(r.shape[0], dtype=np.float64)
+        lib().orc_intersect_sensitivity(self._p, r.ctypes.data, r.shape[0], eps_dir, eps_org, st.ctypes.data,
+                                        tc.ctypes.data, nthreads or hardware_threads())
+        return st.astype(bool), tc
 
     def render(self, cam17, W, H, spp, max_bounces=50, seed=0x5EEDB200, sample_offset=0, rng_mode=RNG_MATCHED, nthreads=0):
         out = np.zeros((H, W, 3), dtype=np.float64)

@@ -1077,8 +1077,13 @@ void orc_intersect(const OrcScene* h, const double* rays, uint64_t n, int32_t* o
 // perturbations (direction +-eps*|d| and origin +-eps_o along each axis).  Rays that are not
 // stable sit within ~eps of a decision boundary (primitive edge, silhouette, t-tie, box
 // face) where an fp32 evaluation may legitimately decide differently.
-void orc_intersect_stable(const OrcScene* h, const double* rays, uint64_t n, double eps_dir, double eps_org,
-                          uint8_t* stable, int nthreads) {
+//
+// orc_intersect_sensitivity is the same probe with the largest relative change of t over the 12 perturbations
+// written to `tchange` (0 for misses and for rays that are not stable): the conditioning of t with respect to
+// the ray.  At grazing incidence on a triangle (|cos| ~ 0.01) a 2e-6 perturbation moves t by ~1e-4, and an
+// fp32 evaluation, whose rounding acts like a perturbation of a few 1e-7, cannot be asked for 1e-5 there.
+static void intersect_sensitivity(const OrcScene* h, const double* rays, uint64_t n, double eps_dir, double eps_org,
+                                  uint8_t* stable, double* tchange, int nthreads) {
     const Scene& s = h->s;
     auto work = [&](uint64_t lo, uint64_t hi) {
         for (uint64_t i = lo; i < hi; ++i) {
@@ -1087,6 +1092,7 @@ void orc_intersect_stable(const OrcScene* h, const double* rays, uint64_t n, dou
             int id0 = h0.hit ? h0.obj->id : -1;
             double dl = mag(r.d) * eps_dir;
             bool ok = true;
+            double worst = 0.0;
             for (int k = 0; k < 12 && ok; ++k) {
                 Ray q = r;
                 double sgn = (k & 1) ? -1. : 1.;
@@ -1098,9 +1104,14 @@ void orc_intersect_stable(const OrcScene* h, const double* rays, uint64_t n, dou
                 Hit hk = tree_intersect(s.bvh.get(), q, s.tmin, s.tmax);
                 int idk = hk.hit ? hk.obj->id : -1;
                 if (idk != id0) ok = false;
-                if (ok && hk.hit && std::fabs(hk.t - h0.t) > 1e-3 * std::fabs(h0.t)) ok = false;
+                if (ok && hk.hit) {
+                    double rel = std::fabs(hk.t - h0.t) / std::fabs(h0.t);
+                    if (rel > 1e-3) ok = false;
+                    worst = std::max(worst, rel);
+                }
             }
             stable[i] = ok ? 1 : 0;
+            if (tchange) tchange[i] = ok ? worst : 0.0;
         }
     };
     std::vector<std::thread> th;
@@ -1111,6 +1122,16 @@ void orc_intersect_stable(const OrcScene* h, const double* rays, uint64_t n, dou
         th.emplace_back(work, lo, hi);
     }
     for (auto& x : th) x.join();
+}
+
+void orc_intersect_stable(const OrcScene* h, const double* rays, uint64_t n, double eps_dir, double eps_org,
+                          uint8_t* stable, int nthreads) {
+    intersect_sensitivity(h, rays, n, eps_dir, eps_org, stable, nullptr, nthreads);
+}
+
+void orc_intersect_sensitivity(const OrcScene* h, const double* rays, uint64_t n, double eps_dir, double eps_org,
+                               uint8_t* stable, double* tchange, int nthreads) {
+    intersect_sensitivity(h, rays, n, eps_dir, eps_org, stable, tchange, nthreads);
 }
 
 // Camera::new -> derived fields.  out: origin(3) e_x(3) e_y(3) z(3) width height ppc xpix ypix

@@ -135,3 +135,25 @@ def test_triangle_basic():
     assert t is None
     t, _ = oracle.triangle_intersect(tri, [0, 0.25, 5, 1, 0, 0])  # parallel: NaN/inf quotients
     assert t is None or not np.isfinite(t)
+
+
+# ---- the conditioning probe the fp32 parity tests lean on
+def test_intersect_sensitivity_is_the_stability_probe_plus_conditioning():
+    from rayrs_b200 import scenes
+    hdri = scenes.synthetic_hdri(64, 32)
+    spec = scenes.copper_torus(24, 12, 64, 48)
+    osc = oracle.OracleScene(spec.tables(), hdri.pixels, heuristic=(spec.heuristic.kind, spec.heuristic.splits), build_mode=1)
+    cam = spec.camera()
+    rng = np.random.default_rng(3)
+    n = 4096
+    rays = oracle.primary_rays(cam.derived17(), 64, 48, rng.integers(0, 48, n), rng.integers(0, 64, n), rng.integers(0, 64, n))
+    oid, ot = osc.intersect(rays)
+    stable = osc.intersect_stable(rays)
+    st2, tchange = osc.intersect_sensitivity(rays)
+    assert np.array_equal(stable, st2)
+    assert np.all(tchange[~stable] == 0) and np.all(tchange[oid < 0] == 0)
+    hit = stable & (oid >= 0)
+    assert np.all(tchange[hit] <= 1e-3) and tchange[hit].max() > 0
+    # a head-on hit of the floor moves by about the perturbation itself; the probe must see that scale
+    floor = hit & (oid == 0)
+    assert floor.any() and np.median(tchange[floor]) < 1e-4

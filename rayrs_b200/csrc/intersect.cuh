@@ -198,6 +198,28 @@ struct TravCounters {
 // ---------------------------------------------------------------------------------------
 #define TRAV_DONE 0xFFFFFFFFu
 
+// Per-thread traversal stack in shared memory, addressed by a 32-bit shared address held in a register: entry e
+// of this thread lives at base + e * stride.  (As a generic pointer derived from threadIdx the compiler re-formed
+// the address — S2R tid, S2UR cta-in-cluster, 4 more — inside every divergent push and pop: 4 % of the warp
+// instructions of the traversal, profiles/r01n_c4.)
+struct SStack {
+    uint32_t base;    // shared-window address of entry 0
+    uint32_t stride;  // bytes between entries: 4 * threads per block
+    __device__ __forceinline__ void init(const uint32_t* entry0, uint32_t threads) {
+        uint32_t a = (uint32_t)__cvta_generic_to_shared(entry0);
+        asm volatile("mov.u32 %0, %1;" : "=r"(base) : "r"(a));  // opaque: keep it, do not rematerialise it
+        stride = 4u * threads;
+    }
+    __device__ __forceinline__ void set(uint32_t e, uint32_t v) const {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + e * stride), "r"(v));
+    }
+    __device__ __forceinline__ uint32_t get(uint32_t e) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + e * stride));
+        return v;
+    }
+};
+
 struct RayK {
     float3 o, d, idir;
     uint32_t selx, sely, selz;  // PRMT selectors: (near, far) = (lo, hi) or (hi, lo) by the sign of 1/d
@@ -213,7 +235,7 @@ struct Trav {
 
 template <bool SPH64>
 __device__ __forceinline__ void trav_begin(const DScene& sc, float3 o, float3 d, uint32_t origin_word,
-                                           const double* __restrict__ org64, uint32_t* stack, RayK& r, Trav& tv) {
+                                           const double* __restrict__ org64, const SStack& stack, RayK& r, Trav& tv) {
     // origin word: RRS_NO_PRIM, or primitive index | RRS_ORG64 (the ray carries its f64 origin in org64)
     r.o = o;
     r.d = d;
@@ -223,7 +245,7 @@ __device__ __forceinline__ void trav_begin(const DScene& sc, float3 o, float3 d,
     r.selx = r.idir.x < 0.f ? 0x1032u : 0x3210u;
     r.sely = r.idir.y < 0.f ? 0x1032u : 0x3210u;
     r.selz = r.idir.z < 0.f ? 0x1032u : 0x3210u;
-    stack[0] = TRAV_DONE;
+    stack.set(0u, TRAV_DONE);
     tv.cur = sc.root;
     tv.sp = 1;
     tv.tbest = sc.tmax;
@@ -235,7 +257,7 @@ __device__ __forceinline__ __half2 u32_as_half2(uint32_t v) { return *reinterpre
 
 // One inner node: both child boxes from one 2 x 256-bit fetch, near child first, far child pushed.
 template <bool COUNT>
-__device__ __forceinline__ void trav_node_step(const DScene& sc, const RayK& r, Trav& tv, uint32_t* stack, int stride,
+__device__ __forceinline__ void trav_node_step(const DScene& sc, const RayK& r, Trav& tv, const SStack& stack,
                                                TravCounters& cnt) {
     uint32_t w[8];
     RRS_CHECK(tv.cur < sc.n_nodes);
@@ -270,7 +292,7 @@ __device__ __forceinline__ void trav_node_step(const DScene& sc, const RayK& r, 
     if (go0 && go1) {
         const bool swap = n1 < n0;
         RRS_CHECK(tv.sp < sc.stack_entries);
-        stack[tv.sp * stride] = swap ? ref0 : ref1;
+        stack.set(tv.sp, swap ? ref0 : ref1);
         ++tv.sp;
         tv.cur = swap ? ref1 : ref0;
     } else if (go0 || go1) {
@@ -278,7 +300,7 @@ __device__ __forceinline__ void trav_node_step(const DScene& sc, const RayK& r, 
     } else {
         RRS_CHECK(tv.sp >= 1u);
         --tv.sp;
-        tv.cur = stack[tv.sp * stride];
+        tv.cur = stack.get(tv.sp);
     }
 }
 
@@ -319,7 +341,7 @@ __device__ __forceinline__ void test_prim(const DScene& sc, uint32_t pi, float4 
 
 // One leaf run (1..4 primitives, DFS order), then pop.
 template <bool COUNT, bool SPH64>
-__device__ __forceinline__ void trav_leaf_step(const DScene& sc, const RayK& r, Trav& tv, uint32_t* stack, int stride,
+__device__ __forceinline__ void trav_leaf_step(const DScene& sc, const RayK& r, Trav& tv, const SStack& stack,
                                                TravCounters& cnt) {
     const uint32_t first = tv.cur & 0x0FFFFFFFu;
     const uint32_t count = ((tv.cur >> 28) & 7u) + 1u;
@@ -347,7 +369,7 @@ __device__ __forceinline__ void trav_leaf_step(const DScene& sc, const RayK& r, 
         c = nc;
     }
     --tv.sp;
-    tv.cur = stack[tv.sp * stride];
+    tv.cur = stack.get(tv.sp);
 }
 
 // Small scenes (<= RRS_BRUTE_MAX reachable primitives, every sphere-series configuration): the BVH is
@@ -433,14 +455,14 @@ __device__ __forceinline__ void stage_brute_prims(const DScene& sc, DPrim* s_pri
 // Per-thread traversal to completion (parity probes; the render path batches the steps per warp).
 template <bool COUNT, bool SPH64>
 __device__ __forceinline__ void closest_hit(const DScene& sc, float3 o, float3 d, uint32_t origin_word,
-                                            const double* __restrict__ org64, uint32_t* stack, int stride, float& tbest,
+                                            const double* __restrict__ org64, const SStack& stack, float& tbest,
                                             uint32_t& best, TravCounters& cnt) {
     RayK r;
     Trav tv;
     trav_begin<SPH64>(sc, o, d, origin_word, org64, stack, r, tv);
     while (tv.cur != TRAV_DONE) {
-        while (trav_on_inner(tv)) trav_node_step<COUNT>(sc, r, tv, stack, stride, cnt);
-        if (tv.cur != TRAV_DONE) trav_leaf_step<COUNT, SPH64>(sc, r, tv, stack, stride, cnt);
+        while (trav_on_inner(tv)) trav_node_step<COUNT>(sc, r, tv, stack, cnt);
+        if (tv.cur != TRAV_DONE) trav_leaf_step<COUNT, SPH64>(sc, r, tv, stack, cnt);
     }
     tbest = tv.tbest;
     best = tv.best;

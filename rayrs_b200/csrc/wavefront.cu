@@ -239,8 +239,8 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
         flush_trav_counters<COUNT>(c, cnt);
         return;
     }
-    uint32_t* stack = s_stack + threadIdx.x;
-    const int stride = blockDim.x;
+    SStack stack;
+    stack.init(s_stack + threadIdx.x, blockDim.x);
     TravCounters cnt{0, 0};
     RayK r;
     Trav tv;
@@ -279,12 +279,12 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
             const uint32_t parked = __ballot_sync(FULL, !inner && tv.cur != TRAV_DONE);
             if (want == 0u || __popc(want) < __popc(parked)) break;
             if (inner) {
-                trav_node_step<COUNT>(sc, r, tv, stack, stride, cnt);
-                for (uint32_t k = 1; k < sc.node_steps && trav_on_inner(tv); ++k) trav_node_step<COUNT>(sc, r, tv, stack, stride, cnt);
+                trav_node_step<COUNT>(sc, r, tv, stack, cnt);
+                for (uint32_t k = 1; k < sc.node_steps && trav_on_inner(tv); ++k) trav_node_step<COUNT>(sc, r, tv, stack, cnt);
             }
         }
         // ---- leaves ----
-        if (!trav_on_inner(tv) && tv.cur != TRAV_DONE) trav_leaf_step<COUNT, SPH64>(sc, r, tv, stack, stride, cnt);
+        if (!trav_on_inner(tv) && tv.cur != TRAV_DONE) trav_leaf_step<COUNT, SPH64>(sc, r, tv, stack, cnt);
         if (has_ray && tv.cur == TRAV_DONE) {
             hits[my_i] = make_float2(tv.tbest, __uint_as_float(tv.best));
             has_ray = false;
@@ -887,6 +887,8 @@ __global__ void __launch_bounds__(kBlock) k_intersect32(DScene sc, const float4*
     __shared__ DPrim s_prims[RRS_BRUTE_MAX];
     stage_brute_prims(sc, s_prims);
     __syncthreads();
+    SStack stack;
+    stack.init(s_stack + threadIdx.x, blockDim.x);
     TravCounters cnt{0, 0};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 o4 = ray_o[i], d4 = ray_d[i];
@@ -895,7 +897,7 @@ __global__ void __launch_bounds__(kBlock) k_intersect32(DScene sc, const float4*
         if (sc.brute_count)
             closest_hit_brute<false, false>(sc, s_prims, xyz(o4), xyz(d4), RRS_NO_PRIM, nullptr, t, prim, cnt);
         else
-            closest_hit<false, false>(sc, xyz(o4), xyz(d4), RRS_NO_PRIM, nullptr, s_stack + threadIdx.x, blockDim.x, t, prim, cnt);
+            closest_hit<false, false>(sc, xyz(o4), xyz(d4), RRS_NO_PRIM, nullptr, stack, t, prim, cnt);
         if (prim == RRS_NO_PRIM) {
             obj_id[i] = -1;
             t_out[i] = INFINITY;

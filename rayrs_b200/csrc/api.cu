@@ -310,9 +310,7 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
     }
     // rays of a deep tree differ widely in length: refill early; a tiny scene amortises the fetch over more lanes
     s.d.refill_lanes = desc->max_depth > 6 ? 4u : 12u;
-    s.d.node_steps = 4u;  // measured best: 3-4 (gpurun_out/sweep_tune*.log)
     if (const char* e = std::getenv("RRS_REFILL_LANES")) s.d.refill_lanes = std::min(32, std::max(1, std::atoi(e)));
-    if (const char* e = std::getenv("RRS_NODE_STEPS")) s.d.node_steps = std::min(15, std::max(1, std::atoi(e)));
     *out = sc;
     return RRS_OK;
 }

@@ -136,7 +136,6 @@ struct DScene {
     uint32_t brute_prim[8];  // their indices: spheres, then planes, then triangles, DFS order inside a group
     uint32_t brute_spheres, brute_planes;  // group sizes (triangles: the rest)
     uint32_t refill_lanes;   // extend refills a warp with new rays once this many lanes are idle
-    uint32_t node_steps;     // inner-node steps a lane may take per ballot round of the batched traversal
 };
 
 struct DCamera {

@@ -239,6 +239,7 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
         flush_trav_counters<COUNT>(c, cnt);
         return;
     }
+    constexpr uint32_t kNodeSteps = 4;  // inner-node steps a lane takes per ballot round (swept 1..8: 3-4 best, gpurun_out/sweep_tune*.log)
     SStack stack;
     stack.init(s_stack + threadIdx.x, blockDim.x);
     TravCounters cnt{0, 0};
@@ -280,7 +281,8 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
             if (want == 0u || __popc(want) < __popc(parked)) break;
             if (inner) {
                 trav_node_step<COUNT>(sc, r, tv, stack, cnt);
-                for (uint32_t k = 1; k < sc.node_steps && trav_on_inner(tv); ++k) trav_node_step<COUNT>(sc, r, tv, stack, cnt);
+#pragma unroll 1
+                for (uint32_t k = 1; k < kNodeSteps && trav_on_inner(tv); ++k) trav_node_step<COUNT>(sc, r, tv, stack, cnt);
             }
         }
         // ---- leaves ----

@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--queue", type=int, default=0, help="rays in flight (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--ref-seconds", type=float, default=120.0, help="--impl reference: CPU time budget of the whole run")
     return ap.parse_args()
 
 
@@ -155,7 +156,7 @@ def run_reference(args):
     threads = oracle.hardware_threads()
     # size the per-step sample from a 1-spp probe so that the whole run ends within a few minutes
     r1, s1 = cpu_render_sample(cfg, specs, hdri, 1, threads)
-    budget = 120.0 / max(1, args.steps + args.warmup)
+    budget = args.ref_seconds / max(1, args.steps + args.warmup)
     spp = int(max(1, min(cfg.spp, budget / max(s1, 1e-3))))
     for _ in range(args.warmup):
         cpu_render_sample(cfg, specs, hdri, spp, threads)

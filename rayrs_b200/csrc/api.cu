@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstring>
 #include <string>
+#include <limits>
 #include <vector>
 
 #include <cuda_fp16.h>
@@ -299,6 +300,30 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
                 s.d.brute_prim[k] = reach[k];
                 if (desc->prims[reach[k]].type == RRS_SPHERE) s.d.brute_spheres++;
                 else if (desc->prims[reach[k]].type == RRS_PLANE) s.d.brute_planes++;
+            }
+            // one box around the sphere group: a ray that misses it skips every sphere test (a one-level hierarchy;
+            // most camera rays of the sphere-row scenes go to the floor or the sky).  Padded outward, so the fp32
+            // slab test in closest_hit_brute stays conservative.
+            s.d.brute_box_on = 0;
+            if (s.d.brute_spheres >= 3) {
+                double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+                for (uint32_t k = 0; k < s.d.brute_spheres; ++k) {
+                    const RrsPrim& p = desc->prims[reach[k]];
+                    const double r = std::sqrt(p.v[0]);
+                    for (int a = 0; a < 3; ++a) {
+                        lo[a] = std::min(lo[a], p.v[1 + a] - r);
+                        hi[a] = std::max(hi[a], p.v[1 + a] + r);
+                    }
+                }
+                bool finite = true;
+                for (int a = 0; a < 3; ++a) {
+                    const double pad = 1e-5 * (hi[a] - lo[a]) + 1e-6 * std::max(std::fabs(lo[a]), std::fabs(hi[a])) + 1e-30;
+                    s.d.brute_box[a] = std::nextafter((float)(lo[a] - pad), -std::numeric_limits<float>::infinity());
+                    s.d.brute_box[3 + a] = std::nextafter((float)(hi[a] + pad), std::numeric_limits<float>::infinity());
+                    finite = finite && std::isfinite(s.d.brute_box[a]) && std::isfinite(s.d.brute_box[3 + a]);
+                }
+                const char* nb = std::getenv("RRS_NO_BRUTE_BOX");
+                s.d.brute_box_on = (finite && !(nb && std::atoi(nb))) ? 1u : 0u;
             }
         }
     }

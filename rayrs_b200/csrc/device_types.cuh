@@ -136,6 +136,8 @@ struct DScene {
     uint32_t brute_prim[8];  // their indices: spheres, then planes, then triangles, DFS order inside a group
     uint32_t brute_spheres, brute_planes;  // group sizes (triangles: the rest)
     uint32_t refill_lanes;   // extend refills a warp with new rays once this many lanes are idle
+    uint32_t brute_box_on;   // the sphere group of the brute-force list has a bounding box worth testing first
+    float brute_box[6];      // lo xyz, hi xyz of that group, padded outward
 };
 
 struct DCamera {

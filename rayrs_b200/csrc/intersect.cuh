@@ -386,6 +386,24 @@ __device__ __forceinline__ void update_hit(const DScene& sc, bool hit, float t, 
     }
 }
 
+// Conservative slab test of a ray against a box padded outward on the host (the sphere group of the brute-force list).
+// min/max drop NaNs (a ray lying in a face plane of the padded box cannot reach what is strictly inside it); the
+// reciprocal is the 1-ulp approximation and the products carry ~1e-7 relative error each, covered by the 1e-6 slack.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ bool ray_meets_box(const float* __restrict__ box, float3 o, float3 d) {
+    const float ix = rcp_approx(d.x), iy = rcp_approx(d.y), iz = rcp_approx(d.z);
+    const float x0 = (box[0] - o.x) * ix, x1 = (box[3] - o.x) * ix;
+    const float y0 = (box[1] - o.y) * iy, y1 = (box[4] - o.y) * iy;
+    const float z0 = (box[2] - o.z) * iz, z1 = (box[5] - o.z) * iz;
+    const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+    return tf >= 0.f && tn <= tf * 1.000001f;
+}
+
 // The list is grouped by type on the host (spheres, planes, triangles; DFS order inside a group), so each group is a
 // tight loop without a per-primitive type dispatch; the tie-break still goes by the DFS index each record carries.
 template <bool COUNT, bool SPH64>
@@ -402,13 +420,16 @@ __device__ __forceinline__ void closest_hit_brute(const DScene& sc, const DPrim*
         // on the frosted-glass series (gpurun_out/sweep_grouped.log)
         RayProj proj;
         if (sc.has_triangles) proj = make_proj(d);
-        for (uint32_t j = 0; j < sc.brute_count; ++j) {
+        // the list starts with the sphere group: skip it when the ray misses the group's box
+        const uint32_t j0 = (sc.brute_box_on && !ray_meets_box(sc.brute_box, o, d)) ? sc.brute_spheres : 0u;
+        for (uint32_t j = j0; j < sc.brute_count; ++j) {
             const DPrim& p = s_prims[j];
             test_prim<SPH64>(sc, sc.brute_prim[j], p.a, p.b, p.c, o, d, proj, origin_prim, o64, tbest, best);
         }
         return;
     }
     uint32_t k = 0;
+    if (sc.brute_box_on && !ray_meets_box(sc.brute_box, o, d)) k = sc.brute_spheres;  // no sphere can be hit
     for (; k < sc.brute_spheres; ++k) {
         const uint32_t pi = sc.brute_prim[k];
         const float4 a = s_prims[k].a, b = s_prims[k].b;

@@ -173,3 +173,46 @@ def test_edge_cases(hdri_small):
     with pytest.raises(Exception):
         sc.intersect(rays, 16)
     sc.close()
+
+
+def test_sphere_group_box_never_changes_an_answer(hdri_small, monkeypatch):
+    """The brute-force path tests one padded box around its sphere group first (scene creation, api.cu).  It must
+    be purely an accelerator: with and without it every ID and every t is bit-identical — including rays that
+    graze the box, lie in its face planes, start inside it or on a sphere, and axis-parallel rays."""
+    spec = scenes.cook_torrance_spheres_metallic(320, 128)
+    osc = oracle.OracleScene(spec.tables(), hdri_small.pixels)
+    rays = fixed_ray_set(spec, osc, 1 << 18, seed=21)
+    rng = np.random.default_rng(5)
+    # the group's exact box is x in [-7.6, 7.6], y in [0, 2], z in [-1, 1]: rays in its face planes and along its edges
+    special = []
+    for y in (0.0, 2.0, 1.0):
+        for z in (-1.0, 1.0, 0.0):
+            special.append([-20.0, y, z, 1.0, 0.0, 0.0])
+            special.append([20.0, y, z, -1.0, 0.0, 0.0])
+    for x in (-7.6, 7.6, -6.6, 0.0):
+        special.append([x, 9.0, 0.0, 0.0, -1.0, 0.0])
+        special.append([x, 1.0, 9.0, 0.0, 0.0, -1.0])
+        special.append([x, 1.0, 0.0, 0.0, 1.0, 0.0])  # from a sphere centre
+    graze = np.concatenate([rng.uniform(-9, 9, (4096, 1)), rng.uniform(1.99, 2.01, (4096, 1)), rng.uniform(-3, 3, (4096, 1)),
+                            rng.normal(size=(4096, 2)) * [1.0, 1e-3], rng.normal(size=(4096, 1))], axis=1)
+    rays = np.concatenate([rays, np.array(special), graze]).astype(np.float32).astype(np.float64)
+    sc_on = spec.scene(hdri_small)
+    monkeypatch.setenv("RRS_NO_BRUTE_BOX", "1")
+    sc_off = spec.scene(hdri_small)
+    monkeypatch.delenv("RRS_NO_BRUTE_BOX")
+    id_on, t_on = sc_on.intersect(rays, 32)
+    id_off, t_off = sc_off.intersect(rays, 32)
+    assert np.array_equal(id_on, id_off)
+    assert np.array_equal(t_on, t_off)
+    assert (id_on >= 1).mean() > 0.05  # spheres are actually hit in this set
+    # and the rendered paths are the same paths
+    cam = spec.camera()
+    from rayrs_b200 import api
+    a = api.render_gpu(cam, sc_on, 8, 50)
+    st_on = sc_on.stats()
+    b = api.render_gpu(cam, sc_off, 8, 50)
+    st_off = sc_off.stats()
+    assert st_on["rays"] == st_off["rays"]
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-6)  # same samples, atomic summation order differs
+    sc_on.close()
+    sc_off.close()

@@ -75,16 +75,65 @@ def bytes_per_ray_model(workload: str):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.  In-process NVML (what nvidia-smi reads) on a
+    thread, one sample every 2 ms, so that a timed region of ~100 ms still holds dozens of samples; an `nvidia-smi
+    -lms` child process is the fallback when the NVML binding is missing (its start-up alone can outlast a short
+    region, which is why it is not the first choice)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, uuid: str | None = None):
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.nvml = None
+        self.handle = None
+        self.thread = None
+        self.running = False
+        self.samples = []
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                idx = gpu_index
+                if visible:
+                    ids = [v.strip() for v in visible.split(",") if v.strip()]
+                    if gpu_index < len(ids) and ids[gpu_index].isdigit():
+                        idx = int(ids[gpu_index])
+                h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.handle = pynvml, h
+        except Exception:
+            self.nvml = None
+
+    def _loop(self):
+        nv, h = self.nvml, self.handle
+        while self.running:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    why = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    why = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.samples.append((mhz, why))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            import threading
+            self.running = True
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         try:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
@@ -94,7 +143,23 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": None}
+        if self.nvml is not None:
+            self.running = False
+            if self.thread is not None:
+                self.thread.join(timeout=2)
+            nv = self.nvml
+            bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            if self.samples:
+                seen = 0
+                for _, why in self.samples:
+                    seen |= why
+                out.update(sm_mhz=float(np.median([m for m, _ in self.samples])), sm_max_mhz=self.max_mhz,
+                           reasons=sorted(k for k, b in bits.items() if seen & b), samples=len(self.samples), source="nvml")
+            return out
         if self.proc is None:
             return out
         time.sleep(0.15)
@@ -121,7 +186,8 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
+                       source="nvidia-smi")
         return out
 
 
@@ -264,11 +330,17 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident timing -----------------------------------------------------------
+    sampler = None
+    if rank == 0:
+        try:
+            uuid = str(torch.cuda.get_device_properties(dev).uuid)
+        except Exception:
+            uuid = None
+        sampler = ClockSampler(local, uuid)  # NVML is initialised here, outside the timed region
     for _ in range(max(3, args.warmup)):
         step_device()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    if sampler is not None:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -291,7 +363,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler is not None else None
     ms_total = float(ms.item())
     rays_all, launches_all = float(tot[0].item()), int(tot[1].item())
 

@@ -127,7 +127,7 @@ def update_model(metrics_csv: Path, key: str, captured_rays: float = 0.0):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("tag")
-    ap.add_argument("--launches", default=str(ROOT / "gpurun_out" / "launches.csv"))
+    ap.add_argument("--launches", default="", help="ncu launch-list csv of the same command (omit for captures without one)")
     ap.add_argument("--rep", default=str(ROOT / "gpurun_out" / "prof.ncu-rep"))
     ap.add_argument("--model-key", default="", help="c1..c5: also record the capture in profiles/bytes_per_ray.json")
     ap.add_argument("--captured-rays", type=float, default=0.0,
@@ -135,7 +135,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     prof = ROOT / "profiles"
     prof.mkdir(exist_ok=True)
-    if Path(a.launches).exists():
+    if a.launches and Path(a.launches).exists():
         launches(Path(a.launches), prof / f"{a.tag}_launches.csv")
     if Path(a.rep).exists():
         metrics(Path(a.rep), prof / f"{a.tag}_metrics.csv", prof / f"{a.tag}_stalls.txt")

@@ -10,6 +10,7 @@
 #include <future>
 #include <limits>
 #include <mutex>
+#include <cstdio>
 #include <thread>
 
 namespace rayrs {
@@ -245,6 +246,54 @@ struct Builder {
     }
     static double key(const Vec3& c, int axis) { return axis == 0 ? c.x : (axis == 1 ? c.y : c.z); }
 
+    struct KeyIdx {
+        double k;
+        uint32_t i;
+    };
+    int borrow_threads(int want) {
+        int got = 0;
+        while (got < want) {
+            int v = spare_threads.load();
+            if (v <= 0) break;
+            if (spare_threads.compare_exchange_weak(v, v - 1)) ++got;
+        }
+        return got;
+    }
+    // stable sort by key; ranges above 64K entries use up to 8 chunks on borrowed threads + stable pairwise merges
+    void stable_sort_pairs(std::vector<KeyIdx>& v) {
+        auto less = [](const KeyIdx& a, const KeyIdx& b) { return a.k < b.k; };
+        const size_t n = v.size();
+        int extra = n > 65536 ? borrow_threads(7) : 0;
+        int chunks = extra >= 7 ? 8 : (extra >= 3 ? 4 : (extra >= 1 ? 2 : 1));
+        if (chunks == 1) {
+            spare_threads.fetch_add(extra);
+            std::stable_sort(v.begin(), v.end(), less);
+            return;
+        }
+        spare_threads.fetch_add(extra - (chunks - 1));  // keep only what the chunking uses
+        std::vector<size_t> cut(chunks + 1);
+        for (int c = 0; c <= chunks; ++c) cut[c] = n * (size_t)c / (size_t)chunks;
+        {
+            std::vector<std::future<void>> jobs;
+            for (int c = 1; c < chunks; ++c)
+                jobs.push_back(std::async(std::launch::async, [&, c]() { std::stable_sort(v.begin() + cut[c], v.begin() + cut[c + 1], less); }));
+            std::stable_sort(v.begin() + cut[0], v.begin() + cut[1], less);
+            for (auto& j : jobs) j.get();
+        }
+        for (int width = 1; width < chunks; width *= 2) {
+            std::vector<std::future<void>> jobs;
+            for (int c = 0; c + width < chunks; c += 2 * width) {
+                const size_t a = cut[c], m = cut[c + width], b = cut[std::min(chunks, c + 2 * width)];
+                auto merge = [&v, a, m, b, less]() { std::inplace_merge(v.begin() + a, v.begin() + m, v.begin() + b, less); };
+                if (c == 0) continue;
+                jobs.push_back(std::async(std::launch::async, merge));
+            }
+            std::inplace_merge(v.begin() + cut[0], v.begin() + cut[width], v.begin() + cut[std::min(chunks, 2 * width)], less);
+            for (auto& j : jobs) j.get();
+        }
+        spare_threads.fetch_add(chunks - 1);
+    }
+
     AxisAlignedBoundingBox range_box(size_t lo, size_t hi) const {
         AxisAlignedBoundingBox b = boxes[order[lo]];
         for (size_t i = lo + 1; i < hi; ++i) b = b.expand(boxes[order[i]]);
@@ -269,14 +318,23 @@ struct Builder {
         if (x >= y && x >= z) { axis = 0; amin = bb.xmin; alen = x; }
         else if (y >= z) { axis = 1; amin = bb.ymin; alen = y; }
         else { axis = 2; amin = bb.zmin; alen = z; }
-        // BvhData::sort — Rust's sort_by is stable
-        std::stable_sort(order.begin() + lo, order.begin() + hi, [&](uint32_t a, uint32_t b) {
-            return key(centers[a], axis) < key(centers[b], axis);
-        });
+        // BvhData::sort — Rust's sort_by is stable.  Sorted as (key, index) pairs: the comparator reads the key
+        // next to the index instead of chasing it through `centers` (the same order as a stable sort of the
+        // indices with that comparator), and a large range is cut into chunks sorted on the spare threads and
+        // merged stably.
         std::vector<double> keys(n);
-        for (size_t k = 0; k < n; ++k) {
-            keys[k] = key(centers[order[lo + k]], axis);
-            if (std::isnan(keys[k])) throw Panic("partial_cmp().unwrap() on NaN centre");  // bvh.rs:104
+        {
+            std::vector<KeyIdx> tmp(n);
+            for (size_t k = 0; k < n; ++k) {
+                const uint32_t i = order[lo + k];
+                tmp[k] = KeyIdx{key(centers[i], axis), i};
+                if (std::isnan(tmp[k].k)) throw Panic("partial_cmp().unwrap() on NaN centre");  // bvh.rs:104
+            }
+            stable_sort_pairs(tmp);
+            for (size_t k = 0; k < n; ++k) {
+                order[lo + k] = tmp[k].i;
+                keys[k] = tmp[k].k;
+            }
         }
         long ind = -1;
         if (heur.kind == BvhHeuristic::kSah) {
@@ -290,19 +348,46 @@ struct Builder {
             const double surface_area = bb.surface_area();
             const double split_dist = alen / (double)(heur.splits - 1);
             double min_sah = std::numeric_limits<double>::infinity();
-            long last = -2;
-            for (uint32_t i = 1; i < heur.splits + 1; ++i) {
-                double thr = amin + (double)i * split_dist;
-                size_t k = std::upper_bound(keys.begin(), keys.end(), thr) - keys.begin();  // first centre > thr
-                if (k >= n) continue;           // split_index -> None
-                if ((long)k == last) continue;  // same split => same cost; strict < keeps the first
-                last = (long)k;
+            auto thr_of = [&](long i) { return amin + (double)i * split_dist; };  // bvh.rs:262, same expression
+            auto consider = [&](size_t k) {  // calculate_sah bvh.rs:15-38 for left = [0,k), right = [k,n)
                 double p_left = k > 0 ? pre[k - 1].surface_area() / surface_area : 0.;
                 double p_right = suf[k].surface_area() / surface_area;
                 double sah = 0.3 + 1. * (p_left * (double)k + p_right * (double)(n - k));
                 if (sah < min_sah) {
                     min_sah = sah;
                     ind = (long)k;
+                }
+            };
+            if (n < (size_t)heur.splits && split_dist > 0. && std::isfinite(split_dist)) {
+                // Few primitives, many thresholds: most of the `splits` thresholds fall between the same two
+                // centres and repeat a split already costed.  Walk the DISTINCT split indices instead, in the order
+                // the threshold loop meets them (k(i) = #centres <= thr_i never decreases with i, and the strict <
+                // keeps the first of equal costs, so the outcome is the loop's).  For the next centre the smallest i
+                // with thr_i >= centre is guessed by a division and then settled with the loop's own expression.
+                const long splits = (long)heur.splits;
+                long i = 1;
+                size_t k = std::upper_bound(keys.begin(), keys.end(), thr_of(1)) - keys.begin();
+                while (k < n) {
+                    consider(k);
+                    const double c = keys[k];  // the next centre a threshold has to reach
+                    long g = (long)std::ceil((c - amin) / split_dist);
+                    g = std::max(g, i + 1);
+                    g = std::min(g, splits + 1);
+                    while (g > i + 1 && thr_of(g - 1) >= c) --g;
+                    while (g <= splits && thr_of(g) < c) ++g;
+                    if (g > splits) break;
+                    i = g;
+                    k = std::upper_bound(keys.begin() + k, keys.end(), thr_of(i)) - keys.begin();
+                }
+            } else {
+                long last = -2;
+                for (uint32_t i = 1; i < heur.splits + 1; ++i) {
+                    double thr = thr_of((long)i);
+                    size_t k = std::upper_bound(keys.begin(), keys.end(), thr) - keys.begin();  // first centre > thr
+                    if (k >= n) continue;           // split_index -> None
+                    if ((long)k == last) continue;  // same split => same cost; strict < keeps the first
+                    last = (long)k;
+                    consider(k);
                 }
             }
         } else {
@@ -439,21 +524,33 @@ FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, u
     if (objects.empty()) throw Panic("Having a BVH for 0 objects does not make sense");
     if (heuristic.kind == BvhHeuristic::kSah && heuristic.splits < 2) throw Panic("Sah needs at least 2 splits");
     const size_t n = objects.size();
+    // RRS_BVH_TIMING=1: where the build time goes, on stderr
+    const bool timing = std::getenv("RRS_BVH_TIMING") != nullptr;
+    auto tick = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        auto now = std::chrono::steady_clock::now();
+        if (timing) std::fprintf(stderr, "[bvh] %-22s %.3f s\n", what, std::chrono::duration<double>(now - tick).count());
+        tick = now;
+    };
     std::vector<AxisAlignedBoundingBox> boxes(n);
     std::vector<Vec3> centers(n);
     for (size_t i = 0; i < n; ++i) {
         boxes[i] = objects[i].bbox();
         centers[i] = boxes[i].center();  // BvhData::new bvh.rs:87-98
     }
+    lap("boxes + centres");
     FlatBvh out;
     out.prim_order.resize(n);
     for (size_t i = 0; i < n; ++i) out.prim_order[i] = (uint32_t)i;
     Builder b(boxes, centers, out.prim_order, heuristic);
+    if (threads <= 0)
+        if (const char* e = std::getenv("RRS_BVH_THREADS")) threads = std::atoi(e);
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
     b.spare_threads = threads - 1;
     b.nodes.reserve(n);
     const int32_t root = b.build(0, n, 0);
     const std::vector<BNode>& bn = b.nodes;
+    lap("recursive build");
 
     // ---- flat numbering: virtual root = 0, then binary Nodes breadth-first for the first
     // `bfs_nodes` (hot top of the tree contiguous), depth-first below (subtrees contiguous)
@@ -487,6 +584,7 @@ FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, u
             }
         }
     }
+    lap("flat numbering");
     out.nodes.assign(flat_to_build.size(), RrsNode{});
     out.nodes_f64.assign(flat_to_build.size(), RrsNodeF64{});
     Flattener fl{bn, out};
@@ -508,6 +606,7 @@ FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, u
         fl.attach((uint32_t)f, 0, nd.child[0], nd.box, flat_index);
         fl.attach((uint32_t)f, 1, nd.child[1], nd.box, flat_index);
     }
+    lap("flatten");
     // depth (stack bound): longest chain of flat nodes
     {
         std::vector<uint32_t> depth(out.nodes.size(), 0);
@@ -528,7 +627,9 @@ FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, u
         }
         out.max_depth = mx;
     }
+    lap("depth");
     dump_topology(bn, root, out.prim_order, out);
+    lap("topology dump");
     return out;
 }
 

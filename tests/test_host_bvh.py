@@ -60,6 +60,39 @@ def test_host_tree_equals_reference_tree(case, heuristic):
     assert np.array_equal(boxes_h, boxes_o)  # bit-identical f64 boxes
 
 
+def _lattice_spheres(seed, n=700):
+    """centres on a coarse lattice: equal keys, thresholds that land exactly on centres, long runs between two
+    thresholds — what the distinct-split walk of the host builder (few primitives, many thresholds) has to get right"""
+    rng = np.random.default_rng(seed)
+    m = Material.no_reflect()
+    pts = rng.integers(0, 9, (n, 3)).astype(np.float64) * np.array([0.5, 0.125, 2.0])
+    return [Object.sphere(float(rng.choice([0.05, 0.1, 0.25])), p, m) for p in pts]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("splits", [2, 3, 10, 257, 1000, 5000])
+def test_distinct_split_walk_equals_threshold_loop(seed, splits):
+    objects = _lattice_spheres(seed) + _random_spheres(60, 100 + seed)
+    host, orc = _both(objects, BvhHeuristic.Sah(splits))
+    _, _, _, topo_h, boxes_h, _ = host.flat()
+    topo_o, boxes_o = orc.tree_dump()  # build_mode=0: the literal loop over every threshold
+    assert np.array_equal(topo_h, topo_o)
+    assert np.array_equal(boxes_h, boxes_o)
+
+
+def test_parallel_sort_path_builds_the_same_tree():
+    """90k triangles: the root ranges are above the builder's 64K threshold for chunked sorting on spare threads +
+    stable merges.  Against the oracle's fast build (itself pinned to the literal one below)."""
+    spec = scenes.copper_torus(300, 150, 32, 32)
+    host = Scene(spec.objects, 1e-6, 1e6, spec.heuristic, HDRI, upload=False)
+    assert host.n_prims == 90001
+    orc = oracle.OracleScene(spec.tables(), HDRI.pixels, heuristic=(spec.heuristic.kind, spec.heuristic.splits), build_mode=1)
+    _, _, _, topo_h, boxes_h, _ = host.flat()
+    topo_o, boxes_o = orc.tree_dump()
+    assert np.array_equal(topo_h, topo_o)
+    assert np.array_equal(boxes_h, boxes_o)
+
+
 def test_oracle_fast_build_equals_literal():
     objects = _random_triangles(5000, 5)
     tables = build_tables(objects)

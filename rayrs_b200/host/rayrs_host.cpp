@@ -300,11 +300,26 @@ struct Builder {
         return b;
     }
 
-    int32_t build(size_t lo, size_t hi, int depth) {
+    // Scratch of one node, reused down the recursion of a thread (everything in it is dead before the children are
+    // built); forked subtrees run on their own threads and get their own.
+    struct Scratch {
+        std::vector<KeyIdx> tmp;
+        std::vector<double> keys;
+        std::vector<AxisAlignedBoundingBox> nb, pre, suf;
+        void release() { *this = Scratch(); }
+    };
+    static Scratch& scratch() {
+        thread_local Scratch s;
+        return s;
+    }
+
+    // known_box: the node's box when the parent already folded it (same elements, same order as range_box -> the
+    // same bits), nullptr at the root
+    int32_t build(size_t lo, size_t hi, int depth, const AxisAlignedBoundingBox* known_box = nullptr) {
         const size_t n = hi - lo;
         if (n == 0) throw Panic("Having a BVH for 0 objects does not make sense");  // bvh.rs:229
         BNode node;
-        node.box = range_box(lo, hi);
+        node.box = known_box ? *known_box : range_box(lo, hi);
         if (n <= 4) {  // bvh.rs:304-315
             node.kind = 1;
             node.first = (uint32_t)lo;
@@ -322,29 +337,37 @@ struct Builder {
         // next to the index instead of chasing it through `centers` (the same order as a stable sort of the
         // indices with that comparator), and a large range is cut into chunks sorted on the spare threads and
         // merged stably.
-        std::vector<double> keys(n);
+        Scratch& sx = scratch();
+        std::vector<double>& keys = sx.keys;
+        std::vector<AxisAlignedBoundingBox>& nb = sx.nb;  // the node's boxes in sorted order: ONE gather through `order`
         {
-            std::vector<KeyIdx> tmp(n);
+            std::vector<KeyIdx>& tmp = sx.tmp;
+            tmp.resize(n);
             for (size_t k = 0; k < n; ++k) {
                 const uint32_t i = order[lo + k];
                 tmp[k] = KeyIdx{key(centers[i], axis), i};
                 if (std::isnan(tmp[k].k)) throw Panic("partial_cmp().unwrap() on NaN centre");  // bvh.rs:104
             }
             stable_sort_pairs(tmp);
+            keys.resize(n);
+            nb.resize(n);
             for (size_t k = 0; k < n; ++k) {
                 order[lo + k] = tmp[k].i;
                 keys[k] = tmp[k].k;
+                nb[k] = boxes[tmp[k].i];
             }
         }
         long ind = -1;
         if (heur.kind == BvhHeuristic::kSah) {
             // bvh.rs:258-271 with calculate_sah bvh.rs:15-38.  left(k) = [0,k), right(k) = [k,n)
-            std::vector<AxisAlignedBoundingBox> suf(n);
-            suf[n - 1] = boxes[order[hi - 1]];
-            for (size_t k = n - 1; k-- > 0;) suf[k] = boxes[order[lo + k]].expand(suf[k + 1]);
-            std::vector<AxisAlignedBoundingBox> pre(n);  // pre[k] = box of [0,k], so left(k) = pre[k-1]
-            pre[0] = boxes[order[lo]];
-            for (size_t k = 1; k < n; ++k) pre[k] = pre[k - 1].expand(boxes[order[lo + k]]);
+            std::vector<AxisAlignedBoundingBox>& suf = sx.suf;
+            suf.resize(n);
+            suf[n - 1] = nb[n - 1];
+            for (size_t k = n - 1; k-- > 0;) suf[k] = nb[k].expand(suf[k + 1]);
+            std::vector<AxisAlignedBoundingBox>& pre = sx.pre;  // pre[k] = box of [0,k], so left(k) = pre[k-1]
+            pre.resize(n);
+            pre[0] = nb[0];
+            for (size_t k = 1; k < n; ++k) pre[k] = pre[k - 1].expand(nb[k]);
             const double surface_area = bb.surface_area();
             const double split_dist = alen / (double)(heur.splits - 1);
             double min_sah = std::numeric_limits<double>::infinity();
@@ -397,12 +420,16 @@ struct Builder {
             ind = k >= n ? -1 : (long)k;
         }
         if (ind < 0 || ind == 0 || ind == (long)n - 1) ind = (long)(n / 2);  // bvh.rs:279-287
-        keys.clear();
-        keys.shrink_to_fit();
+        // the children's boxes, folded left to right over their elements in this node's sorted order — what their own
+        // range_box would gather again
+        AxisAlignedBoundingBox box_l = nb[0], box_r = nb[(size_t)ind];
+        for (size_t k = 1; k < (size_t)ind; ++k) box_l = box_l.expand(nb[k]);
+        for (size_t k = (size_t)ind + 1; k < n; ++k) box_r = box_r.expand(nb[k]);
+        if (n > (1u << 16)) sx.release();  // do not hold the top levels' buffers while the subtrees are built
         node.kind = 0;
         const size_t mid = lo + (size_t)ind;
         auto side = [&](size_t a, size_t b) -> int32_t {
-            if (b - a > 1) return build(a, b, depth + 1);
+            if (b - a > 1) return build(a, b, depth + 1, a == lo ? &box_l : &box_r);
             BNode leaf;
             leaf.kind = 2;
             leaf.first = (uint32_t)a;

@@ -4,21 +4,26 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1..c5] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the hot path over the workload: every scene of the named BASELINE
-configuration rendered once at its full resolution / spp / depth (default c2 = BASELINE.json
-configs[1]: Cook-Torrance metallic + plastic sphere series, 1024x1024, 256 spp).
+A "step" is one pass of the hot path over the workload: every scene of the named BASELINE configuration rendered
+once at its full resolution / spp / depth.  Default workload: c5 = BASELINE.json configs[4] (3840x2160, 4.0M-triangle
+mesh + 7 spheres + floor, 4096 spp) — the configuration `metric` is quoted on ("at 1/2/4/8 B200"), the BVH-traversal
+path, and it fits one GPU.
 
-  value   Mrays/s with the scene resident in HBM: rrs_render_accumulate into a device buffer
-          (+ the NCCL reduce at N > 1 + resolve), CUDA events on the launching stream, max over ranks.
-  e2e     the same metric through the public render call with HOST buffers (rrs_render: camera and
-          parameters host->device, image device->host every step), wall clock.
-  N > 1   weak scaling: every GPU renders the configuration's spp over its own disjoint global
-          sample range (spp_total = N * spp), one reduce(sum) merges the radiance buffers.
+  value   Mrays/s with the scene resident in HBM: ONE library call per scene (rrs_render_multi: sample split,
+          persistent render kernel, ncclReduce at N > 1, resolve on rank 0) into a DEVICE image, CUDA events on the
+          launching stream, max over ranks.
+  e2e     the same call with a HOST image buffer on rank 0 (camera + parameters host->device, image device->host
+          inside the timed region), wall clock, max over ranks.
+  N > 1   STRONG scaling: the configuration's spp is split over the GPUs (rank g renders rrs_sample_range(g, N, spp)
+          of every pixel), one reduce(sum) of the fp32 radiance buffers merges them.
+  extra   per_config: mini-records of the other BASELINE configurations (N = 1 only); parity_check: path census,
+          NaN / negative pixels, and the N-GPU merged image against a single-GPU render of the same samples.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -44,8 +49,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
-    ap.add_argument("--spp", type=int, default=0, help="override spp (invalidates the headline; for experiments)")
+    ap.add_argument("--workload", default="c5", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--spp", type=int, default=0, help="override the TOTAL spp (invalidates the headline; for experiments)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (0 = max(3, steps // 4))")
+    ap.add_argument("--no-per-config", action="store_true", help="skip the mini-records of the other configurations")
+    ap.add_argument("--flags", type=int, default=0, help="RRS_FLAG_* for the timed renders (experiments)")
     ap.add_argument("--queue", type=int, default=0, help="rays in flight (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
@@ -72,6 +80,67 @@ def bytes_per_ray_model(workload: str):
         if workload in d:
             return d[workload]
     return None
+
+
+COUNTERS_FILE = "profiles/r02_counters.json"
+
+
+def kernel_counters(workload: str):
+    """Per-ray constants of the render kernel measured by ncu on THIS command (`ncu ... python bench.py --workload X
+    --spp S`, scripts/ncu_counters.py -> profiles/r02_counters.json): warp instructions, thread instructions and
+    DRAM bytes per ray.  They are properties of the code and the workload (spp-invariant), so a launch's counts are
+    these times its rays; the launch TIME is measured live."""
+    p = ROOT / COUNTERS_FILE
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+def roofline_block(workload, kname, rays, kernel_ms, n_launch, step_ms_total, clocks, sms, peak_hbm, peak_src):
+    """The roofline of the render kernel.  Primary bound = the one that binds: thread-instruction issue
+    (148 SMs x 128 lanes x SM clock).  The HBM figures ride along: the SURVEY 8(d) algorithmic-bytes model
+    (`hbm_model`, an upper bound on traffic that an L2-resident scene never moves) and the measured DRAM bytes."""
+    kms = max(kernel_ms, 1e-9)
+    roof = {"bound": "issue", "kernel": kname, "achieved": None, "peak": None, "unit": "Tthread-inst/s", "frac": None,
+            "traffic": None, "avg_launch_ms": kms / max(1, n_launch), "launches": n_launch,
+            "share_of_step": kms / max(step_ms_total, 1e-9)}
+    c = kernel_counters(workload)
+    mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+    roof["peak"] = sms * 128 * mhz * 1e6 / 1e12
+    roof["peak_source"] = f"{sms} SMs x 128 lanes x {mhz:.0f} MHz (SM clock sampled during the timed region)"
+    if c:
+        ti = c["thread_inst_per_ray"] * rays
+        wi = c["warp_inst_per_ray"] * rays
+        roof["achieved"] = ti / (kms * 1e-3) / 1e12
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["warp_issue_frac"] = wi / (kms * 1e-3) / (sms * 4 * mhz * 1e6)
+        roof["lanes_per_instruction"] = c["thread_inst_per_ray"] / c["warp_inst_per_ray"]
+        roof["warp_inst_per_ray"] = c["warp_inst_per_ray"]
+        roof["thread_inst_per_ray"] = c["thread_inst_per_ray"]
+        roof["traffic"] = c["dram_bytes_per_ray"] * rays / max(1, n_launch)
+        roof["dram"] = {"bytes_per_ray": c["dram_bytes_per_ray"], "achieved": c["dram_bytes_per_ray"] * rays / (kms * 1e-3) / 1e9,
+                        "peak": peak_hbm, "unit": "GB/s", "frac": c["dram_bytes_per_ray"] * rays / (kms * 1e-3) / 1e9 / peak_hbm,
+                        "peak_source": peak_src}
+        roof["counters_source"] = c.get("source", COUNTERS_FILE)
+        for k in ("l2_hit_pct", "issue_active_pct", "captured"):
+            if k in c:
+                roof[k] = c[k]
+    model = bytes_per_ray_model(workload)
+    if model:
+        kb = model["kernel_bytes_per_ray"]
+        b = kb["generate"] + kb["extend"] + kb["shade"]
+        roof["hbm_model"] = {"bytes_per_ray": b, "achieved": rays * b / (kms * 1e-3) / 1e9, "peak": peak_hbm, "unit": "GB/s",
+                             "frac": rays * b / (kms * 1e-3) / 1e9 / peak_hbm,
+                             "note": "SURVEY 8(d) algorithmic bytes (32 B per visited node + 64 B per tested primitive + 144 B of "
+                                     "queue state per ray) counted as if every byte came from HBM; the tree is L2-resident or "
+                                     "shared-memory-resident, so these bytes are not moved: a model figure, not a bound"}
+        roof["oracle_traversal"] = {"box_tests_per_ray": model["N_nodes"], "node_visits_per_ray": model["N_nodes"] / 2.0,
+                                    "prims_tested_per_ray": model["N_prims"],
+                                    "note": "ordered, t-pruned traversal of the exact-box reference tree, counted by the oracle"}
+    return roof
 
 
 class ClockSampler:
@@ -235,10 +304,14 @@ def run_reference(args):
     sample = f"{args.workload}: all {len(specs)} scene(s) at {cfg.width}x{cfg.height}, {spp} of {cfg.spp} spp per step (Mrays/s is spp-invariant)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": secs / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": secs / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": cfg.description, "cpu_threads": threads,
-                   "note": "restated reference (oracle port, g++ -O3 -ffp-contract=off), not the Rust binary: no Rust toolchain in the image"},
+        "config": {"workload": cfg.description, "scenes": [s.name for s in specs], "width": cfg.width, "height": cfg.height,
+                   "spp_total": cfg.spp, "max_bounces": cfg.max_bounces, "hdri": "synthetic 2048x1024",
+                   "spp_per_step": spp, "cpu_threads": threads,
+                   "note": "restated reference (oracle port, g++ -O3 -ffp-contract=off), not the Rust binary: no Rust toolchain in "
+                           "the image; each step renders a bounded sample of the workload (spp_per_step of spp_total samples per "
+                           "pixel at full resolution; Mrays/s is spp-invariant)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -249,11 +322,13 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+KERNEL_NAMES = {0: "k_wavefront", 1: "k_generate/k_extend/k_shade", 2: "k_pathloop"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from rayrs_b200 import _ffi, api, scenes
-    from rayrs_b200.multigpu import sample_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -265,62 +340,64 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    # ---- the library's communicator: rank 0 makes the NCCL id, torch.distributed only carries its 128 bytes ----
+    def exchange(raw):
+        box = [raw]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    if world > 1:
+        comm = api.Comm(world, rank, local, exchange)
+        comm_ptr = comm.ptr
+    else:
+        comm = None
+        comm_ptr = C.c_void_p()
+        devs = (C.c_int * 1)(local)
+        _ffi.check(_ffi.cuda_lib().rrs_comm_init_all(devs, 1, C.byref(comm_ptr)))
+
     cfg = scenes.CONFIGS[args.workload]
-    spp = args.spp or cfg.spp
+    spp_total = args.spp or cfg.spp          # strong scaling: the configuration's spp, split over the ranks
+    first, count = api.sample_range(rank, world, spp_total)
     specs = cfg.specs()
     hdri = scenes.synthetic_hdri(2048, 1024)
     t_setup = time.time()
     built = [(spec, spec.scene(hdri, device=local, with_f64=False), spec.camera()) for spec in specs]
     t_setup = time.time() - t_setup
+    build_s = sum(sc.build_seconds for _, sc, _ in built)
     W, H = cfg.width, cfg.height
-    first, count = sample_range(rank, world, spp * world)  # weak scaling: `spp` samples per GPU
-    assert count == spp
-    spp_total = spp * world
     stream = torch.cuda.current_stream(dev)
     sptr = stream.cuda_stream
-    acc = [torch.zeros((H, W, 4), dtype=torch.float32, device=dev) for _ in built]
-    out = [torch.empty((H, W, 3), dtype=torch.float32, device=dev) for _ in built]
+    out = [torch.empty((H, W, 3), dtype=torch.float32, device=dev) for _ in built] if rank == 0 else [None] * len(built)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+
+    def render(sc, cam, spp, out_ptr, out_is_device, flags=0, max_bounces=None):
+        """ONE library call: sample split over the ranks of the communicator, render, reduce, resolve on rank 0"""
+        api.render_multi(cam, [sc.handle], comm_ptr, spp, cfg.max_bounces if max_bounces is None else max_bounces,
+                         out_ptr=out_ptr, out_is_device=out_is_device, streams=[sptr], queue_capacity=args.queue, flags=flags)
 
     def step_device(flags=0):
-        """inputs resident in HBM; returns (rays, launches, phase dict)"""
+        """inputs resident in HBM, image stays on the device; returns (rays, launches, stats of the last scene)"""
         rays = launches = 0
-        ph = {"generate_ms": 0.0, "extend_ms": 0.0, "shade_ms": 0.0, "iterations": 0, "device_ms": 0.0, "kernel_form": 0}
+        kernel_ms = 0.0
+        st = None
         flush.fill_(1)  # L2 flush between timed iterations (inside the region: ~0.1 ms); a torch kernel, not counted
         for k, (spec, sc, cam) in enumerate(built):
-            acc[k].zero_()
-            api.render_accumulate(cam, sc, spp, cfg.max_bounces, acc[k].data_ptr(), sptr, sample_offset=first,
-                                  spp_total=spp_total, queue_capacity=args.queue, flags=flags)
-            st = sc.stats()
+            render(sc, cam, spp_total, out[k].data_ptr() if rank == 0 else 0, True, flags)
+            st = sc.stats()                      # waits for this rank's part
             rays += st["rays"]
-            launches += st["kernel_launches"]  # OUR kernels only (the render kernel); torch's zero_ / fill_ are not counted
-            for key in ph:
-                ph[key] = st[key] if key == "kernel_form" else ph[key] + st[key]
-            if world > 1:
-                dist.reduce(acc[k], dst=0, op=dist.ReduceOp.SUM)
-            if rank == 0:
-                api.resolve(sc, acc[k].data_ptr(), W, H, spp_total, out[k].data_ptr(), True, sptr)
-                launches += 1
-        return rays, launches, ph
+            launches += st["kernel_launches"]    # OUR render + resolve kernels and NCCL's reduce; torch's fill_ is not counted
+            kernel_ms += st["device_ms"]
+        return rays, launches, kernel_ms, st
 
     # the caller's image buffers, page-locked (the library DMAs straight into a pinned destination)
-    host_pin = [torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True) for _ in built]
-    host_out = [t.numpy() for t in host_pin]
+    host_pin = [torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True) for _ in built] if rank == 0 else []
 
     def step_e2e():
-        """public API with HOST buffers.  N == 1: rrs_render (h2d camera+params, d2h image).
-        N > 1: accumulate + reduce + resolve to a host buffer on rank 0."""
+        """the public call with a HOST image on rank 0: camera + parameters host->device, image device->host"""
         rays = 0
         for k, (spec, sc, cam) in enumerate(built):
-            if world == 1:
-                api.render_gpu(cam, sc, spp, cfg.max_bounces, out=host_out[k], queue_capacity=args.queue)
-            else:
-                acc[k].zero_()
-                api.render_accumulate(cam, sc, spp, cfg.max_bounces, acc[k].data_ptr(), sptr, sample_offset=first,
-                                      spp_total=spp_total, queue_capacity=args.queue)
-                dist.reduce(acc[k], dst=0, op=dist.ReduceOp.SUM)
-                if rank == 0:
-                    api.resolve(sc, acc[k].data_ptr(), W, H, spp_total, host_out[k].ctypes.data, False, sptr)
+            render(sc, cam, spp_total, host_pin[k].data_ptr() if rank == 0 else 0, False, args.flags)
             rays += sc.stats()["rays"]
         return rays
 
@@ -337,25 +414,22 @@ def run_ours(args):
         except Exception:
             uuid = None
         sampler = ClockSampler(local, uuid)  # NVML is initialised here, outside the timed region
-    for _ in range(max(3, args.warmup)):
-        step_device()
+    warmup = max(3, args.warmup)
+    for _ in range(warmup):
+        step_device(args.flags)
     barrier()
     if sampler is not None:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     rays = launches = 0
-    phases = {"generate_ms": 0.0, "extend_ms": 0.0, "shade_ms": 0.0, "iterations": 0}
-    kernel_ms, kernel_launches, kernel_form = 0.0, 0, 0
+    kernel_ms = 0.0
+    last = None
     for _ in range(args.steps):
-        r, l, ph = step_device(0)
+        r, l, km, last = step_device(args.flags)
         rays += r
         launches += l
-        kernel_form = ph["kernel_form"]
-        for key in phases:
-            phases[key] += ph[key]
-        kernel_ms += ph["device_ms"]
-        kernel_launches += len(built)
+        kernel_ms += km
     e1.record(stream)
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -366,15 +440,17 @@ def run_ours(args):
     clocks = sampler.stop() if sampler is not None else None
     ms_total = float(ms.item())
     rays_all, launches_all = float(tot[0].item()), int(tot[1].item())
+    census = {k: int(last[k]) for k in ("census_mismatch_pixels", "nan_pixels", "negative_pixels")} if rank == 0 else None
 
     # ---- end to end ---------------------------------------------------------------------------
+    e2e_steps = args.e2e_steps or max(3, args.steps // 4)
     for _ in range(2):
         step_e2e()
     barrier()
     t0 = time.perf_counter()
     rays_e2e = 0
     e2e_step_ms = []
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         ts = time.perf_counter()
         rays_e2e += step_e2e()
         e2e_step_ms.append((time.perf_counter() - ts) * 1e3)
@@ -385,58 +461,70 @@ def run_ours(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_r, op=dist.ReduceOp.SUM)
 
+    # ---- parity check carried in the line: the N-GPU merged image against ONE GPU rendering the same samples ----
+    # (collective: every rank joins the split render; rank 0 then renders the same 8 spp alone through rrs_render)
+    check_spp = 8
+    spec0, sc0, cam0 = built[0]
+    chk = torch.empty((H, W, 3), dtype=torch.float32, device=dev) if rank == 0 else None
+    render(sc0, cam0, check_spp, chk.data_ptr() if rank == 0 else 0, True)
+    sc0.stats()
+    parity = None
+    if rank == 0:
+        st_multi = sc0.stats()
+        solo = api.render_gpu(cam0, sc0, check_spp, cfg.max_bounces, out=np.empty((H, W, 3), dtype=np.float32),
+                              queue_capacity=args.queue)
+        a = chk.cpu().numpy().astype(np.float64)
+        b = solo.astype(np.float64)
+        rel = np.abs(a - b) / (np.abs(b) + 1e-3)
+        parity = {"timed_steps": census,
+                  "split_vs_single_gpu": {"scene": spec0.name, "spp": check_spp, "n_gpus": world,
+                                          "max_rel_diff": float(rel.max()), "mean_rel_diff": float(rel.mean()),
+                                          "census_mismatch_pixels": int(st_multi["census_mismatch_pixels"]),
+                                          "tolerance": 1e-4},
+                  "ok": bool(census["census_mismatch_pixels"] == 0 and census["nan_pixels"] == 0 and census["negative_pixels"] == 0
+                             and st_multi["census_mismatch_pixels"] == 0 and rel.max() <= 1e-4)}
+    barrier()
+
+    # ---- traversal counters of this workload (COUNT form of the kernel, reduced spp; BVH scenes only) ----
+    trav = None
+    if rank == 0 and any(sc.n_prims > 8 for _, sc, _ in built):
+        nv = pt = rr = 0
+        for spec, sc, cam in built:
+            tmp = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+            api.render_accumulate(cam, sc, 2, cfg.max_bounces, tmp.data_ptr(), sptr, spp_total=2, queue_capacity=args.queue,
+                                  flags=_ffi.RRS_FLAG_COUNT_TRAVERSAL)
+            st = sc.stats()
+            nv += st["nodes_visited"]
+            pt += st["prims_tested"]
+            rr += st["rays"]
+            del tmp
+        trav = {"node_visits_per_ray": nv / max(1, rr), "box_tests_per_ray": 2.0 * nv / max(1, rr), "prims_tested_per_ray": pt / max(1, rr),
+                "sample": "2 spp, RRS_FLAG_COUNT_TRAVERSAL"}
+    barrier()
+
+    # ---- mini-records of the other configurations (N = 1) -------------------------------------
+    per_config = None
+    if world == 1 and not args.no_per_config:
+        per_config = {}
+        peak, peak_src = measured_peaks()
+        for key in ("c1", "c2", "c3", "c4"):
+            if key == args.workload:
+                continue
+            try:
+                per_config[key] = mini_record(key, scenes, api, _ffi, torch, dev, sptr, hdri, flush, clocks, sms, peak, peak_src, args)
+            except Exception as e:  # a mini-record must not take the headline down
+                per_config[key] = {"error": repr(e)}
+
     if rank == 0:
         value = rays_all / (ms_total * 1e-3) / 1e6
         e2e_value = float(e2e_r.item()) / float(e2e_s.item()) / 1e6
         peak, peak_src = measured_peaks()
-        model = bytes_per_ray_model(args.workload)
-        # The dominant kernel is the one persistent render kernel (one launch per scene render): k_pathloop for the
-        # small-scene configurations, k_wavefront otherwise.  Its launch durations are the CUDA-event times of
-        # rrs_render_accumulate on the launching stream, measured live above.
-        kname = {0: "k_wavefront", 1: "k_generate/k_extend/k_shade", 2: "k_pathloop"}.get(kernel_form, "?")
-        kms = kernel_ms
-        n_launch = max(1, kernel_launches)
-        rays_rank0 = rays  # timed on this rank over its own rays
-        roof = {"bound": "hbm", "kernel": kname, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
-                "traffic": None, "peak_source": peak_src, "avg_launch_ms": kms / n_launch, "launches": n_launch,
-                "share_of_step": kms / ms_total}
-        if model:
-            kb = model["kernel_bytes_per_ray"]
-            b = kb["generate"] + kb["extend"] + kb["shade"]
-            roof["bytes_per_ray"] = b
-            roof["bytes_per_launch"] = rays_rank0 * b / n_launch
-            roof["achieved"] = rays_rank0 * b / (kms * 1e-3) / 1e9
-            roof["frac"] = roof["achieved"] / peak
-            ncu = dict(model.get("ncu", {}))
-            if ncu.get("rays_per_launch_captured"):
-                # captured at reduced spp: per-launch counts scale with the rays of the launch
-                k = (rays_rank0 / n_launch) / ncu["rays_per_launch_captured"]
-                for f in ("dram_bytes_per_launch", "warp_instructions_per_launch"):
-                    ncu[f] = ncu[f] * k
-                ncu["scaled_by_rays"] = k
-            roof["traffic"] = ncu.get("dram_bytes_per_launch")
-            roof["ncu"] = {k: v for k, v in ncu.items() if k != "dram_bytes_per_launch"} or None
-            if ncu.get("warp_instructions_per_launch") and clocks and clocks.get("sm_mhz"):
-                # the limit that actually binds: issue slots.  warp instructions per launch are a constant of the code
-                # and the workload (ncu capture of this command, profiles/); the launch time is measured live.
-                sms = torch.cuda.get_device_properties(dev).multi_processor_count
-                peak_issue = sms * 4 * clocks["sm_mhz"] * 1e6          # 4 schedulers per SM, 1 warp instruction per cycle each
-                ach = ncu["warp_instructions_per_launch"] / (kms / n_launch * 1e-3)
-                roof["issue"] = {"bound": "issue slots", "achieved": ach / 1e9, "peak": peak_issue / 1e9, "unit": "Gwarp-inst/s",
-                                 "frac": ach / peak_issue, "warp_instructions_per_ray": ncu["warp_instructions_per_launch"] / (rays_rank0 / n_launch)}
-            small = all(sc.n_prims <= 8 for _, sc, _ in built)   # the brute-force form: scene staged in shared memory
-            if small:
-                roof["note"] = ("algorithmic bytes follow SURVEY 8(d) (node + primitive fetches + 144 B of queue state per ray, all counted "
-                                "as HBM traffic).  Here the primitives sit in shared memory, the closest hit is fused into the shade phase "
-                                "(no hit queue, one read of the ray record) and part of the queue stripes stays in L2, so the measured DRAM "
-                                "traffic (roofline.traffic) is below the algorithmic figure and frac > 1 only says the kernel is not "
-                                "HBM-bound: it is issue-bound (roofline.issue, roofline.ncu, profiles/)")
-            else:
-                roof["note"] = ("algorithmic bytes follow SURVEY 8(d): 32 B per visited node + 64 B per tested primitive + 144 B of queue "
-                                "state per ray, all counted as HBM traffic.  The node and primitive arrays of this scene fit the 126 MB L2, "
-                                "so most of those fetches never reach DRAM (roofline.traffic is the measured DRAM figure) and frac > 1 only "
-                                "says the kernel is not HBM-bound: traversal is bound by issue slots at low SIMT efficiency "
-                                "(roofline.issue, roofline.ncu, profiles/)")
+        kname = KERNEL_NAMES.get(int(last["kernel_form"]), "?")
+        # the dominant kernel is the one persistent render kernel (one launch per scene render); its launch durations
+        # are the CUDA-event times around it on the launching stream (RrsStats.device_ms), measured live above
+        roof = roofline_block(args.workload, kname, rays, kernel_ms, args.steps * len(built), ms_total, clocks, sms, peak, peak_src)
+        if trav:
+            roof["gpu_traversal"] = trav
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             import oracle  # cpu_baseline leg: the one place bench.py may execute oracle/
@@ -444,34 +532,103 @@ def run_ours(args):
             threads = oracle.hardware_threads()
             r1, s1 = cpu_render_sample(cfg, specs, hdri, 1, threads)
             s_spp = int(max(1, min(cfg.spp, args.cpu_seconds / max(s1, 1e-3))))
-            r, s = cpu_render_sample(cfg, specs, hdri, s_spp, threads)
+            r, s = cpu_render_sample(cfg, specs, hdri, s_spp, threads) if s_spp > 1 else (r1, s1)
             cpu = {"value": r / s / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{args.workload}: all {len(specs)} scene(s) at {W}x{H}, {s_spp} of {cfg.spp} spp, {r} rays in {s:.1f} s"}
         cam_bytes = (len(bytes(_ffi.RrsCamera())) + len(bytes(_ffi.RrsRenderParams()))) * len(built)
+        spp_note = "" if not args.spp else f" [total spp overridden to {spp_total}]"
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg.description + (f" [spp overridden to {spp}]" if args.spp else ""),
-                       "scenes": [s.name for s in specs], "width": W, "height": H, "spp_per_gpu": spp, "spp_total": spp_total,
+            "config": {"workload": cfg.description + spp_note,
+                       "scenes": [s.name for s in specs], "width": W, "height": H, "spp_total": spp_total,
+                       "spp_per_gpu": [api.sample_range(r_, world, spp_total)[1] for r_ in range(world)],
+                       "primitives": [sc.n_prims for _, sc, _ in built], "bvh_nodes": [sc.n_nodes for _, sc, _ in built],
                        "max_bounces": cfg.max_bounces, "hdri": "synthetic 2048x1024",
-                       "parallelism": f"sample-split x{world}, one NCCL reduce(sum) of the fp32 radiance buffer",
+                       "parallelism": f"sample-split x{world} inside rrs_render_multi, one ncclReduce(sum) of the fp32 radiance buffer",
                        "l2": "256 MB L2 flush between steps (inside the timed region)",
-                       "rays_per_step": rays_all / args.steps, "scene_setup_s": t_setup},
+                       "rays_per_step": rays_all / args.steps, "scene_setup_s": t_setup, "bvh_build_s": build_s},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cam_bytes,
-                    "d2h_bytes_per_step": W * H * 3 * 4 * len(built), "ms_per_step": e2e_step_ms},
+                    "d2h_bytes_per_step": W * H * 3 * 4 * len(built), "steps": e2e_steps, "ms_per_step": e2e_step_ms,
+                    "with_setup": {"value": float(e2e_r.item()) / e2e_steps / (float(e2e_s.item()) / e2e_steps + t_setup) / 1e6, "unit": UNIT,
+                                   "note": "one step plus the scene setup of this run (mesh load + host BVH build + upload), "
+                                           "which the reference's timer excludes (main.rs:59-100)"}},
             "gpu_launches": launches_all,
             "clocks": clocks,
             "roofline": roof,
-            "phases_ms": ({k: v for k, v in phases.items()} if kernel_form != 2 else
-                          {"iterations": phases["iterations"], "note": "k_pathloop interleaves generate/extend/shade per lane"}),
+            "phases_ms": {k: float(last[k]) for k in ("generate_ms", "extend_ms", "shade_ms")} | {"iterations": int(last["iterations"]),
+                          "note": "last timed launch; shares from in-kernel cycle counters"},
             "cpu_baseline": cpu,
+            "extra": {"parity_check": parity, "per_config": per_config},
         }
         print(json.dumps(line), flush=True)
     for _, sc, _ in built:
         sc.close()
+    if comm is not None:
+        comm.close()
+    else:
+        _ffi.cuda_lib().rrs_comm_destroy(comm_ptr)
     if world > 1:
         dist.destroy_process_group()
+
+
+def mini_record(key, scenes, api, _ffi, torch, dev, sptr, hdri, flush, clocks, sms, peak, peak_src, args, steps=2):
+    """One BASELINE configuration at full size on one GPU: 1 warm-up + `steps` timed steps (L2 flushed), device-resident."""
+    cfg = scenes.CONFIGS[key]
+    specs = cfg.specs()
+    t0 = time.time()
+    built = [(spec, spec.scene(hdri, device=dev.index, with_f64=False), spec.camera()) for spec in specs]
+    setup = time.time() - t0
+    W, H = cfg.width, cfg.height
+    acc = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+    img = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        rays, kms, st = 0, 0.0, None
+        flush.fill_(1)
+        for spec, sc, cam in built:
+            acc.zero_()
+            api.render_accumulate(cam, sc, cfg.spp, cfg.max_bounces, acc.data_ptr(), sptr, spp_total=cfg.spp)
+            api.resolve(sc, acc.data_ptr(), W, H, cfg.spp, img.data_ptr(), True, sptr)
+            st = sc.stats()
+            rays += st["rays"]
+            kms += st["device_ms"]
+        return rays, kms, st
+
+    step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    rays = 0
+    kms = 0.0
+    st = None
+    for _ in range(steps):
+        r, k, st = step()
+        rays += r
+        kms += k
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    rec = {"workload": cfg.description, "value": rays / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+           "rays_per_step": rays / steps, "scene_setup_s": setup,
+           "census_mismatch_pixels": int(st["census_mismatch_pixels"]), "nan_pixels": int(st["nan_pixels"]),
+           "roofline": roofline_block(key, KERNEL_NAMES.get(int(st["kernel_form"]), "?"), rays, kms, steps * len(built), ms, clocks, sms, peak, peak_src)}
+    if any(sc.n_prims > 8 for _, sc, _ in built):
+        nv = pt = rr = 0
+        for spec, sc, cam in built:
+            acc.zero_()
+            api.render_accumulate(cam, sc, 2, cfg.max_bounces, acc.data_ptr(), sptr, spp_total=2, flags=_ffi.RRS_FLAG_COUNT_TRAVERSAL)
+            s2 = sc.stats()
+            nv += s2["nodes_visited"]
+            pt += s2["prims_tested"]
+            rr += s2["rays"]
+        rec["roofline"]["gpu_traversal"] = {"node_visits_per_ray": nv / max(1, rr), "box_tests_per_ray": 2.0 * nv / max(1, rr),
+                                            "prims_tested_per_ray": pt / max(1, rr), "sample": "2 spp, RRS_FLAG_COUNT_TRAVERSAL"}
+    for _, sc, _ in built:
+        sc.close()
+    return rec
 
 
 def main():

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RRS_ABI_VERSION 1
+#define RRS_ABI_VERSION 2
 
 typedef enum RrsStatus {
     RRS_OK = 0,
@@ -35,7 +35,8 @@ typedef enum RrsStatus {
     RRS_ERR_NO_DEVICE = -2, /* no CUDA device, or not an sm_100 part                          */
     RRS_ERR_CUDA = -3,      /* CUDA runtime failure (message carries cudaGetErrorString)      */
     RRS_ERR_TOO_DEEP = -4,  /* BVH deeper than the traversal stack (RRS_MAX_STACK)            */
-    RRS_ERR_NOMEM = -5
+    RRS_ERR_NOMEM = -5,
+    RRS_ERR_COMM = -6       /* NCCL missing (libnccl.so.2 could not be loaded) or an NCCL call failed */
 } RrsStatus;
 
 /* Primitive kinds: the three Hittable impls reachable from the scene API
@@ -136,7 +137,8 @@ typedef struct RrsSceneDesc {
     uint32_t n_nodes;
     const RrsNode* nodes;
     const RrsNodeF64* nodes_f64; /* may be NULL: precision=64 queries then fail with RRS_ERR_INVALID */
-    uint32_t max_depth;          /* deepest node-stack the tree can need (host computes it) */
+    uint32_t max_depth;          /* deepest chain of RrsNodes from node 0 (the host computes it; the library walks the
+                                    tree itself and rejects a cycle, a node reached twice or a deeper chain) */
     uint32_t n_materials;
     const RrsMaterial* materials;
     uint32_t n_emissions;
@@ -147,7 +149,14 @@ typedef struct RrsSceneDesc {
     const float* hdri_rgb;
     /* Scene::new z_near / z_far (lib.rs:227-245; main.rs:52 passes 1e-6, 1e6) */
     double t_min, t_max;
+    uint32_t flags;        /* RRS_SCENE_* tuning switches, 0 = defaults */
+    uint32_t refill_lanes; /* BVH traversal: idle lanes of a warp that trigger a fetch of new rays; 0 = library default */
 } RrsSceneDesc;
+
+/* RrsSceneDesc.flags (measurement switches: every one keeps the results identical) */
+#define RRS_SCENE_NO_BRUTE 1u      /* scenes of <= 8 primitives: traverse the BVH instead of testing every primitive */
+#define RRS_SCENE_NO_BRUTE_BOX 2u  /* ... keep the brute-force list but drop the box around its sphere group */
+#define RRS_SCENE_NO_L2_PERSIST 4u /* do not pin the node / primitive arrays in L2 (access-policy window) */
 
 /* Derived camera fields exactly as Camera::new computes them (lib.rs:113-132), so that the
  * FOV quirk (z scaled by width/tan(fov/2)) stays on the host. */
@@ -169,7 +178,7 @@ typedef struct RrsRenderParams {
     uint32_t max_bounces;     /* rayrs/src/main.rs:77 passes 50 */
     uint64_t seed;            /* key of the counter-based RNG */
     uint32_t queue_capacity;  /* rays in flight; 0 = library default */
-    uint32_t flags;           /* reserved, 0 */
+    uint32_t flags;           /* RRS_FLAG_*, 0 = defaults */
 } RrsRenderParams;
 
 typedef struct RrsRay {
@@ -191,6 +200,9 @@ typedef struct RrsStats {
     uint64_t nodes_visited;   /* only with RRS_FLAG_COUNT_TRAVERSAL */
     uint64_t prims_tested;
     uint64_t kernel_form;     /* RRS_FORM_*: which render kernel the last render used */
+    uint64_t census_mismatch_pixels; /* last resolve: pixels whose count of terminated paths != spp_total (the accumulator's
+                                        .w lane counts them; 0 for a complete image — a built-in check of the queue
+                                        bookkeeping and, on several GPUs, of the sample split + reduce) */
 } RrsStats;
 
 #define RRS_FORM_WAVEFRONT 0u /* fused persistent wavefront kernel, ray/hit queues in HBM (k_wavefront) */
@@ -202,13 +214,19 @@ typedef struct RrsStats {
 #define RRS_FLAG_SPLIT_KERNELS 4u   /* one generate/extend/shade launch per wavefront iteration instead of the
                                        single fused persistent kernel (per-phase profiling) */
 #define RRS_FLAG_FORCE_QUEUES 8u    /* use the queue-based wavefront kernel (the default; kept for A/B scripts) */
+#define RRS_FLAG_NO_L2_WINDOW 32u    /* this render: no L2 access-policy window over the node / primitive arrays (A/B) */
 #define RRS_FLAG_FORCE_PATHLOOP 16u /* small scenes (<= 8 primitives): use the register-resident path loop
                                        (k_pathloop) instead of the queued kernel (A/B measurements, tests) */
 
 typedef struct RrsScene RrsScene;
 
-/* Scene::new (lib.rs:227-245) device half: validates, converts and uploads. */
+/* Scene::new (lib.rs:227-245) device half: validates, converts and uploads.
+ * An RrsScene carries mutable render state (ray queues, counters, staging buffers, statistics): one handle must
+ * not be used from two threads or two streams at the same time.  Handles on different devices are independent. */
 int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out);
+/* The same scene on n devices: validated and converted ONCE on the host, uploaded n times (the multi-GPU sample
+ * split replicates the scene).  out[i] lives on devices[i]; on failure nothing is left allocated. */
+int rrs_scene_create_multi(const RrsSceneDesc* desc, const int* devices, int n, RrsScene** out);
 void rrs_scene_destroy(RrsScene* scene);
 
 /* The render call (replaces rayrs/src/main.rs:61-94).  out_rgb: HOST buffer of
@@ -218,10 +236,45 @@ int rrs_render(RrsScene* scene, const RrsCamera* camera, const RrsRenderParams* 
 
 /* Same, but ACCUMULATES the per-pixel radiance SUM of this call's samples into a DEVICE
  * buffer of height*width float4 (rgb + sample count in .w), enqueued on `cuda_stream`
- * (a cudaStream_t; NULL = default stream) and not synchronised.  Used for the multi-GPU
- * sample split: each GPU accumulates its slice, one reduce merges the buffers. */
+ * (a cudaStream_t; NULL = default stream).  ASYNCHRONOUS: the call returns once the work is enqueued (one
+ * persistent kernel + a 128-byte counter read-back); rrs_stats / rrs_resolve / rrs_scene_destroy wait for it.
+ * Only RRS_FLAG_SPLIT_KERNELS (per-phase profiling) polls the device and therefore blocks.
+ * Used for the multi-GPU sample split: each GPU accumulates its slice, one reduce merges the buffers. */
 int rrs_render_accumulate(RrsScene* scene, const RrsCamera* camera, const RrsRenderParams* params,
                           void* d_sum_rgba, void* cuda_stream);
+
+/* ---- multi-GPU: samples of a pixel split over the GPUs of one box, ONE ncclReduce(sum) of the fp32 radiance
+ * buffers (the reference's seam is still the one render call, rayrs/src/main.rs:57-101).
+ * NCCL is loaded at run time (dlopen "libnccl.so.2") the first time a communicator is made, so a single-GPU
+ * host needs no NCCL; a missing library is RRS_ERR_COMM. */
+typedef struct RrsComm RrsComm;
+typedef struct RrsUniqueId { char bytes[128]; } RrsUniqueId; /* ncclUniqueId */
+
+/* (first global sample, number of samples) of `rank` among `world`: contiguous, disjoint, covering [0, spp);
+ * the first spp % world ranks take one extra sample. */
+int rrs_sample_range(uint32_t rank, uint32_t world, uint32_t spp, uint32_t* first, uint32_t* count);
+
+/* one process driving n devices (ncclCommInitAll): local rank i = global rank i on devices[i] */
+int rrs_comm_init_all(const int* devices, int n, RrsComm** out);
+/* one process per device: rank 0 makes the id, the host passes it to the other ranks by its own means
+ * (a file, MPI, torch.distributed ...), every rank then joins (ncclCommInitRank; collective) */
+int rrs_comm_unique_id(RrsUniqueId* out);
+int rrs_comm_init_rank(const RrsUniqueId* id, int world, int rank, int device, RrsComm** out);
+void rrs_comm_destroy(RrsComm* comm);
+
+/* The render call on several GPUs.  scenes[i] (i < n_local) is the scene on the i-th device of `comm`
+ * (n_local = n for rrs_comm_init_all, 1 for rrs_comm_init_rank; collective across processes in the second case).
+ * params->spp is the TOTAL sample count of the image (sample_offset = first global sample, normally 0); every
+ * global rank renders rrs_sample_range(rank, world, spp) into its own radiance buffer, the buffers are summed
+ * on global rank 0 by one ncclReduce, and rank 0 divides by spp and counts NaN / negative pixels.
+ * out_rgb (height*width*3 floats; host memory, or device memory on rank 0's GPU when out_is_device) is written
+ * by the process that holds global rank 0 and ignored elsewhere (may be NULL there).
+ * cuda_streams: n_local cudaStream_t to enqueue on, or NULL for the library's own per-device streams.
+ * Returns after the image is complete on rank 0 (other ranks: after their part is enqueued and the
+ * reduce has been issued; rrs_stats waits).  The RNG is keyed by the global sample index, so the
+ * image is independent of the number of GPUs up to fp32 summation order. */
+int rrs_render_multi(RrsScene* const* scenes, int n_local, RrsComm* comm, const RrsCamera* camera,
+                     const RrsRenderParams* params, float* out_rgb, int out_is_device, void* const* cuda_streams);
 
 /* d_sum_rgba (device, float4 per pixel) -> out (device or host per `out_is_device`) mean
  * RGB f32, dividing by spp_total, and counting NaN / negative pixels into the stats. */

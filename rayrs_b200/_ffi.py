@@ -12,9 +12,9 @@ _PKG = Path(__file__).resolve().parent
 CUDA_LIB_PATH = _PKG / "librayrs_b200.so"
 HOST_LIB_PATH = _PKG / "librayrs_host.so"
 
-RRS_ABI_VERSION = 1
+RRS_ABI_VERSION = 2
 RRS_OK = 0
-RRS_ERR_INVALID, RRS_ERR_NO_DEVICE, RRS_ERR_CUDA, RRS_ERR_TOO_DEEP, RRS_ERR_NOMEM = -1, -2, -3, -4, -5
+RRS_ERR_INVALID, RRS_ERR_NO_DEVICE, RRS_ERR_CUDA, RRS_ERR_TOO_DEEP, RRS_ERR_NOMEM, RRS_ERR_COMM = -1, -2, -3, -4, -5, -6
 RRS_REF_LEAF = 0x80000000
 RRS_REF_EMPTY = 0xFFFFFFFF
 RRS_FLAG_COUNT_TRAVERSAL = 1
@@ -22,6 +22,8 @@ RRS_FLAG_TIME_PHASES = 2
 RRS_FLAG_SPLIT_KERNELS = 4
 RRS_FLAG_FORCE_QUEUES = 8
 RRS_FLAG_FORCE_PATHLOOP = 16
+RRS_FLAG_NO_L2_WINDOW = 32
+RRS_SCENE_NO_BRUTE, RRS_SCENE_NO_BRUTE_BOX, RRS_SCENE_NO_L2_PERSIST = 1, 2, 4
 
 
 class RrsPrim(C.Structure):
@@ -54,7 +56,7 @@ class RrsSceneDesc(C.Structure):
                 ("max_depth", C.c_uint32), ("n_materials", C.c_uint32), ("materials", C.POINTER(RrsMaterial)),
                 ("n_emissions", C.c_uint32), ("emissions", C.POINTER(RrsEmission)),
                 ("hdri_width", C.c_uint32), ("hdri_height", C.c_uint32), ("hdri_rgb", C.POINTER(C.c_float)),
-                ("t_min", C.c_double), ("t_max", C.c_double)]
+                ("t_min", C.c_double), ("t_max", C.c_double), ("flags", C.c_uint32), ("refill_lanes", C.c_uint32)]
 
 
 class RrsCamera(C.Structure):
@@ -69,6 +71,10 @@ class RrsRenderParams(C.Structure):
                 ("queue_capacity", C.c_uint32), ("flags", C.c_uint32)]
 
 
+class RrsUniqueId(C.Structure):
+    _fields_ = [("bytes", C.c_char * 128)]
+
+
 class RrsRay(C.Structure):
     _fields_ = [("origin", C.c_double * 3), ("direction", C.c_double * 3)]
 
@@ -78,7 +84,7 @@ class RrsStats(C.Structure):
                 ("iterations", C.c_uint64), ("nan_pixels", C.c_uint64), ("negative_pixels", C.c_uint64),
                 ("device_ms", C.c_double), ("extend_ms", C.c_double), ("shade_ms", C.c_double),
                 ("generate_ms", C.c_double), ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64),
-                ("kernel_form", C.c_uint64)]
+                ("kernel_form", C.c_uint64), ("census_mismatch_pixels", C.c_uint64)]
 
 
 RRS_FORM_WAVEFRONT, RRS_FORM_SPLIT, RRS_FORM_PATHLOOP = 0, 1, 2
@@ -87,7 +93,15 @@ RRS_FORM_WAVEFRONT, RRS_FORM_SPLIT, RRS_FORM_PATHLOOP = 0, 1, 2
 # every symbol include/rayrs_b200.h declares: (name, restype, argtypes)
 CUDA_SYMBOLS = {
     "rrs_scene_create": (C.c_int, [C.POINTER(RrsSceneDesc), C.c_int, C.POINTER(C.c_void_p)]),
+    "rrs_scene_create_multi": (C.c_int, [C.POINTER(RrsSceneDesc), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
     "rrs_scene_destroy": (None, [C.c_void_p]),
+    "rrs_sample_range": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "rrs_comm_init_all": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "rrs_comm_unique_id": (C.c_int, [C.POINTER(RrsUniqueId)]),
+    "rrs_comm_init_rank": (C.c_int, [C.POINTER(RrsUniqueId), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "rrs_comm_destroy": (None, [C.c_void_p]),
+    "rrs_render_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.POINTER(RrsCamera), C.POINTER(RrsRenderParams),
+                                    C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "rrs_render": (C.c_int, [C.c_void_p, C.POINTER(RrsCamera), C.POINTER(RrsRenderParams), C.c_void_p]),
     "rrs_render_accumulate": (C.c_int, [C.c_void_p, C.POINTER(RrsCamera), C.POINTER(RrsRenderParams), C.c_void_p, C.c_void_p]),
     "rrs_resolve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p]),
@@ -107,9 +121,12 @@ HOST_SYMBOLS = {
     "rrh_last_error": (C.c_char_p, []),
     "rrh_scene_new": (C.c_void_p, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int,
                                     C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_int,
-                                    C.c_int, C.c_int]),
+                                    C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "rrh_scene_free": (None, [C.c_void_p]),
     "rrh_scene_handle": (C.c_void_p, [C.c_void_p]),
+    "rrh_scene_handle_at": (C.c_void_p, [C.c_void_p, C.c_uint32]),
+    "rrh_scene_comm": (C.c_void_p, [C.c_void_p]),
+    "rrh_scene_build_timing": (None, [C.c_void_p, C.POINTER(C.c_double)]),
     "rrh_scene_info": (None, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "rrh_scene_copy": (None, [C.c_void_p] * 7),
     "rrh_camera_new": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_uint32,

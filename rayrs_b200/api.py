@@ -257,7 +257,11 @@ class Scene:
     uploads it to GPU `device`.  upload=False builds the host half only (no GPU needed)."""
 
     def __init__(self, objects: Sequence[Object], z_near: float, z_far: float, heuristic: BvhHeuristic, hdri: Image,
-                 device: int = 0, with_f64: bool = True, upload: bool = True):
+                 device: int = 0, with_f64: bool = True, upload: bool = True, devices: Sequence[int] | None = None,
+                 scene_flags: int = 0, refill_lanes: int = 0, bvh_threads: int = 0):
+        """devices: the GPUs that hold the scene (default [device]); the BVH is built and flattened once and
+        uploaded to each, and render_gpu() then splits the samples over them (rrs_render_multi).
+        scene_flags / refill_lanes: RrsSceneDesc.flags / .refill_lanes (measurement switches)."""
         lib = _ffi.host_lib()
         flat = []
         for o in objects:
@@ -267,10 +271,13 @@ class Scene:
         self.z_near, self.z_far, self.heuristic = float(z_near), float(z_far), heuristic
         t = self.tables
         h = np.ascontiguousarray(hdri.pixels, dtype=np.float64)
+        self.devices = [int(d) for d in devices] if devices else [int(device)]
+        devs = (C.c_int * len(self.devices))(*self.devices)
         self._p = lib.rrh_scene_new(t.objs.ctypes.data, t.objs.shape[0], t.mats.ctypes.data, t.mats.shape[0],
                                     t.emis.ctypes.data if t.emis.size else None, t.emis.shape[0], heuristic.kind,
                                     heuristic.splits, h.ctypes.data, hdri.width, hdri.height, float(z_near),
-                                    float(z_far), int(device), int(with_f64), int(upload))
+                                    float(z_far), int(device), int(with_f64), int(upload), int(scene_flags),
+                                    int(refill_lanes), int(bvh_threads), devs, len(self.devices))
         if not self._p:
             raise ValueError(lib.rrh_last_error().decode())
         info = (C.c_uint64 * 7)()
@@ -279,13 +286,18 @@ class Scene:
         self.n_nodes, self.n_prims, self.max_depth, self.dead_nodes, self.n_materials, self._topo_len, self._n_boxes = (
             int(x) for x in info)
         self.build_seconds = bs.value
+        t6 = (C.c_double * 6)()
+        lib.rrh_scene_build_timing(self._p, t6)
+        self.build_timing = dict(zip(("boxes", "recursive", "numbering", "flatten", "depth", "topology"), (float(x) for x in t6)))
         self.handle = lib.rrh_scene_handle(self._p) if upload else None
+        self.handles = [lib.rrh_scene_handle_at(self._p, i) for i in range(len(self.devices))] if upload else []
 
     def close(self):
         if getattr(self, "_p", None):
             _ffi.host_lib().rrh_scene_free(self._p)
             self._p = None
             self.handle = None
+            self.handles = []
 
     def __del__(self):
         try:
@@ -343,11 +355,20 @@ class Scene:
         _ffi.check(_ffi.cuda_lib().rrs_rng_uniforms(self.handle, seed, pixel, sample, slot, out.ctypes.data))
         return out
 
-    def stats(self) -> dict:
+    def stats(self, index: int = 0) -> dict:
+        """RrsStats of the last render on the index-th device of the scene (waits for an asynchronous render)."""
         self._need_gpu()
         st = _ffi.RrsStats()
-        _ffi.check(_ffi.cuda_lib().rrs_stats(self.handle, C.byref(st)))
+        _ffi.check(_ffi.cuda_lib().rrs_stats(self.handles[index], C.byref(st)))
         return {name: getattr(st, name) for name, _ in _ffi.RrsStats._fields_}
+
+    def comm(self) -> int:
+        """The scene's own communicator over its devices (single-process multi-GPU)."""
+        self._need_gpu()
+        c = _ffi.host_lib().rrh_scene_comm(self._p)
+        if not c:
+            raise _ffi.RayrsError(_ffi.RRS_ERR_COMM, _ffi.host_lib().rrh_last_error().decode())
+        return c
 
 
 DEFAULT_SEED = 0x5EEDB200
@@ -368,8 +389,51 @@ def render_gpu(camera: Camera, scene: Scene, spp: int, max_bounces: int = 50, ou
     p = render_params(camera, spp, max_bounces, **opts)
     if out is None:
         out = np.empty((camera.y_pixels(), camera.x_pixels(), 3), dtype=np.float32)
+    if len(scene.handles) > 1:  # the scene lives on several GPUs: still one call
+        render_multi(camera, scene.handles, scene.comm(), spp, max_bounces, out_ptr=out.ctypes.data, **opts)
+        return out
     _ffi.check(_ffi.cuda_lib().rrs_render(scene.handle, C.byref(camera.c), C.byref(p), out.ctypes.data))
     return out
+
+
+def sample_range(rank: int, world: int, spp: int) -> tuple[int, int]:
+    """rrs_sample_range: (first global sample, number of samples) of `rank`."""
+    first, count = C.c_uint32(), C.c_uint32()
+    _ffi.check(_ffi.cuda_lib().rrs_sample_range(int(rank), int(world), int(spp), C.byref(first), C.byref(count)))
+    return int(first.value), int(count.value)
+
+
+class Comm:
+    """RrsComm of one process per GPU (torchrun): rank 0 makes the id, `exchange(bytes) -> bytes` hands it to
+    the other ranks (e.g. a torch.distributed broadcast — plumbing), every rank joins."""
+
+    def __init__(self, world: int, rank: int, device: int, exchange):
+        lib = _ffi.cuda_lib()
+        uid = _ffi.RrsUniqueId()
+        if rank == 0:
+            _ffi.check(lib.rrs_comm_unique_id(C.byref(uid)))
+        raw = exchange(bytes(uid) if rank == 0 else None)
+        C.memmove(C.byref(uid), raw, 128)
+        self.ptr = C.c_void_p()
+        _ffi.check(lib.rrs_comm_init_rank(C.byref(uid), int(world), int(rank), int(device), C.byref(self.ptr)))
+        self.world, self.rank = world, rank
+
+    def close(self):
+        if self.ptr:
+            _ffi.cuda_lib().rrs_comm_destroy(self.ptr)
+            self.ptr = None
+
+
+def render_multi(camera: Camera, handles, comm, spp: int, max_bounces: int = 50, out_ptr: int = 0, out_is_device: bool = False,
+                 streams=None, **opts) -> None:
+    """rrs_render_multi: `spp` TOTAL samples split over the ranks of `comm`, one NCCL reduce, mean image written on
+    global rank 0 to out_ptr (host memory, or rank 0's GPU when out_is_device).  handles: this process's scene
+    handles, one per local device of the communicator; comm: RrsComm pointer (Scene.comm() or Comm.ptr)."""
+    p = render_params(camera, spp, max_bounces, **opts)
+    hs = (C.c_void_p * len(handles))(*handles)
+    st = (C.c_void_p * len(handles))(*streams) if streams is not None else None
+    _ffi.check(_ffi.cuda_lib().rrs_render_multi(hs, len(handles), comm, C.byref(camera.c), C.byref(p), C.c_void_p(out_ptr),
+                                                int(out_is_device), st))
 
 
 def render_accumulate(camera: Camera, scene: Scene, spp: int, max_bounces: int, d_sum_ptr: int, stream_ptr: int = 0,

@@ -14,15 +14,15 @@
 
 using namespace rrs;
 
-struct RrsScene {
-    SceneImpl impl;
-};
 
 static thread_local std::string g_last_error;
 
 static int fail(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
+}
+namespace rrs {
+int api_fail(int code, const std::string& msg) { return fail(code, msg); }  // multi.cu shares the error channel
 }
 
 static bool in01(const double* c) {
@@ -40,7 +40,7 @@ static int usable_devices() {
     int ok = 0;
     for (int d = 0; d < n; ++d) {
         cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ok++;
+        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10 && p.minor == 0) ok++;
     }
     return ok;
 }
@@ -58,49 +58,71 @@ int rrs_abi_version(void) { return RRS_ABI_VERSION; }
 const char* rrs_last_error(void) { return g_last_error.c_str(); }
 int rrs_device_count(void) { return usable_devices(); }
 
-int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
-    if (!desc || !out) return fail(RRS_ERR_INVALID, "null argument");
-    *out = nullptr;
-    if (desc->abi_version != RRS_ABI_VERSION) return fail(RRS_ERR_INVALID, "ABI version mismatch");
-    // --- validation: the reference's construction-time assert!s -------------------------
-    if (desc->n_prims == 0 || !desc->prims) return fail(RRS_ERR_INVALID, "a BVH for 0 objects does not make sense (bvh.rs:229)");
-    if (desc->n_prims >= (1u << 28)) return fail(RRS_ERR_INVALID, "too many primitives (max 2^28-1)");
-    if (desc->n_nodes == 0 || !desc->nodes) return fail(RRS_ERR_INVALID, "no BVH nodes");
-    if (!(desc->t_min >= 0.)) return fail(RRS_ERR_INVALID, "z_near must be >= 0 (lib.rs:234)");
-    if (!(desc->t_max > desc->t_min)) return fail(RRS_ERR_INVALID, "z_far must be > z_near (lib.rs:235)");
-    if (desc->n_materials == 0 || !desc->materials) return fail(RRS_ERR_INVALID, "no materials");
-    if (desc->hdri_width < 2 || desc->hdri_height < 2 || !desc->hdri_rgb) return fail(RRS_ERR_INVALID, "HDRI must be at least 2x2");
+// ---------------------------------------------------------------------------------------
+// Scene::new, device half.  Three steps so that a scene replicated on n GPUs is validated and
+// converted once: validate(desc) -> convert(desc) -> upload(device) x n.
+// ---------------------------------------------------------------------------------------
+namespace {
+
+// Everything derived from the description on the host: the device records and the DScene fields that do not
+// depend on device addresses.
+struct HostScene {
+    std::vector<DPrim> prims;
+    std::vector<DNode16> nodes;
+    std::vector<DMat> mats;
+    std::vector<float4> emis;
+    std::vector<float4> hdri;
+    std::vector<double4> sphere64;  // exact sphere parameters (see "sphere re-entry" in intersect.cuh)
+    bool transmissive_sphere = false;
+    std::vector<double> tri64;  // 9 doubles per primitive index, only when a triangle vertex is not exact in fp32
+    DScene d{};  // pointer members are filled per device
+};
+
+int validate_desc(const RrsSceneDesc* desc, std::string& err) {
+    auto bad = [&](int code, const char* m) { err = m; return code; };
+    if (desc->abi_version != RRS_ABI_VERSION) return bad(RRS_ERR_INVALID, "ABI version mismatch");
+    // --- the reference's construction-time assert!s ----------------------------------------
+    if (desc->n_prims == 0 || !desc->prims) return bad(RRS_ERR_INVALID, "a BVH for 0 objects does not make sense (bvh.rs:229)");
+    if (desc->n_prims >= (1u << 28)) return bad(RRS_ERR_INVALID, "too many primitives (max 2^28-1)");
+    if (desc->n_nodes == 0 || !desc->nodes) return bad(RRS_ERR_INVALID, "no BVH nodes");
+    if (desc->n_nodes >= 0x80000000u) return bad(RRS_ERR_INVALID, "too many BVH nodes");
+    if (!(desc->t_min >= 0.)) return bad(RRS_ERR_INVALID, "z_near must be >= 0 (lib.rs:234)");
+    if (!(desc->t_max > desc->t_min)) return bad(RRS_ERR_INVALID, "z_far must be > z_near (lib.rs:235)");
+    if (desc->n_materials == 0 || !desc->materials) return bad(RRS_ERR_INVALID, "no materials");
+    if (desc->n_emissions > 0 && !desc->emissions) return bad(RRS_ERR_INVALID, "n_emissions > 0 but emissions is NULL");
+    if (desc->hdri_width < 2 || desc->hdri_height < 2 || !desc->hdri_rgb) return bad(RRS_ERR_INVALID, "HDRI must be at least 2x2");
+    if (desc->refill_lanes > 32) return bad(RRS_ERR_INVALID, "refill_lanes must be within 0..32");
     for (uint32_t i = 0; i < desc->n_materials; ++i) {
         const RrsMaterial& m = desc->materials[i];
-        if (m.tag > RRS_MAT_NO_REFLECT) return fail(RRS_ERR_INVALID, "unknown material tag");
+        if (m.tag > RRS_MAT_NO_REFLECT) return bad(RRS_ERR_INVALID, "unknown material tag");
         if (m.tag == RRS_MAT_NO_REFLECT) continue;
-        if (!in01(m.color)) return fail(RRS_ERR_INVALID, "material color must be within [0,1] (material.rs:597)");
+        if (!in01(m.color)) return bad(RRS_ERR_INVALID, "material color must be within [0,1] (material.rs:597)");
         bool rough = m.tag == RRS_MAT_COOK_TORRANCE || m.tag == RRS_MAT_COOK_TORRANCE_REFRACT ||
                      m.tag == RRS_MAT_COOK_TORRANCE_GLASS || m.tag == RRS_MAT_PLASTIC;
         bool has_ior = m.tag == RRS_MAT_REFRACT || m.tag == RRS_MAT_GLASS || m.tag == RRS_MAT_COOK_TORRANCE_REFRACT ||
                        m.tag == RRS_MAT_COOK_TORRANCE_GLASS || m.tag == RRS_MAT_PLASTIC ||
                        (m.tag == RRS_MAT_COOK_TORRANCE && m.fresnel_kind == RRS_FRESNEL_DIELECTRIC);
-        if (rough && !(m.alpha > 0. && std::isfinite(m.alpha))) return fail(RRS_ERR_INVALID, "alpha must be positive and finite (material.rs:706-707)");
-        if (has_ior && !(m.ior > 0. && std::isfinite(m.ior))) return fail(RRS_ERR_INVALID, "ior must be positive and finite (material.rs:629-630)");
-        if (m.tag == RRS_MAT_PLASTIC && !in01(m.spec_color)) return fail(RRS_ERR_INVALID, "spec_color must be within [0,1] (material.rs:882)");
-        if (m.fresnel_kind > RRS_FRESNEL_METALLIC) return fail(RRS_ERR_INVALID, "unknown Fresnel kind");
+        if (rough && !(m.alpha > 0. && std::isfinite(m.alpha))) return bad(RRS_ERR_INVALID, "alpha must be positive and finite (material.rs:706-707)");
+        if (has_ior && !(m.ior > 0. && std::isfinite(m.ior))) return bad(RRS_ERR_INVALID, "ior must be positive and finite (material.rs:629-630)");
+        if (m.tag == RRS_MAT_PLASTIC && !in01(m.spec_color)) return bad(RRS_ERR_INVALID, "spec_color must be within [0,1] (material.rs:882)");
+        if (m.fresnel_kind > RRS_FRESNEL_METALLIC) return bad(RRS_ERR_INVALID, "unknown Fresnel kind");
     }
     for (uint32_t i = 0; i < desc->n_emissions; ++i) {
-        if (!(desc->emissions[i].strength >= 0.)) return fail(RRS_ERR_INVALID, "emission strength must be >= 0 (material.rs:1064)");
-        if (!in01(desc->emissions[i].color)) return fail(RRS_ERR_INVALID, "RGB values need to be between 0 and 1 (material.rs:1065-1068)");
+        if (!(desc->emissions[i].strength >= 0.)) return bad(RRS_ERR_INVALID, "emission strength must be >= 0 (material.rs:1064)");
+        if (!in01(desc->emissions[i].color)) return bad(RRS_ERR_INVALID, "RGB values need to be between 0 and 1 (material.rs:1065-1068)");
     }
     for (uint32_t i = 0; i < desc->n_prims; ++i) {
         const RrsPrim& p = desc->prims[i];
-        if (p.type > RRS_TRIANGLE) return fail(RRS_ERR_INVALID, "unknown primitive type");
-        if (p.material >= desc->n_materials) return fail(RRS_ERR_INVALID, "primitive material index out of range");
-        if (p.emission >= (int32_t)desc->n_emissions) return fail(RRS_ERR_INVALID, "primitive emission index out of range");
-        if (p.type == RRS_SPHERE && !(p.v[0] > 0.)) return fail(RRS_ERR_INVALID, "Radius has to be positive (geometry.rs:97)");
+        if (p.type > RRS_TRIANGLE) return bad(RRS_ERR_INVALID, "unknown primitive type");
+        if (p.material >= desc->n_materials) return bad(RRS_ERR_INVALID, "primitive material index out of range");
+        if (p.emission >= (int32_t)desc->n_emissions) return bad(RRS_ERR_INVALID, "primitive emission index out of range");
+        if (p.type == RRS_SPHERE && !(p.v[0] > 0.)) return bad(RRS_ERR_INVALID, "Radius has to be positive (geometry.rs:97)");
         if (p.type == RRS_PLANE) {
-            if (!(p.v[0] >= 0. && p.v[0] <= 5.)) return fail(RRS_ERR_INVALID, "unknown plane axis");
-            if (!(p.v[1] < p.v[2] && p.v[3] < p.v[4])) return fail(RRS_ERR_INVALID, "Plane cannot be constructed with umin >= umax or vmin >= vmax (geometry.rs:205-212)");
+            if (!(p.v[0] >= 0. && p.v[0] <= 5.)) return bad(RRS_ERR_INVALID, "unknown plane axis");
+            if (!(p.v[1] < p.v[2] && p.v[3] < p.v[4])) return bad(RRS_ERR_INVALID, "Plane cannot be constructed with umin >= umax or vmin >= vmax (geometry.rs:205-212)");
         }
         for (int k = 0; k < 9; ++k)
-            if (std::isnan(p.v[k])) return fail(RRS_ERR_INVALID, "NaN in primitive (bvh.rs:104 partial_cmp().unwrap() panics)");
+            if (std::isnan(p.v[k])) return bad(RRS_ERR_INVALID, "NaN in primitive (bvh.rs:104 partial_cmp().unwrap() panics)");
     }
     for (uint32_t i = 0; i < desc->n_nodes; ++i) {
         const RrsNode& nd = desc->nodes[i];
@@ -109,41 +131,39 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
             if (r == RRS_REF_EMPTY) continue;
             if (r & RRS_REF_LEAF) {
                 uint32_t first = r & 0x0FFFFFFFu, count = ((r >> 28) & 7u) + 1u;
-                if (count > 4 || first + count > desc->n_prims) return fail(RRS_ERR_INVALID, "leaf run out of range");
+                if (count > 4 || first + count > desc->n_prims) return bad(RRS_ERR_INVALID, "leaf run out of range");
             } else if (r >= desc->n_nodes || r == 0) {
-                return fail(RRS_ERR_INVALID, "node reference out of range");
+                return bad(RRS_ERR_INVALID, "node reference out of range");
             }
         }
     }
-    if (desc->max_depth + 3 > 120) return fail(RRS_ERR_TOO_DEEP, "BVH deeper than the 117-entry shared-memory traversal stack");
-
-    // --- device ---------------------------------------------------------------------------
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        return fail(RRS_ERR_NO_DEVICE, "no CUDA device: rayrs_b200 has no CPU fallback");
+    // The traversal stack in shared memory is sized from max_depth and the release kernels do not bounds-check it,
+    // so the value is not taken on trust: walk the node graph from node 0, reject a node reached twice (a cycle or
+    // a DAG — neither is a tree, and a cycle would spin the persistent kernel forever) and a chain longer than stated.
+    if (desc->max_depth > 117u) return bad(RRS_ERR_TOO_DEEP, "BVH deeper than the 117-entry shared-memory traversal stack");
+    {
+        std::vector<uint8_t> seen(desc->n_nodes, 0);
+        std::vector<std::pair<uint32_t, uint32_t>> todo;  // (node, depth)
+        todo.emplace_back(0u, 1u);
+        seen[0] = 1;
+        while (!todo.empty()) {
+            const auto [f, depth] = todo.back();
+            todo.pop_back();
+            if (depth > desc->max_depth) return bad(RRS_ERR_INVALID, "BVH is deeper than RrsSceneDesc.max_depth states");
+            for (uint32_t r : {desc->nodes[f].ref0, desc->nodes[f].ref1}) {
+                if (r == RRS_REF_EMPTY || (r & RRS_REF_LEAF)) continue;
+                if (seen[r]) return bad(RRS_ERR_INVALID, "BVH node reached twice: the node graph must be a tree (no cycles, no shared subtrees)");
+                seen[r] = 1;
+                todo.emplace_back(r, depth + 1u);
+            }
+        }
     }
-    if (device < 0 || device >= ndev) return fail(RRS_ERR_INVALID, "device index out of range");
-    cudaDeviceProp prop;
-    std::string err;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(RRS_ERR_CUDA, "cudaGetDeviceProperties failed");
-    if (prop.major != 10) return fail(RRS_ERR_NO_DEVICE, std::string("device is not sm_100 (") + prop.name + "): kernels are built for sm_100a only");
-    if (cudaSetDevice(device) != cudaSuccess) return fail(RRS_ERR_CUDA, "cudaSetDevice failed");
+    return RRS_OK;
+}
 
-    auto* sc = new RrsScene();
-    SceneImpl& s = sc->impl;
-    s.device = device;
-    s.num_sms = prop.multiProcessorCount;
-    s.n_prims = desc->n_prims;
-    s.n_nodes = desc->n_nodes;
-    s.max_depth = desc->max_depth;
-    s.tmin = desc->t_min;
-    s.tmax = desc->t_max;
-
-    // --- fp32 records ---------------------------------------------------------------------
-    std::vector<DPrim> hp(desc->n_prims);
-    std::vector<double4> hs64;  // exact sphere parameters (see "sphere re-entry" in intersect.cuh)
-    bool transmissive_sphere = false, has_triangles = false;
+void convert_desc(const RrsSceneDesc* desc, HostScene& h) {
+    h.prims.resize(desc->n_prims);
+    bool has_triangles = false, inexact_vertex = false;
     for (uint32_t i = 0; i < desc->n_prims; ++i) {
         const RrsPrim& p = desc->prims[i];
         DPrim q;
@@ -155,20 +175,21 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
         std::memcpy(&femi, &emi, 4);
         if (p.type == RRS_TRIANGLE) {
             has_triangles = true;
+            for (int k = 0; k < 9; ++k) inexact_vertex = inexact_vertex || (double)(float)p.v[k] != p.v[k];
             // the three vertices (shared vertices of a mesh must stay bit-identical across triangles
             // for the watertight test, so no per-triangle edge vectors are stored)
             q.a = make_float4((float)p.v[0], (float)p.v[1], (float)p.v[2], fmeta);
             q.b = make_float4((float)p.v[3], (float)p.v[4], (float)p.v[5], fobj);
             q.c = make_float4((float)p.v[6], (float)p.v[7], (float)p.v[8], femi);
         } else if (p.type == RRS_SPHERE) {
-            uint32_t sidx = (uint32_t)hs64.size();
+            uint32_t sidx = (uint32_t)h.sphere64.size();
             float fsidx;
             std::memcpy(&fsidx, &sidx, 4);
-            hs64.push_back(make_double4(p.v[1], p.v[2], p.v[3], p.v[0]));
+            h.sphere64.push_back(make_double4(p.v[1], p.v[2], p.v[3], p.v[0]));
             uint32_t tag = desc->materials[p.material].tag;
             if (tag == RRS_MAT_REFRACT || tag == RRS_MAT_GLASS || tag == RRS_MAT_COOK_TORRANCE_REFRACT ||
                 tag == RRS_MAT_COOK_TORRANCE_GLASS)
-                transmissive_sphere = true;
+                h.transmissive_sphere = true;
             q.a = make_float4((float)p.v[1], (float)p.v[2], (float)p.v[3], fmeta);
             q.b = make_float4((float)p.v[0], fsidx, 0.f, fobj);
             q.c = make_float4(0.f, 0.f, 0.f, femi);
@@ -181,9 +202,15 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
             q.c = make_float4(0.f, 0.f, 0.f, femi);
         }
         q.pad = make_float4(0.f, 0.f, 0.f, 0.f);
-        hp[i] = q;
+        h.prims[i] = q;
     }
-    std::vector<DMat> hm(desc->n_materials);
+    if (inexact_vertex) {
+        // the f64 vertices travel too: triangle_t64 (intersect.cuh) re-evaluates the accepted hit's distance from them
+        h.tri64.assign((size_t)desc->n_prims * 9, 0.);
+        for (uint32_t i = 0; i < desc->n_prims; ++i)
+            if (desc->prims[i].type == RRS_TRIANGLE) std::memcpy(&h.tri64[(size_t)i * 9], desc->prims[i].v, 9 * sizeof(double));
+    }
+    h.mats.resize(desc->n_materials);
     for (uint32_t i = 0; i < desc->n_materials; ++i) {
         const RrsMaterial& m = desc->materials[i];
         float ftag, fkind;
@@ -197,22 +224,19 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
         d.m0 = make_float4((float)m.color[0], (float)m.color[1], (float)m.color[2], ftag);
         d.m1 = make_float4((float)m.spec_color[0], (float)m.spec_color[1], (float)m.spec_color[2], (float)(m.alpha * m.alpha));
         d.m2 = make_float4((float)m.ior, fkind, (float)r0, 0.f);
-        hm[i] = d;
+        h.mats[i] = d;
     }
-    std::vector<float4> he(std::max<uint32_t>(desc->n_emissions, 1));
+    h.emis.resize(std::max<uint32_t>(desc->n_emissions, 1));
     for (uint32_t i = 0; i < desc->n_emissions; ++i) {
         const RrsEmission& e = desc->emissions[i];
-        he[i] = make_float4((float)(e.strength * e.color[0]), (float)(e.strength * e.color[1]), (float)(e.strength * e.color[2]), 0.f);
+        h.emis[i] = make_float4((float)(e.strength * e.color[0]), (float)(e.strength * e.color[1]), (float)(e.strength * e.color[2]), 0.f);
     }
     size_t ntex = (size_t)desc->hdri_width * desc->hdri_height;
-    std::vector<float4> hh(ntex);
+    h.hdri.resize(ntex);
     for (size_t i = 0; i < ntex; ++i)
-        hh[i] = make_float4(desc->hdri_rgb[3 * i], desc->hdri_rgb[3 * i + 1], desc->hdri_rgb[3 * i + 2], 0.f);
-
-    int rc = RRS_OK;
+        h.hdri[i] = make_float4(desc->hdri_rgb[3 * i], desc->hdri_rgb[3 * i + 1], desc->hdri_rgb[3 * i + 2], 0.f);
     static_assert(sizeof(RrsNode) == 64, "RrsNode must be 64 bytes");
     static_assert(sizeof(RrsNodeF64) == 128, "RrsNodeF64 must be 128 bytes");
-    if (rc == RRS_OK) rc = upload(&s.prims, hp.data(), hp.size(), err);
     {
         // device nodes: fp16 boxes rounded outward, one half2 (lo, hi) word per axis (device_types.cuh).
         // An RRS_REF_EMPTY child must fail the slab test by itself (the traversal does not look at the
@@ -224,10 +248,10 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
             std::memcpy(&bh, &hh, 2);
             return (uint32_t)bl | ((uint32_t)bh << 16);
         };
-        std::vector<DNode16> hn(desc->n_nodes);
+        h.nodes.resize(desc->n_nodes);
         for (uint32_t i = 0; i < desc->n_nodes; ++i) {
             const RrsNode& nd = desc->nodes[i];
-            DNode16& q = hn[i];
+            DNode16& q = h.nodes[i];
             for (int k = 0; k < 3; ++k) {
                 q.w[k] = nd.ref0 == RRS_REF_EMPTY ? pack(INFINITY, -INFINITY) : pack(nd.lo0[k], nd.hi0[k]);
                 q.w[3 + k] = nd.ref1 == RRS_REF_EMPTY ? pack(INFINITY, -INFINITY) : pack(nd.lo1[k], nd.hi1[k]);
@@ -235,37 +259,19 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
             q.w[6] = nd.ref0;
             q.w[7] = nd.ref1;
         }
-        if (rc == RRS_OK) rc = upload(&s.nodes, hn.data(), hn.size(), err);
     }
-    if (rc == RRS_OK) rc = upload(&s.mats, hm.data(), hm.size(), err);
-    if (rc == RRS_OK) rc = upload(&s.emis, he.data(), he.size(), err);
-    if (rc == RRS_OK) rc = upload(&s.hdri, hh.data(), hh.size(), err);
-    if (rc == RRS_OK && transmissive_sphere) rc = upload(&s.sphere64, hs64.data(), hs64.size(), err);
-    if (rc == RRS_OK && desc->nodes_f64) {
-        rc = upload(&s.nodes_f64, desc->nodes_f64, desc->n_nodes, err);
-        if (rc == RRS_OK) rc = upload(&s.prims_f64, desc->prims, desc->n_prims, err);
-    }
-    if (rc != RRS_OK) {
-        rrs_scene_destroy(sc);
-        return fail(rc, err);
-    }
-    s.d.prims = s.prims;
-    s.d.nodes = s.nodes;
-    s.d.mats = s.mats;
-    s.d.emis = s.emis;
-    s.d.hdri = s.hdri;
-    s.d.n_prims = desc->n_prims;
-    s.d.n_nodes = desc->n_nodes;
-    s.d.n_mats = desc->n_materials;
-    s.d.hdri_w = desc->hdri_width;
-    s.d.hdri_h = desc->hdri_height;
-    s.d.tmin = (float)desc->t_min;
-    s.d.tmax = (float)desc->t_max;
-    s.d.tmin64 = desc->t_min;
-    s.d.tmax64 = desc->t_max;
-    s.d.sphere64 = s.sphere64;
-    s.d.stack_entries = std::max<uint32_t>(desc->max_depth + 3, 4);  // + the TRAV_DONE sentinel
-    s.d.has_triangles = has_triangles ? 1u : 0u;
+    DScene& d = h.d;
+    d.n_prims = desc->n_prims;
+    d.n_nodes = desc->n_nodes;
+    d.n_mats = desc->n_materials;
+    d.hdri_w = desc->hdri_width;
+    d.hdri_h = desc->hdri_height;
+    d.tmin = (float)desc->t_min;
+    d.tmax = (float)desc->t_max;
+    d.tmin64 = desc->t_min;
+    d.tmax64 = desc->t_max;
+    d.stack_entries = std::max<uint32_t>(desc->max_depth + 3, 4);  // + the TRAV_DONE sentinel
+    d.has_triangles = has_triangles ? 1u : 0u;
     {
         // primitives the traversal can reach (leaf runs below live nodes), for the small-scene path
         std::vector<uint32_t> reach;
@@ -286,28 +292,27 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
         }
         std::sort(reach.begin(), reach.end());
         reach.erase(std::unique(reach.begin(), reach.end()), reach.end());
-        s.d.brute_count = 0;
-        const char* e = std::getenv("RRS_NO_BRUTE");
-        if (small && !reach.empty() && !(e && std::atoi(e))) {
-            s.d.brute_count = (uint32_t)reach.size();
+        d.brute_count = 0;
+        if (small && !reach.empty() && !(desc->flags & RRS_SCENE_NO_BRUTE)) {
+            d.brute_count = (uint32_t)reach.size();
             // grouped by type (spheres, planes, triangles), DFS order inside a group
             std::stable_sort(reach.begin(), reach.end(), [&](uint32_t x, uint32_t y) {
                 auto rank = [&](uint32_t i) { return desc->prims[i].type == RRS_SPHERE ? 0 : (desc->prims[i].type == RRS_PLANE ? 1 : 2); };
                 return rank(x) < rank(y);
             });
-            s.d.brute_spheres = s.d.brute_planes = 0;
+            d.brute_spheres = d.brute_planes = 0;
             for (size_t k = 0; k < reach.size(); ++k) {
-                s.d.brute_prim[k] = reach[k];
-                if (desc->prims[reach[k]].type == RRS_SPHERE) s.d.brute_spheres++;
-                else if (desc->prims[reach[k]].type == RRS_PLANE) s.d.brute_planes++;
+                d.brute_prim[k] = reach[k];
+                if (desc->prims[reach[k]].type == RRS_SPHERE) d.brute_spheres++;
+                else if (desc->prims[reach[k]].type == RRS_PLANE) d.brute_planes++;
             }
             // one box around the sphere group: a ray that misses it skips every sphere test (a one-level hierarchy;
             // most camera rays of the sphere-row scenes go to the floor or the sky).  Padded outward, so the fp32
             // slab test in closest_hit_brute stays conservative.
-            s.d.brute_box_on = 0;
-            if (s.d.brute_spheres >= 3) {
+            d.brute_box_on = 0;
+            if (d.brute_spheres >= 3) {
                 double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-                for (uint32_t k = 0; k < s.d.brute_spheres; ++k) {
+                for (uint32_t k = 0; k < d.brute_spheres; ++k) {
                     const RrsPrim& p = desc->prims[reach[k]];
                     const double r = std::sqrt(p.v[0]);
                     for (int a = 0; a < 3; ++a) {
@@ -318,12 +323,11 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
                 bool finite = true;
                 for (int a = 0; a < 3; ++a) {
                     const double pad = 1e-5 * (hi[a] - lo[a]) + 1e-6 * std::max(std::fabs(lo[a]), std::fabs(hi[a])) + 1e-30;
-                    s.d.brute_box[a] = std::nextafter((float)(lo[a] - pad), -std::numeric_limits<float>::infinity());
-                    s.d.brute_box[3 + a] = std::nextafter((float)(hi[a] + pad), std::numeric_limits<float>::infinity());
-                    finite = finite && std::isfinite(s.d.brute_box[a]) && std::isfinite(s.d.brute_box[3 + a]);
+                    d.brute_box[a] = std::nextafter((float)(lo[a] - pad), -std::numeric_limits<float>::infinity());
+                    d.brute_box[3 + a] = std::nextafter((float)(hi[a] + pad), std::numeric_limits<float>::infinity());
+                    finite = finite && std::isfinite(d.brute_box[a]) && std::isfinite(d.brute_box[3 + a]);
                 }
-                const char* nb = std::getenv("RRS_NO_BRUTE_BOX");
-                s.d.brute_box_on = (finite && !(nb && std::atoi(nb))) ? 1u : 0u;
+                d.brute_box_on = (finite && !(desc->flags & RRS_SCENE_NO_BRUTE_BOX)) ? 1u : 0u;
             }
         }
     }
@@ -331,12 +335,123 @@ int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
         // children of the reference root lie inside its box, so its own slab test (the virtual root's
         // only job) can be skipped whenever the root is an inner node
         const RrsNode& vr = desc->nodes[0];
-        s.d.root = (vr.ref1 == RRS_REF_EMPTY && vr.ref0 != RRS_REF_EMPTY && !(vr.ref0 & RRS_REF_LEAF)) ? vr.ref0 : 0u;
+        d.root = (vr.ref1 == RRS_REF_EMPTY && vr.ref0 != RRS_REF_EMPTY && !(vr.ref0 & RRS_REF_LEAF)) ? vr.ref0 : 0u;
     }
     // rays of a deep tree differ widely in length: refill early; a tiny scene amortises the fetch over more lanes
-    s.d.refill_lanes = desc->max_depth > 6 ? 4u : 12u;
-    if (const char* e = std::getenv("RRS_REFILL_LANES")) s.d.refill_lanes = std::min(32, std::max(1, std::atoi(e)));
+    d.refill_lanes = desc->refill_lanes ? desc->refill_lanes : (desc->max_depth > 6 ? 4u : 12u);
+}
+
+int upload_scene(const RrsSceneDesc* desc, const HostScene& h, int device, RrsScene** out, std::string& err) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        err = "no CUDA device: rayrs_b200 has no CPU fallback";
+        return RRS_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) { err = "device index out of range"; return RRS_ERR_INVALID; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { err = "cudaGetDeviceProperties failed"; return RRS_ERR_CUDA; }
+    if (!(prop.major == 10 && prop.minor == 0)) {
+        // the library holds sm_100a code only: an architecture-specific cubin has no PTX fallback and loads on 10.0 parts alone
+        err = std::string("device is not sm_100 (") + prop.name + "): kernels are built for sm_100a only";
+        return RRS_ERR_NO_DEVICE;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { err = "cudaSetDevice failed"; return RRS_ERR_CUDA; }
+
+    auto* sc = new RrsScene();
+    SceneImpl& s = sc->impl;
+    s.device = device;
+    s.num_sms = prop.multiProcessorCount;
+    s.n_prims = desc->n_prims;
+    s.n_nodes = desc->n_nodes;
+    s.max_depth = desc->max_depth;
+    s.tmin = desc->t_min;
+    s.tmax = desc->t_max;
+    int rc = RRS_OK;
+    {
+        // nodes and primitives share ONE allocation (nodes first) so that a single L2 access-policy window can
+        // cover what the traversal fetches (wavefront.cu, "L2 residency")
+        const size_t node_bytes = (sizeof(DNode16) * h.nodes.size() + 255) & ~(size_t)255;
+        const size_t prim_bytes = sizeof(DPrim) * h.prims.size();
+        auto up = [&]() -> int {
+            RRS_CUDA_CHECK(cudaMalloc(&s.geom_blob, node_bytes + prim_bytes), err);
+            RRS_CUDA_CHECK(cudaMemcpy(s.geom_blob, h.nodes.data(), sizeof(DNode16) * h.nodes.size(), cudaMemcpyHostToDevice), err);
+            RRS_CUDA_CHECK(cudaMemcpy(s.geom_blob + node_bytes, h.prims.data(), prim_bytes, cudaMemcpyHostToDevice), err);
+            return RRS_OK;
+        };
+        rc = up();
+        s.nodes = reinterpret_cast<DNode16*>(s.geom_blob);
+        s.prims = reinterpret_cast<DPrim*>(s.geom_blob + node_bytes);
+        s.node_bytes = node_bytes;
+        s.geom_bytes = node_bytes + prim_bytes;
+    }
+    if (rc == RRS_OK) rc = upload(&s.mats, h.mats.data(), h.mats.size(), err);
+    if (rc == RRS_OK) rc = upload(&s.emis, h.emis.data(), h.emis.size(), err);
+    if (rc == RRS_OK) rc = upload(&s.hdri, h.hdri.data(), h.hdri.size(), err);
+    if (rc == RRS_OK && h.transmissive_sphere) rc = upload(&s.sphere64, h.sphere64.data(), h.sphere64.size(), err);
+    if (rc == RRS_OK && !h.tri64.empty()) rc = upload(&s.tri64, h.tri64.data(), h.tri64.size(), err);
+    if (rc == RRS_OK && desc->nodes_f64) {
+        rc = upload(&s.nodes_f64, desc->nodes_f64, desc->n_nodes, err);
+        if (rc == RRS_OK) rc = upload(&s.prims_f64, desc->prims, desc->n_prims, err);
+    }
+    if (rc == RRS_OK && !(desc->flags & RRS_SCENE_NO_L2_PERSIST)) {
+        // L2 residency: set aside as much of L2 as the device allows for persisting lines; the render pins the
+        // node (+ primitive) array in it through an access-policy window on its stream
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+        if (max_persist > 0 && max_window > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess) {
+            s.l2_persist_bytes = (size_t)max_persist;
+            s.l2_window_max = (size_t)max_window;
+        }
+        cudaGetLastError();
+    }
+    if (rc != RRS_OK) {
+        rrs_scene_destroy(sc);
+        return rc;
+    }
+    s.d = h.d;
+    s.d.prims = s.prims;
+    s.d.nodes = s.nodes;
+    s.d.mats = s.mats;
+    s.d.emis = s.emis;
+    s.d.hdri = s.hdri;
+    s.d.sphere64 = s.sphere64;
+    s.d.tri64 = s.tri64;
     *out = sc;
+    return RRS_OK;
+}
+
+}  // namespace
+
+int rrs_scene_create(const RrsSceneDesc* desc, int device, RrsScene** out) {
+    return rrs_scene_create_multi(desc, &device, 1, out);
+}
+
+int rrs_scene_create_multi(const RrsSceneDesc* desc, const int* devices, int n, RrsScene** out) {
+    if (!desc || !out || !devices || n < 1) return fail(RRS_ERR_INVALID, "null argument");
+    for (int i = 0; i < n; ++i) out[i] = nullptr;
+    std::string err;
+    int rc = validate_desc(desc, err);
+    if (rc != RRS_OK) return fail(rc, err);
+    // a host without any CUDA device fails before the conversion work
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(RRS_ERR_NO_DEVICE, "no CUDA device: rayrs_b200 has no CPU fallback");
+    }
+    HostScene h;
+    convert_desc(desc, h);
+    for (int i = 0; i < n; ++i) {
+        rc = upload_scene(desc, h, devices[i], &out[i], err);
+        if (rc != RRS_OK) {
+            for (int k = 0; k < i; ++k) {
+                rrs_scene_destroy(out[k]);
+                out[k] = nullptr;
+            }
+            return fail(rc, err);
+        }
+    }
     return RRS_OK;
 }
 
@@ -345,10 +460,11 @@ void rrs_scene_destroy(RrsScene* scene) {
     SceneImpl& s = scene->impl;
     cudaSetDevice(s.device);
     wf_free(&s);
-    cudaFree(s.prims); cudaFree(s.nodes); cudaFree(s.mats); cudaFree(s.emis); cudaFree(s.hdri);
-    cudaFree(s.prims_f64); cudaFree(s.nodes_f64); cudaFree(s.sphere64); cudaFree(s.accum); cudaFree(s.census); cudaFree(s.resolve_dev);
+    cudaFree(s.geom_blob); cudaFree(s.mats); cudaFree(s.emis); cudaFree(s.hdri);
+    cudaFree(s.prims_f64); cudaFree(s.nodes_f64); cudaFree(s.sphere64); cudaFree(s.tri64); cudaFree(s.accum); cudaFree(s.census); cudaFree(s.resolve_dev);
     if (s.resolve_pinned) cudaFreeHost(s.resolve_pinned);
     if (s.h_census) cudaFreeHost(s.h_census);
+    if (s.own_stream) cudaStreamDestroy(s.own_stream);
     delete scene;
 }
 
@@ -438,6 +554,7 @@ int rrs_rng_uniforms(RrsScene* scene, uint64_t seed, uint32_t pixel, uint32_t sa
 
 int rrs_stats(RrsScene* scene, RrsStats* out) {
     if (!scene || !out) return fail(RRS_ERR_INVALID, "null argument");
+    wf_finish_stats(&scene->impl);  // waits for an asynchronous rrs_render_accumulate
     *out = scene->impl.stats;
     return RRS_OK;
 }

@@ -129,6 +129,9 @@ struct DScene {
     // exact f64 (centre xyz, r^2) of every sphere; non-null only when the scene holds a sphere with a
     // transmissive material — see "sphere re-entry" in intersect.cuh
     const double4* sphere64;
+    // f64 vertices (9 doubles per primitive index) when some triangle vertex is not exactly representable in fp32,
+    // else nullptr — see triangle_t64 in intersect.cuh
+    const double* tri64;
     uint32_t stack_entries;  // per-thread traversal stack size (entries, including the sentinel)
     uint32_t has_triangles;  // 0: no triangle in the scene (the per-leaf shear setup is skipped)
     uint32_t root;           // node the traversal starts at (the virtual root's only child when that is an inner node)

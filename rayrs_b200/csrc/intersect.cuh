@@ -184,6 +184,32 @@ __device__ __forceinline__ bool hit_triangle(float4 a, float4 b, float4 c, float
     return true;
 }
 
+// Hit distance of an ACCEPTED triangle hit, re-evaluated in f64 (Moeller-Trumbore as geometry.rs:359-375 writes it:
+// t = (q . e2) / (p . e1), p = d x e2, q = (o - p1) x e1).  The fp32 projection test above decides WHETHER a triangle
+// is hit (watertight) and which hit is closest; its distance carries three fp32 ulps of backward error, which at
+// grazing incidence — where t itself is ill-conditioned — reached 1.28e-5 relative on one ray in 10^7
+// (profiles/r01p_parity_measured.txt).  The closest hit's distance is therefore recomputed once per ray from the
+// vertices the reference holds: the fp32 records when every vertex of the scene is exactly representable in fp32
+// (PLY meshes), the f64 copy `tri64` otherwise.  ~45 f64 instructions per hit, outside the traversal loop.
+__device__ __forceinline__ float triangle_t64(const DScene& sc, uint32_t pi, float4 a, float4 b, float4 c, float3 o, float3 d,
+                                              float t32) {
+    double p1x = a.x, p1y = a.y, p1z = a.z, p2x = b.x, p2y = b.y, p2z = b.z, p3x = c.x, p3y = c.y, p3z = c.z;
+    if (sc.tri64 != nullptr) {
+        const double* v = sc.tri64 + 9 * (size_t)pi;
+        p1x = v[0]; p1y = v[1]; p1z = v[2]; p2x = v[3]; p2y = v[4]; p2z = v[5]; p3x = v[6]; p3y = v[7]; p3z = v[8];
+    }
+    const double e1x = p2x - p1x, e1y = p2y - p1y, e1z = p2z - p1z;
+    const double e2x = p3x - p1x, e2y = p3y - p1y, e2z = p3z - p1z;
+    const double tx = (double)o.x - p1x, ty = (double)o.y - p1y, tz = (double)o.z - p1z;
+    const double dx = d.x, dy = d.y, dz = d.z;
+    const double px = dy * e2z - dz * e2y, py = dz * e2x - dx * e2z, pz = dx * e2y - dy * e2x;
+    const double qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
+    const double den = px * e1x + py * e1y + pz * e1z;
+    const double t64 = (qx * e2x + qy * e2y + qz * e2z) / den;
+    // a degenerate denominator (den ~ 0 in f64 while the fp32 projection accepted) keeps the fp32 value
+    return fabs(t64 - (double)t32) <= 1e-2 * fabs((double)t32) ? (float)t64 : t32;
+}
+
 struct TravCounters {
     uint32_t nodes, prims;
 };
@@ -434,17 +460,7 @@ __device__ __forceinline__ void closest_hit_brute(const DScene& sc, const DPrim*
         const uint32_t pi = sc.brute_prim[k];
         const float4 a = s_prims[k].a, b = s_prims[k].b;
         float t;
-        bool hit;
-        if (SPH64 && pi == origin_prim && o64 != nullptr) {
-            // re-entry: the reference's f64 arithmetic on the f64 hit point, then the leaf filter in f64
-            double t64;
-            double4 s64 = sc.sphere64[__float_as_uint(b.y)];
-            hit = sphere_intersect64(s64, o64[0], o64[1], o64[2], (double)d.x, (double)d.y, (double)d.z, t64) &&
-                  t64 > sc.tmin64 && t64 < sc.tmax64;
-            t = (float)t64;
-        } else {
-            hit = hit_sphere(a, b, o, d, pi == origin_prim, t);
-        }
+        const bool hit = hit_sphere(a, b, o, d, pi == origin_prim, t);  // (the f64 re-entry variants took the loop above)
         update_hit(sc, hit, t, pi, tbest, best);
     }
     for (; k < sc.brute_spheres + sc.brute_planes; ++k) {
@@ -487,6 +503,15 @@ __device__ __forceinline__ void closest_hit(const DScene& sc, float3 o, float3 d
     }
     tbest = tv.tbest;
     best = tv.best;
+}
+
+// triangle_t64 for the closest hit `best` of a finished query (no-op for misses, spheres and planes)
+__device__ __forceinline__ float refine_hit_t(const DScene& sc, uint32_t best, float3 o, float3 d, float t) {
+    if (best == RRS_NO_PRIM || !sc.has_triangles) return t;
+    const float4* pp = reinterpret_cast<const float4*>(sc.prims + best);
+    const float4 a = __ldg(pp);
+    if (prim_type(a) != RRS_TRIANGLE) return t;
+    return triangle_t64(sc, best, a, __ldg(pp + 1), __ldg(pp + 2), o, d, t);
 }
 
 }  // namespace rrs

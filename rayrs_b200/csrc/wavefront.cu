@@ -41,6 +41,28 @@ static constexpr int kBlock = RRS_BLOCK_THREADS;  // threads per block of the pe
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// Queue traffic streams (every ray / state / hit record is written once and read once): ld/st.global.cs marks the
+// lines evict-first so that they do not push the BVH out of L2 (see "L2 residency" in wf_render_accumulate).
+#ifndef RRS_QUEUE_STREAMING
+#define RRS_QUEUE_STREAMING 1
+#endif
+template <typename T>
+__device__ __forceinline__ T ldq(const T* p) {
+#if RRS_QUEUE_STREAMING
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+template <typename T>
+__device__ __forceinline__ void stq(T* p, T v) {
+#if RRS_QUEUE_STREAMING
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 // ---------------------------------------------------------------------------------------
 // Queue layout: the ray / state / hit queues are split into `regions` stripes of `region_cap`
 // slots; block b of every kernel owns stripe b.  All queue bookkeeping (work cursor, append
@@ -166,9 +188,9 @@ __device__ __forceinline__ void phase_generate(const RenderConst& rc, DCounters*
         }
         if (!valid) continue;
         RRS_CHECK(slot < q.region_cap);
-        ray_o[slot] = make_float4(rc.cam.origin.x, rc.cam.origin.y, rc.cam.origin.z, __uint_as_float(RRS_NO_PRIM));
-        ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
-        state[slot] = make_float4(1.f, 1.f, 1.f, __uint_as_float(sample << 8));
+        stq(ray_o + slot, make_float4(rc.cam.origin.x, rc.cam.origin.y, rc.cam.origin.z, __uint_as_float(RRS_NO_PRIM)));
+        stq(ray_d + slot, make_float4(d.x, d.y, d.z, __uint_as_float(pixel)));
+        stq(state + slot, make_float4(1.f, 1.f, 1.f, __uint_as_float(sample << 8)));
     }
     __syncthreads();
     if (threadIdx.x == 0) count[b] = rc.exact_tiles ? n0 + got : s_u32[1];
@@ -228,12 +250,12 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
             if (base >= n) break;
             const uint32_t i = base + lane;
             if (i < n) {
-                float4 o4 = ray_o[i], d4 = ray_d[i];
+                float4 o4 = ldq(ray_o + i), d4 = ldq(ray_d + i);
                 const double* o64 = (SPH64 && q.org64) ? q.org64 + 3 * (off + i) : nullptr;
                 float t;
                 uint32_t prim;
                 closest_hit_brute<COUNT, SPH64>(sc, s_prims, xyz(o4), xyz(d4), __float_as_uint(o4.w), o64, t, prim, cnt);
-                hits[i] = make_float2(t, __uint_as_float(prim));
+                stq(hits + i, make_float2(t, __uint_as_float(prim)));
             }
         }
         flush_trav_counters<COUNT>(c, cnt);
@@ -261,7 +283,7 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
             exhausted = base + (uint32_t)__popc(idle) >= n;
             const uint32_t i = base + (uint32_t)__popc(idle & lt_mask);
             if (!has_ray && i < n) {
-                float4 o4 = ray_o[i], d4 = ray_d[i];
+                float4 o4 = ldq(ray_o + i), d4 = ldq(ray_d + i);
                 const double* o64 = (SPH64 && q.org64) ? q.org64 + 3 * (off + i) : nullptr;
                 trav_begin<SPH64>(sc, xyz(o4), xyz(d4), __float_as_uint(o4.w), o64, stack, r, tv);
                 has_ray = true;
@@ -288,7 +310,7 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
         // ---- leaves ----
         if (!trav_on_inner(tv) && tv.cur != TRAV_DONE) trav_leaf_step<COUNT, SPH64>(sc, r, tv, stack, cnt);
         if (has_ray && tv.cur == TRAV_DONE) {
-            hits[my_i] = make_float2(tv.tbest, __uint_as_float(tv.best));
+            stq(hits + my_i, make_float2(tv.tbest, __uint_as_float(tv.best)));
             has_ray = false;
         }
     }
@@ -384,6 +406,14 @@ __device__ __forceinline__ NextRay shade_hit(const DScene& sc, const RenderConst
         nrm = normalize3(f3((float)(nx * inv_r), (float)(ny * inv_r), (float)(nz * inv_r)));
         pos = f3((float)p64x, (float)p64y, (float)p64z);
         carry64 = true;
+    } else if (prim_type(a) == RRS_TRIANGLE) {
+        // the accepted hit's distance in f64 (triangle_t64), then Ray::point lib.rs:41-43 and the flat normal of
+        // Triangle::new geometry.rs:341-355 from the same three vertices
+        const float4 b = __ldg(pp + 1), c = __ldg(pp + 2);
+        const float t = triangle_t64(sc, prim, a, b, c, o, d, h.x);
+        pos = madd3(d, t, o);
+        const float3 p1 = xyz(a);
+        nrm = normalize3(cross3(sub3(xyz(b), p1), sub3(xyz(c), p1)));
     } else {
         pos = madd3(d, h.x, o);  // Ray::point lib.rs:41-43
         nrm = prim_normal(sc.prims, prim, a, pos);
@@ -403,7 +433,9 @@ __device__ __forceinline__ NextRay shade_hit(const DScene& sc, const RenderConst
         }
         thr = mul3(thr, so.color);
         float p = fmaxf(fmaxf(thr.x, thr.y), thr.z);
-        if (!(u.w > p) && bounce + 1u < rc.max_bounces) {
+        // lib.rs:543-546: `if random() > p { break }`, then thr / p.  p == 0 (a black surface) ends the path here: the
+        // 24-bit uniform is exactly 0 once in 2^24 draws, and surviving on it would put 0/0 into the accumulator
+        if (p > 0.f && !(u.w > p) && bounce + 1u < rc.max_bounces) {
             thr = f3(thr.x / p, thr.y / p, thr.z / p);
             finished = false;
             alive = true;
@@ -457,7 +489,7 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
         nr.alive = false;
         nr.carry64 = false;
         if (i < n) {
-            float4 o4 = ray_o[i], d4 = ray_d[i], st = state[i];
+            float4 o4 = ldq(ray_o + i), d4 = ldq(ray_d + i), st = ldq(state + i);
             const double* o64 = (SPH64 && q.org64) ? q.org64 + 3 * (off + i) : nullptr;
             float2 h;
             if (INLINE_HIT) {
@@ -465,7 +497,7 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
                 closest_hit_brute<COUNT, SPH64>(sc, s_prims, xyz(o4), xyz(d4), __float_as_uint(o4.w), o64, h.x, prim, tcnt);
                 h.y = __uint_as_float(prim);
             } else {
-                h = hits[i];
+                h = ldq(hits + i);
             }
             if (__float_as_uint(h.y) == RRS_NO_PRIM) {
                 shade_miss(sc, accum, d4, st);
@@ -483,9 +515,9 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
             if (alive) {
                 uint32_t slot = obase + __popc(ballot & ((1u << lane) - 1u));
                 RRS_CHECK(slot < q.region_cap);
-                out_o[slot] = nr.no;
-                out_d[slot] = nr.nd;
-                out_state[slot] = nr.ns;
+                stq(out_o + slot, nr.no);
+                stq(out_d + slot, nr.nd);
+                stq(out_state + slot, nr.ns);
                 if (SPH64 && nr.carry64 && q.org64) {
                     double* o64 = q.org64 + 3 * (ooff + slot);
                     o64[0] = nr.p64x; o64[1] = nr.p64y; o64[2] = nr.p64z;
@@ -577,9 +609,9 @@ __device__ __forceinline__ bool small_scene_iteration(const DScene& sc, const Re
         const double* o64 = nullptr;
         if (valid) {
             if (i < n0) {  // a survivor of the previous bounce
-                o4 = ray_o[i];
-                d4 = ray_d[i];
-                st = state[i];
+                o4 = ldq(ray_o + i);
+                d4 = ldq(ray_d + i);
+                st = ldq(state + i);
                 if (SPH64 && q.org64) o64 = q.org64 + 3 * (off + i);
             } else {       // a new path: Camera::generate_primary_ray, straight into registers
                 uint32_t pixel = 0, sample = 0;
@@ -608,9 +640,9 @@ __device__ __forceinline__ bool small_scene_iteration(const DScene& sc, const Re
             if (nr.alive) {
                 const uint32_t slot = obase + __popc(ballot & lt_mask);
                 RRS_CHECK(slot < q.region_cap);
-                out_o[slot] = nr.no;
-                out_d[slot] = nr.nd;
-                out_state[slot] = nr.ns;
+                stq(out_o + slot, nr.no);
+                stq(out_d + slot, nr.nd);
+                stq(out_state + slot, nr.ns);
                 if (SPH64 && nr.carry64 && q.org64) {
                     double* w64 = q.org64 + 3 * (ooff + slot);
                     w64[0] = nr.p64x; w64[1] = nr.p64y; w64[2] = nr.p64z;
@@ -823,12 +855,13 @@ k_pathloop(DScene sc, RenderConst rc, DCounters* __restrict__ c, float4* __restr
 // resolve: sum -> mean, NaN / negative census (rayrs/src/main.rs:81-89)
 // ---------------------------------------------------------------------------------------
 __global__ void k_resolve(const float4* __restrict__ accum, float* __restrict__ out, uint32_t npix, float inv_spp,
-                          unsigned long long* __restrict__ census) {
-    uint32_t nan_cnt = 0, neg_cnt = 0;
+                          float expect_paths, unsigned long long* __restrict__ census) {
+    uint32_t nan_cnt = 0, neg_cnt = 0, miss_cnt = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
-        float4 a = accum[i];
+        float4 a = __ldcs(accum + i);
         if (isnan(a.x) || isnan(a.y) || isnan(a.z)) nan_cnt++;
         if (a.x < 0.f || a.y < 0.f || a.z < 0.f) neg_cnt++;
+        if (a.w != expect_paths) miss_cnt++;  // path census: every pixel must have terminated exactly spp_total paths
         out[3 * (size_t)i + 0] = a.x * inv_spp;
         out[3 * (size_t)i + 1] = a.y * inv_spp;
         out[3 * (size_t)i + 2] = a.z * inv_spp;
@@ -836,10 +869,12 @@ __global__ void k_resolve(const float4* __restrict__ accum, float* __restrict__ 
     for (int o = 16; o > 0; o >>= 1) {
         nan_cnt += __shfl_xor_sync(0xFFFFFFFFu, nan_cnt, o);
         neg_cnt += __shfl_xor_sync(0xFFFFFFFFu, neg_cnt, o);
+        miss_cnt += __shfl_xor_sync(0xFFFFFFFFu, miss_cnt, o);
     }
-    if ((threadIdx.x & 31) == 0 && (nan_cnt | neg_cnt)) {
+    if ((threadIdx.x & 31) == 0 && (nan_cnt | neg_cnt | miss_cnt)) {
         atomicAdd(census + 0, (unsigned long long)nan_cnt);
         atomicAdd(census + 1, (unsigned long long)neg_cnt);
+        atomicAdd(census + 2, (unsigned long long)miss_cnt);
     }
 }
 
@@ -893,13 +928,14 @@ __global__ void __launch_bounds__(kBlock) k_intersect32(DScene sc, const float4*
     stack.init(s_stack + threadIdx.x, blockDim.x);
     TravCounters cnt{0, 0};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 o4 = ray_o[i], d4 = ray_d[i];
+        float4 o4 = ldq(ray_o + i), d4 = ldq(ray_d + i);
         float t;
         uint32_t prim;
         if (sc.brute_count)
             closest_hit_brute<false, false>(sc, s_prims, xyz(o4), xyz(d4), RRS_NO_PRIM, nullptr, t, prim, cnt);
         else
             closest_hit<false, false>(sc, xyz(o4), xyz(d4), RRS_NO_PRIM, nullptr, stack, t, prim, cnt);
+        t = refine_hit_t(sc, prim, xyz(o4), xyz(d4), t);
         if (prim == RRS_NO_PRIM) {
             obj_id[i] = -1;
             t_out[i] = INFINITY;
@@ -972,6 +1008,7 @@ static int ensure_wavefront(SceneImpl* s, uint32_t regions, uint32_t region_cap,
 }
 
 void wf_free(SceneImpl* s) {
+    wf_finish_stats(s);  // an asynchronous render may still be running
     Wavefront& w = s->wf;
     free_queues(w);
     cudaFree(w.counters);
@@ -1007,6 +1044,7 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     if ((unsigned long long)p->sample_offset + p->spp > (1ull << 24)) { err = "sample index exceeds 2^24"; return RRS_ERR_INVALID; }
     if ((unsigned long long)p->width * p->height > 0xFFFFFFFFull) { err = "image too large"; return RRS_ERR_INVALID; }
     RRS_CUDA_CHECK(cudaSetDevice(s->device), err);
+    wf_finish_stats(s);  // a scene's queues and counters serve one render at a time
     // ---- launch geometry: every kernel runs `regions` blocks, block b owns queue stripe b ----
     const bool count = (p->flags & RRS_FLAG_COUNT_TRAVERSAL) != 0;
     const bool phases = (p->flags & RRS_FLAG_TIME_PHASES) != 0;
@@ -1082,8 +1120,37 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     DCounters init{};
     init.total_paths = rc.npix_pad * (unsigned long long)p->spp;
     if (p->max_bounces == 0) init.total_paths = 0;  // radiance() with 0 bounces returns black
-    *w.h_counters = init;
-    RRS_CUDA_CHECK(cudaMemcpyAsync(w.counters, w.h_counters, sizeof(DCounters), cudaMemcpyHostToDevice, stream), err);
+    // pageable source: the runtime stages it before the call returns, so `init` may die with this frame
+    RRS_CUDA_CHECK(cudaMemcpyAsync(w.counters, &init, sizeof(DCounters), cudaMemcpyHostToDevice, stream), err);
+
+    // ---- L2 residency ------------------------------------------------------------------------
+    // The traversal's node / primitive fetches are the only traffic with reuse; the ray, state and hit queues stream
+    // (written once, read once, ld/st.global.cs) and the accumulator is touched once per path.  Without help the
+    // queue streams evict the tree: the 1M-triangle scene (20 MB of nodes + 64 MB of primitives, smaller than the
+    // 126 MB L2) ran at a 56 % L2 hit rate and 181 B of DRAM reads per ray (profiles/r01o_c4_wavefront_metrics.csv).
+    // An access-policy window marks the tree persisting: over [nodes | primitives] when most of it fits the
+    // persisting carve-out, over the nodes alone otherwise.
+    bool window_set = false;
+    if (!brute && s->l2_persist_bytes && s->geom_blob && !(p->flags & RRS_FLAG_NO_L2_WINDOW)) {
+        size_t bytes = s->geom_bytes;
+        if ((double)s->l2_persist_bytes < 0.6 * (double)bytes) bytes = s->node_bytes;
+        bytes = std::min(bytes, s->l2_window_max);
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.base_ptr = s->geom_blob;
+        av.accessPolicyWindow.num_bytes = bytes;
+        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)s->l2_persist_bytes / (double)bytes);
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        window_set = cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+        cudaGetLastError();
+    }
+    auto clear_window = [&]() {
+        if (!window_set) return;
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.num_bytes = 0;  // launches after this one run without a window
+        cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+    };
 
     // event pool: [0]=start [1]=stop, then 5 per iteration when phase timing is on
     auto get_event = [&](size_t idx) -> cudaEvent_t {
@@ -1097,12 +1164,12 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     cudaEvent_t ev_start = get_event(0), ev_stop = get_event(1);
     RRS_CUDA_CHECK(cudaEventRecord(ev_start, stream), err);
 
-    uint64_t launches = 0, iters = 0;
-    std::vector<size_t> phase_ev;  // indices of per-iteration event groups
+    uint64_t launches = 0;
+    s->phase_ev.clear();
     const bool split = (p->flags & RRS_FLAG_SPLIT_KERNELS) != 0;
     // The register-resident path loop beat the queued kernel by 16 % while that still ran a separate extend phase
-    // (gpurun_out/sweep_pathloop.log); with the closest hit fused into the shade phase the queued kernel is as fast or
-    // faster on every small scene (plastic series +5 %, gpurun_out/sweep_pl_vs_q.log) — compaction gives it full warps
+    // (profiles/ab_logs/sweep_pathloop.log); with the closest hit fused into the shade phase the queued kernel is as
+    // fast or faster on every small scene (plastic series +5 %, sweep_pl_vs_q.log) — compaction gives it full warps
     // every iteration — so the path loop is an option (RRS_FLAG_FORCE_PATHLOOP), not the default.
     const bool want_pathloop = (p->flags & RRS_FLAG_FORCE_PATHLOOP) != 0;
     const bool pathloop = !split && brute && want_pathloop && !(p->flags & RRS_FLAG_FORCE_QUEUES);
@@ -1113,16 +1180,13 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
         path_fn<<<(uint32_t)s->num_sms * (uint32_t)std::max(occ_path, 1), kBlock, 0, stream>>>(s->d, rc, w.counters, d_accum);
         launches = 1;
         RRS_CUDA_CHECK(cudaGetLastError(), err);
-        RRS_CUDA_CHECK(cudaMemcpyAsync(w.h_counters, w.counters, sizeof(DCounters), cudaMemcpyDeviceToHost, stream), err);
-        RRS_CUDA_CHECK(cudaStreamSynchronize(stream), err);
     } else if (!split) {
         // one persistent launch for the whole render
         fused_fn<<<regions, kBlock, smem, stream>>>(s->d, rc, w.counters, q, d_accum);
         launches = 1;
         RRS_CUDA_CHECK(cudaGetLastError(), err);
-        RRS_CUDA_CHECK(cudaMemcpyAsync(w.h_counters, w.counters, sizeof(DCounters), cudaMemcpyDeviceToHost, stream), err);
-        RRS_CUDA_CHECK(cudaStreamSynchronize(stream), err);
     } else {
+        // per-phase profiling form: the host polls the `done` flag, so this branch blocks
         int cur = 0;
         const uint32_t chunk = 8;
         size_t ev_next = 2;
@@ -1135,7 +1199,7 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
                     e0 = ev_next;
                     ev_next += 5;
                     get_event(e0 + 4);
-                    phase_ev.push_back(e0);
+                    s->phase_ev.push_back(e0);
                     cudaEventRecord(s->ev_pool[e0], stream);
                 }
                 k_plan<<<1, 32, 0, stream>>>(w.counters);
@@ -1155,22 +1219,44 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
             done = w.h_counters->done != 0;
         }
     }
+    clear_window();
+    RRS_CUDA_CHECK(cudaMemcpyAsync(w.h_counters, w.counters, sizeof(DCounters), cudaMemcpyDeviceToHost, stream), err);
     RRS_CUDA_CHECK(cudaEventRecord(ev_stop, stream), err);
-    RRS_CUDA_CHECK(cudaEventSynchronize(ev_stop), err);
+    // not synchronised: the statistics are completed by wf_finish_stats (rrs_stats, rrs_resolve, the next render)
+    s->stats = RrsStats{};
+    s->stats.kernel_launches = launches;
+    s->stats.paths = (uint64_t)p->width * p->height * p->spp;
+    s->stats.kernel_form = pathloop ? RRS_FORM_PATHLOOP : (split ? RRS_FORM_SPLIT : RRS_FORM_WAVEFRONT);
+    s->stats_pending = true;
+    s->pending_split = split;
+    s->pending_phases = phases;
+    s->pending_window = window_set;
+    return RRS_OK;
+}
+
+void wf_finish_stats(SceneImpl* s) {
+    if (!s->stats_pending) return;
+    s->stats_pending = false;
+    cudaSetDevice(s->device);
+    if (s->ev_pool.size() < 2 || cudaEventSynchronize(s->ev_pool[1]) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    if (s->pending_window) {
+        cudaCtxResetPersistingL2Cache();  // hand the carve-out back: the next launch may be a different scene's
+        cudaGetLastError();
+    }
+    Wavefront& w = s->wf;
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, ev_start, ev_stop);
-    iters = w.h_counters->iterations;
+    cudaEventElapsedTime(&ms, s->ev_pool[0], s->ev_pool[1]);
     RrsStats& st = s->stats;
     st.rays = w.h_counters->rays;
-    st.paths = (uint64_t)p->width * p->height * p->spp;
-    st.kernel_launches = launches;
-    st.iterations = iters;
+    st.iterations = w.h_counters->iterations;
     st.device_ms = ms;
-    st.kernel_form = pathloop ? RRS_FORM_PATHLOOP : (split ? RRS_FORM_SPLIT : RRS_FORM_WAVEFRONT);
     st.nodes_visited = w.h_counters->nodes_visited;
     st.prims_tested = w.h_counters->prims_tested;
     st.generate_ms = st.extend_ms = st.shade_ms = 0.;
-    if (!split) {
+    if (!s->pending_split) {
         // per-phase share of the fused kernel from its in-kernel cycle counters (summed over blocks)
         double cg = (double)w.h_counters->cyc_generate, ce = (double)w.h_counters->cyc_extend, cs = (double)w.h_counters->cyc_shade;
         double tot = cg + ce + cs;
@@ -1179,9 +1265,9 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
             st.extend_ms = ms * ce / tot;
             st.shade_ms = ms * cs / tot;
         }
-    } else if (phases) {
+    } else if (s->pending_phases) {
         double g = 0, e = 0, sh = 0;
-        for (size_t e0 : phase_ev) {
+        for (size_t e0 : s->phase_ev) {
             float a = 0, b = 0, c2 = 0;
             cudaEventElapsedTime(&a, s->ev_pool[e0 + 1], s->ev_pool[e0 + 2]);
             cudaEventElapsedTime(&b, s->ev_pool[e0 + 2], s->ev_pool[e0 + 3]);
@@ -1192,20 +1278,20 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
         st.extend_ms = e;
         st.shade_ms = sh;
     }
-    return RRS_OK;
 }
 
 int wf_resolve(SceneImpl* s, const float4* d_accum, uint32_t w, uint32_t h, uint32_t spp_total, float* out,
                bool out_is_device, cudaStream_t stream, std::string& err) {
     if (!d_accum || !out || spp_total == 0) { err = "bad resolve argument"; return RRS_ERR_INVALID; }
+    if (w == 0 || h == 0 || (unsigned long long)w * h > 0xFFFFFFFFull) { err = "bad image size"; return RRS_ERR_INVALID; }
     RRS_CUDA_CHECK(cudaSetDevice(s->device), err);
     const uint32_t npix = w * h;
     const size_t bytes = sizeof(float) * 3 * (size_t)npix;
     if (!s->census) {
-        RRS_CUDA_CHECK(cudaMalloc(&s->census, 2 * sizeof(unsigned long long)), err);
-        RRS_CUDA_CHECK(cudaMallocHost(&s->h_census, 2 * sizeof(unsigned long long)), err);
+        RRS_CUDA_CHECK(cudaMalloc(&s->census, 3 * sizeof(unsigned long long)), err);
+        RRS_CUDA_CHECK(cudaMallocHost(&s->h_census, 3 * sizeof(unsigned long long)), err);
     }
-    RRS_CUDA_CHECK(cudaMemsetAsync(s->census, 0, 2 * sizeof(unsigned long long), stream), err);
+    RRS_CUDA_CHECK(cudaMemsetAsync(s->census, 0, 3 * sizeof(unsigned long long), stream), err);
     float* d_out = out;
     bool direct = false;  // the caller's host buffer is page-locked: DMA straight into it
     if (!out_is_device) {
@@ -1226,14 +1312,16 @@ int wf_resolve(SceneImpl* s, const float4* d_accum, uint32_t w, uint32_t h, uint
         d_out = s->resolve_dev;
     }
     int grid = std::min<uint32_t>((npix + 255) / 256, (uint32_t)s->num_sms * 8u);
-    k_resolve<<<grid, 256, 0, stream>>>(d_accum, d_out, npix, 1.0f / (float)spp_total, s->census);
+    k_resolve<<<grid, 256, 0, stream>>>(d_accum, d_out, npix, 1.0f / (float)spp_total, (float)spp_total, s->census);
     if (!out_is_device)
         RRS_CUDA_CHECK(cudaMemcpyAsync(direct ? out : s->resolve_pinned, d_out, bytes, cudaMemcpyDeviceToHost, stream), err);
-    RRS_CUDA_CHECK(cudaMemcpyAsync(s->h_census, s->census, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), err);
+    RRS_CUDA_CHECK(cudaMemcpyAsync(s->h_census, s->census, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), err);
     RRS_CUDA_CHECK(cudaStreamSynchronize(stream), err);
     if (!out_is_device && !direct) std::memcpy(out, s->resolve_pinned, bytes);
+    wf_finish_stats(s);
     s->stats.nan_pixels = s->h_census[0];
     s->stats.negative_pixels = s->h_census[1];
+    s->stats.census_mismatch_pixels = s->h_census[2];
     s->stats.kernel_launches += 1;
     return RRS_OK;
 }
@@ -1241,6 +1329,7 @@ int wf_resolve(SceneImpl* s, const float4* d_accum, uint32_t w, uint32_t h, uint
 int wf_to_raw_bytes(SceneImpl* s, const float4* d_accum, uint32_t w, uint32_t h, uint32_t spp_total, double gamma,
                     uint8_t* out, bool out_is_device, cudaStream_t stream, uint64_t* census3, std::string& err) {
     if (!d_accum || !out || spp_total == 0) { err = "bad to_raw_bytes argument"; return RRS_ERR_INVALID; }
+    if (w == 0 || h == 0 || (unsigned long long)w * h > 0xFFFFFFFFull) { err = "bad image size"; return RRS_ERR_INVALID; }
     RRS_CUDA_CHECK(cudaSetDevice(s->device), err);
     const uint32_t npix = w * h;
     const size_t bytes = 3 * (size_t)npix;

@@ -59,14 +59,18 @@ struct SceneImpl {
     int num_sms = 0;
     DScene d{};
     // owned device allocations
-    DPrim* prims = nullptr;
-    DNode16* nodes = nullptr;
+    char* geom_blob = nullptr;  // [nodes | primitives] in one allocation: one L2 access-policy window covers both
+    size_t node_bytes = 0, geom_bytes = 0;
+    size_t l2_persist_bytes = 0, l2_window_max = 0;  // 0: L2 persistence unavailable or switched off
+    DPrim* prims = nullptr;     // into geom_blob
+    DNode16* nodes = nullptr;   // into geom_blob
     DMat* mats = nullptr;
     float4* emis = nullptr;
     float4* hdri = nullptr;
     RrsPrim* prims_f64 = nullptr;
     RrsNodeF64* nodes_f64 = nullptr;
     double4* sphere64 = nullptr;
+    double* tri64 = nullptr;
     uint32_t n_prims = 0, n_nodes = 0;
     uint32_t max_depth = 0;
     double tmin = 0, tmax = 0;
@@ -80,7 +84,21 @@ struct SceneImpl {
     float* resolve_pinned = nullptr;  // pinned staging for the device->host copy
     size_t resolve_bytes = 0;
     std::vector<cudaEvent_t> ev_pool;
+    cudaStream_t own_stream = nullptr;  // rrs_render_multi without caller streams
+    // rrs_render_accumulate is asynchronous: the statistics of the last render are completed by wf_finish_stats
+    bool stats_pending = false;
+    bool pending_split = false, pending_phases = false, pending_window = false;
+    std::vector<size_t> phase_ev;  // event-pool indices of the per-iteration groups (RRS_FLAG_TIME_PHASES)
 };
+
+}  // namespace rrs
+
+// the opaque handle of include/rayrs_b200.h
+struct RrsScene {
+    rrs::SceneImpl impl;
+};
+
+namespace rrs {
 
 // wavefront.cu
 int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderParams* p, float4* d_accum,
@@ -95,6 +113,7 @@ int wf_material_evaluate(SceneImpl* s, uint32_t material, const double* nv, cons
 int wf_background(SceneImpl* s, const double* dirs, size_t n, float* out, std::string& err);
 int wf_rng_uniforms(SceneImpl* s, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, float* out4,
                     std::string& err);
+void wf_finish_stats(SceneImpl* s);  // waits for the last render of this scene and completes s->stats
 void wf_free(SceneImpl* s);
 // verify_f64.cu
 int vf_intersect64(SceneImpl* s, const RrsRay* rays, size_t n, int32_t* obj_id, double* t, std::string& err);

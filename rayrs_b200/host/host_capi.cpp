@@ -49,7 +49,8 @@ const char* rrh_last_error(void) { return g_err.c_str(); }
 
 void* rrh_scene_new(const double* objs, uint64_t n_obj, const double* mats, uint64_t n_mat, const double* emis,
                     uint64_t n_emis, int heuristic, uint32_t splits, const double* hdri, uint64_t hw, uint64_t hh,
-                    double tmin, double tmax, int device, int with_f64, int upload) {
+                    double tmin, double tmax, int device, int with_f64, int upload, uint32_t scene_flags,
+                    uint32_t refill_lanes, int bvh_threads, const int* devices, int n_devices) {
     try {
         std::vector<Material> mt;
         for (uint64_t i = 0; i < n_mat; ++i) mt.push_back(material_from_row(mats + 12 * i));
@@ -80,7 +81,14 @@ void* rrh_scene_new(const double* objs, uint64_t n_obj, const double* mats, uint
         img.pixels.resize(hw * hh);
         for (uint64_t i = 0; i < hw * hh; ++i) img.pixels[i] = Vec3(hdri[3 * i], hdri[3 * i + 1], hdri[3 * i + 2]);
         BvhHeuristic h = heuristic == 0 ? BvhHeuristic::Midpoint() : BvhHeuristic::Sah(splits);
-        return new Scene(objects, tmin, tmax, h, img, device, with_f64 != 0, upload != 0);
+        SceneOptions opt;
+        opt.devices = (devices && n_devices > 0) ? std::vector<int>(devices, devices + n_devices) : std::vector<int>{device};
+        opt.with_f64 = with_f64 != 0;
+        opt.upload = upload != 0;
+        opt.flags = scene_flags;
+        opt.refill_lanes = refill_lanes;
+        opt.bvh_threads = bvh_threads;
+        return new Scene(objects, tmin, tmax, h, img, opt);
     } catch (const std::exception& e) {
         g_err = e.what();
         return nullptr;
@@ -89,6 +97,25 @@ void* rrh_scene_new(const double* objs, uint64_t n_obj, const double* mats, uint
 
 void rrh_scene_free(void* s) { delete static_cast<Scene*>(s); }
 RrsScene* rrh_scene_handle(void* s) { return static_cast<Scene*>(s)->handle(); }
+// the handle on the i-th device the scene was uploaded to (nullptr past the end)
+RrsScene* rrh_scene_handle_at(void* s, uint32_t i) {
+    const auto& h = static_cast<Scene*>(s)->handles();
+    return i < h.size() ? h[i] : nullptr;
+}
+// the scene's own communicator over its devices (rrs_comm_init_all), made on first use; nullptr on failure
+RrsComm* rrh_scene_comm(void* s) {
+    try {
+        return static_cast<Scene*>(s)->comm();
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+// [boxes, recursive build, numbering, flatten, depth, topology dump] seconds of the host BVH build
+void rrh_scene_build_timing(void* s, double* out6) {
+    const BvhBuildTiming& t = static_cast<Scene*>(s)->build_timing();
+    out6[0] = t.boxes; out6[1] = t.recursive; out6[2] = t.numbering; out6[3] = t.flatten; out6[4] = t.depth; out6[5] = t.topology;
+}
 
 // info: [n_nodes, n_prims, max_depth, dead_nodes, n_materials, topology_len, n_boxes]
 void rrh_scene_info(void* s, uint64_t* info7, double* build_seconds) {

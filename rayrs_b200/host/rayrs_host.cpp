@@ -547,16 +547,15 @@ void dump_topology(const std::vector<BNode>& bn, int32_t b, const std::vector<ui
 
 }  // namespace
 
-FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, uint32_t bfs_nodes, int threads) {
+FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, uint32_t bfs_nodes, int threads,
+                   BvhBuildTiming* timing) {
     if (objects.empty()) throw Panic("Having a BVH for 0 objects does not make sense");
     if (heuristic.kind == BvhHeuristic::kSah && heuristic.splits < 2) throw Panic("Sah needs at least 2 splits");
     const size_t n = objects.size();
-    // RRS_BVH_TIMING=1: where the build time goes, on stderr
-    const bool timing = std::getenv("RRS_BVH_TIMING") != nullptr;
     auto tick = std::chrono::steady_clock::now();
-    auto lap = [&](const char* what) {
+    auto lap = [&](double BvhBuildTiming::*field) {
         auto now = std::chrono::steady_clock::now();
-        if (timing) std::fprintf(stderr, "[bvh] %-22s %.3f s\n", what, std::chrono::duration<double>(now - tick).count());
+        if (timing) timing->*field = std::chrono::duration<double>(now - tick).count();
         tick = now;
     };
     std::vector<AxisAlignedBoundingBox> boxes(n);
@@ -565,19 +564,17 @@ FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, u
         boxes[i] = objects[i].bbox();
         centers[i] = boxes[i].center();  // BvhData::new bvh.rs:87-98
     }
-    lap("boxes + centres");
+    lap(&BvhBuildTiming::boxes);
     FlatBvh out;
     out.prim_order.resize(n);
     for (size_t i = 0; i < n; ++i) out.prim_order[i] = (uint32_t)i;
     Builder b(boxes, centers, out.prim_order, heuristic);
-    if (threads <= 0)
-        if (const char* e = std::getenv("RRS_BVH_THREADS")) threads = std::atoi(e);
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
     b.spare_threads = threads - 1;
     b.nodes.reserve(n);
     const int32_t root = b.build(0, n, 0);
     const std::vector<BNode>& bn = b.nodes;
-    lap("recursive build");
+    lap(&BvhBuildTiming::recursive);
 
     // ---- flat numbering: virtual root = 0, then binary Nodes breadth-first for the first
     // `bfs_nodes` (hot top of the tree contiguous), depth-first below (subtrees contiguous)
@@ -611,7 +608,7 @@ FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, u
             }
         }
     }
-    lap("flat numbering");
+    lap(&BvhBuildTiming::numbering);
     out.nodes.assign(flat_to_build.size(), RrsNode{});
     out.nodes_f64.assign(flat_to_build.size(), RrsNodeF64{});
     Flattener fl{bn, out};
@@ -633,7 +630,7 @@ FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, u
         fl.attach((uint32_t)f, 0, nd.child[0], nd.box, flat_index);
         fl.attach((uint32_t)f, 1, nd.child[1], nd.box, flat_index);
     }
-    lap("flatten");
+    lap(&BvhBuildTiming::flatten);
     // depth (stack bound): longest chain of flat nodes
     {
         std::vector<uint32_t> depth(out.nodes.size(), 0);
@@ -654,9 +651,9 @@ FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, u
         }
         out.max_depth = mx;
     }
-    lap("depth");
+    lap(&BvhBuildTiming::depth);
     dump_topology(bn, root, out.prim_order, out);
-    lap("topology dump");
+    lap(&BvhBuildTiming::topology);
     return out;
 }
 
@@ -702,10 +699,25 @@ RrsCamera Camera::derived() const {
 // ---------------------------------------------------------------------------------------
 Scene::Scene(const std::vector<Object>& objects, double z_near, double z_far, BvhHeuristic heuristic, const Image& hdri,
              int device, bool with_f64, bool upload) {
+    SceneOptions opt;
+    opt.devices = {device};
+    opt.with_f64 = with_f64;
+    opt.upload = upload;
+    init(objects, z_near, z_far, heuristic, hdri, opt);
+}
+
+Scene::Scene(const std::vector<Object>& objects, double z_near, double z_far, BvhHeuristic heuristic, const Image& hdri,
+             const SceneOptions& opt) {
+    init(objects, z_near, z_far, heuristic, hdri, opt);
+}
+
+void Scene::init(const std::vector<Object>& objects, double z_near, double z_far, BvhHeuristic heuristic, const Image& hdri,
+                 const SceneOptions& opt) {
     require(z_near >= 0., "Scene::new: z_near must be >= 0");
     require(z_far > z_near, "Scene::new: z_far must be > z_near");
+    require(!opt.devices.empty(), "Scene::new: no device");
     auto t0 = std::chrono::steady_clock::now();
-    bvh_ = Bvh::build(heuristic, objects);
+    bvh_ = Bvh::build(heuristic, objects, 1023, opt.bvh_threads, &timing_);
     build_seconds_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
     // materials / emissions: objects carry them by value (mat.clone() in lib.rs:407-415);
@@ -741,7 +753,7 @@ Scene::Scene(const std::vector<Object>& objects, double z_near, double z_far, Bv
         p.emission = emi_index(o.emission);
         std::memcpy(p.v, o.geom.v, sizeof(p.v));
     }
-    if (!upload) return;
+    if (!opt.upload) return;
     std::vector<float> rgb(hdri.pixels.size() * 3);
     for (size_t i = 0; i < hdri.pixels.size(); ++i) {
         rgb[3 * i] = (float)hdri.pixels[i].x;
@@ -754,7 +766,7 @@ Scene::Scene(const std::vector<Object>& objects, double z_near, double z_far, Bv
     d.prims = prims_.data();
     d.n_nodes = (uint32_t)bvh_.nodes.size();
     d.nodes = bvh_.nodes.data();
-    d.nodes_f64 = with_f64 ? bvh_.nodes_f64.data() : nullptr;
+    d.nodes_f64 = opt.with_f64 ? bvh_.nodes_f64.data() : nullptr;
     d.max_depth = bvh_.max_depth;
     d.n_materials = (uint32_t)materials_.size();
     d.materials = materials_.data();
@@ -765,12 +777,29 @@ Scene::Scene(const std::vector<Object>& objects, double z_near, double z_far, Bv
     d.hdri_rgb = rgb.data();
     d.t_min = z_near;
     d.t_max = z_far;
-    int rc = rrs_scene_create(&d, device, &handle_);
-    if (rc != RRS_OK) throw Panic(std::string("rrs_scene_create failed: ") + rrs_last_error());
+    d.flags = opt.flags;
+    d.refill_lanes = opt.refill_lanes;
+    devices_ = opt.devices;
+    handles_.assign(devices_.size(), nullptr);
+    int rc = rrs_scene_create_multi(&d, devices_.data(), (int)devices_.size(), handles_.data());
+    if (rc != RRS_OK) {
+        handles_.clear();
+        throw Panic(std::string("rrs_scene_create failed: ") + rrs_last_error());
+    }
 }
 
 Scene::~Scene() {
-    if (handle_) rrs_scene_destroy(handle_);
+    if (comm_) rrs_comm_destroy(comm_);
+    for (RrsScene* h : handles_)
+        if (h) rrs_scene_destroy(h);
+}
+
+RrsComm* Scene::comm() const {
+    if (!comm_) {
+        int rc = rrs_comm_init_all(devices_.data(), (int)devices_.size(), &comm_);
+        if (rc != RRS_OK) throw Panic(std::string("rrs_comm_init_all failed: ") + rrs_last_error());
+    }
+    return comm_;
 }
 
 void render_gpu_into(const Camera& c, const Scene& s, uint32_t spp, uint32_t max_bounces, const RenderOptions& opt,
@@ -787,6 +816,12 @@ void render_gpu_into(const Camera& c, const Scene& s, uint32_t spp, uint32_t max
     p.seed = opt.seed;
     p.queue_capacity = opt.queue_capacity;
     p.flags = opt.flags;
+    if (s.handles().size() > 1) {
+        // the scene lives on several GPUs: sample split + one reduce, still one call (rrs_render_multi)
+        int rc = rrs_render_multi(s.handles().data(), (int)s.handles().size(), s.comm(), &cam, &p, out_rgb, 0, nullptr);
+        if (rc != RRS_OK) throw Panic(std::string("rrs_render_multi failed: ") + rrs_last_error());
+        return;
+    }
     int rc = rrs_render(s.handle(), &cam, &p, out_rgb);
     if (rc != RRS_OK) throw Panic(std::string("rrs_render failed: ") + rrs_last_error());
 }

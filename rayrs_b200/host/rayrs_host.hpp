@@ -135,10 +135,16 @@ struct FlatBvh {
     std::vector<double> boxes;
 };
 
+// where the build time goes (seconds), filled when a pointer is handed to Bvh::build
+struct BvhBuildTiming {
+    double boxes = 0, recursive = 0, numbering = 0, flatten = 0, depth = 0, topology = 0;
+};
+
 struct Bvh {
-    // Bvh::build bvh.rs:199-210.  threads: worker threads for independent subtrees.
+    // Bvh::build bvh.rs:199-210.  threads: worker threads for independent subtrees and chunked sorts
+    // (0 = one per hardware thread).
     static FlatBvh build(BvhHeuristic heuristic, const std::vector<Object>& objects, uint32_t bfs_nodes = 1023,
-                         int threads = 0);
+                         int threads = 0, BvhBuildTiming* timing = nullptr);
 };
 
 struct Image {
@@ -161,16 +167,32 @@ private:
     uint32_t ppc_;
 };
 
+// Device side of Scene::new: which GPUs hold the scene, and the library's measurement switches.
+struct SceneOptions {
+    std::vector<int> devices{0};  // the BVH is built and flattened ONCE and uploaded to each of them
+    bool with_f64 = true;         // also upload the f64 twins (rrs_intersect precision 64)
+    bool upload = true;           // false: host half only (no GPU needed)
+    uint32_t flags = 0;           // RRS_SCENE_*
+    uint32_t refill_lanes = 0;    // 0 = library default
+    int bvh_threads = 0;          // 0 = one per hardware thread
+};
+
 class Scene {
 public:
     // Scene::new lib.rs:227-245 (+ upload to the GPU `device`)
     Scene(const std::vector<Object>& objects, double z_near, double z_far, BvhHeuristic heuristic, const Image& hdri,
           int device = 0, bool with_f64 = true, bool upload = true);
+    Scene(const std::vector<Object>& objects, double z_near, double z_far, BvhHeuristic heuristic, const Image& hdri,
+          const SceneOptions& opt);
     ~Scene();
     Scene(const Scene&) = delete;
     Scene& operator=(const Scene&) = delete;
 
-    RrsScene* handle() const { return handle_; }
+    RrsScene* handle() const { return handles_.empty() ? nullptr : handles_[0]; }
+    const std::vector<RrsScene*>& handles() const { return handles_; }
+    const std::vector<int>& devices() const { return devices_; }
+    RrsComm* comm() const;  // made on first use (rrs_comm_init_all over devices())
+    const BvhBuildTiming& build_timing() const { return timing_; }
     const FlatBvh& bvh() const { return bvh_; }
     const std::vector<RrsPrim>& prims() const { return prims_; }
     const std::vector<RrsMaterial>& materials() const { return materials_; }
@@ -181,8 +203,13 @@ private:
     std::vector<RrsPrim> prims_;
     std::vector<RrsMaterial> materials_;
     std::vector<RrsEmission> emissions_;
-    RrsScene* handle_ = nullptr;
+    std::vector<RrsScene*> handles_;
+    std::vector<int> devices_;
+    mutable RrsComm* comm_ = nullptr;
+    BvhBuildTiming timing_;
     double build_seconds_ = 0;
+    void init(const std::vector<Object>& objects, double z_near, double z_far, BvhHeuristic heuristic, const Image& hdri,
+              const SceneOptions& opt);
 };
 
 struct RenderOptions {
@@ -193,7 +220,8 @@ struct RenderOptions {
     uint32_t flags = 0;
 };
 
-// Drop-in for the tile loop of rayrs/src/main.rs:57-101.
+// Drop-in for the tile loop of rayrs/src/main.rs:57-101.  A scene that lives on several GPUs (SceneOptions::devices)
+// is rendered by all of them: samples split, one NCCL reduce (rrs_render_multi).
 Image render_gpu(const Camera& c, const Scene& s, uint32_t spp, uint32_t max_bounces, const RenderOptions& opt = RenderOptions());
 // same, into a caller-provided float buffer (height*width*3)
 void render_gpu_into(const Camera& c, const Scene& s, uint32_t spp, uint32_t max_bounces, const RenderOptions& opt,

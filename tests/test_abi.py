@@ -38,7 +38,9 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_ffi.RrsPrim) == 88
     assert C.sizeof(_ffi.RrsRay) == 48
     assert C.sizeof(_ffi.RrsMaterial) == 72
-    assert C.sizeof(_ffi.RrsStats) == 104
+    assert C.sizeof(_ffi.RrsStats) == 112
+    assert C.sizeof(_ffi.RrsUniqueId) == 128
+    assert C.sizeof(_ffi.RrsSceneDesc) == 112
 
 
 def test_abi_version_and_error_channel():
@@ -51,6 +53,110 @@ def test_abi_version_and_error_channel():
     desc.abi_version = 99
     assert lib.rrs_scene_create(C.byref(desc), 0, C.byref(out)) == _ffi.RRS_ERR_INVALID
     assert b"ABI" in lib.rrs_last_error()
+
+
+def _tiny_desc(keep):
+    """A valid 3-node description (virtual root -> inner node -> two leaf runs) the tests below damage."""
+    prims = (_ffi.RrsPrim * 2)()
+    for i, x in enumerate((-2.0, 2.0)):
+        prims[i].type, prims[i].obj_id, prims[i].material, prims[i].emission = 0, i, 0, -1
+        prims[i].v[0], prims[i].v[1] = 1.0, x
+    nodes = (_ffi.RrsNode * 3)()
+    inf = float("inf")
+    for nd in nodes:
+        nd.lo0[:] = nd.lo1[:] = [inf] * 3
+        nd.hi0[:] = nd.hi1[:] = [-inf] * 3
+        nd.ref0 = nd.ref1 = _ffi.RRS_REF_EMPTY
+    nodes[0].ref0 = 1
+    nodes[0].lo0[:], nodes[0].hi0[:] = [-3, -1, -1], [3, 1, 1]
+    nodes[1].ref0, nodes[1].ref1 = _ffi.RRS_REF_LEAF | 0, _ffi.RRS_REF_LEAF | 1
+    nodes[1].lo0[:], nodes[1].hi0[:] = [-3, -1, -1], [-1, 1, 1]
+    nodes[1].lo1[:], nodes[1].hi1[:] = [1, -1, -1], [3, 1, 1]
+    mats = (_ffi.RrsMaterial * 1)()
+    mats[0].tag = 0
+    mats[0].color[:] = [0.5, 0.5, 0.5]
+    hdri = (C.c_float * 12)(*([1.0] * 12))
+    d = _ffi.RrsSceneDesc()
+    d.abi_version = _ffi.RRS_ABI_VERSION
+    d.n_prims, d.prims = 2, prims
+    d.n_nodes, d.nodes = 3, nodes
+    d.max_depth = 2
+    d.n_materials, d.materials = 1, mats
+    d.hdri_width, d.hdri_height, d.hdri_rgb = 2, 2, hdri
+    d.t_min, d.t_max = 1e-6, 1e6
+    keep.extend([prims, nodes, mats, hdri])
+    return d, nodes
+
+
+def test_malformed_trees_are_rejected_not_trusted():
+    """The traversal stack is sized from max_depth and release kernels do not bounds-check it: a cycle, a node
+    reached twice, an understated depth or a wrapping max_depth must come back as an error (validated on the host,
+    before any device is touched, so this runs on the CPU box too)."""
+    lib = _ffi.cuda_lib()
+    out = C.c_void_p()
+    keep = []
+
+    def status(d):
+        rc = lib.rrs_scene_create(C.byref(d), 0, C.byref(out))
+        if rc == _ffi.RRS_OK:  # a GPU box accepts the valid description
+            lib.rrs_scene_destroy(out)
+        return rc, lib.rrs_last_error().decode()
+
+    d, nodes = _tiny_desc(keep)
+    rc, msg = status(d)
+    assert rc in (_ffi.RRS_OK, _ffi.RRS_ERR_NO_DEVICE), msg  # the undamaged description passes validation
+    d, nodes = _tiny_desc(keep)
+    nodes[1].ref1 = 1  # a node that is its own child: the persistent kernel would never finish
+    rc, msg = status(d)
+    assert rc == _ffi.RRS_ERR_INVALID and "twice" in msg
+    d, nodes = _tiny_desc(keep)
+    nodes[1].ref0, nodes[1].ref1 = 2, 2  # a shared subtree (DAG)
+    nodes[2].ref0 = _ffi.RRS_REF_LEAF | 0
+    rc, msg = status(d)
+    assert rc == _ffi.RRS_ERR_INVALID and "twice" in msg
+    d, nodes = _tiny_desc(keep)
+    d.max_depth = 1  # understated: the real chain is 2 nodes long
+    rc, msg = status(d)
+    assert rc == _ffi.RRS_ERR_INVALID and "deeper" in msg
+    for wrap in (0xFFFFFFFD, 0xFFFFFFFF, 118):
+        d, nodes = _tiny_desc(keep)
+        d.max_depth = wrap  # + 3 must not wrap around the 120-entry limit
+        rc, msg = status(d)
+        assert rc == _ffi.RRS_ERR_TOO_DEEP, (wrap, msg)
+    d, nodes = _tiny_desc(keep)
+    d.n_emissions = 1  # emissions == NULL
+    rc, msg = status(d)
+    assert rc == _ffi.RRS_ERR_INVALID and "emissions" in msg
+    d, nodes = _tiny_desc(keep)
+    d.refill_lanes = 33
+    rc, msg = status(d)
+    assert rc == _ffi.RRS_ERR_INVALID
+
+
+def test_sample_range_is_a_partition_and_matches_the_python_mirror():
+    from rayrs_b200 import api
+    from rayrs_b200.multigpu import sample_range
+    for world in (1, 2, 3, 4, 8):
+        for spp in (0, 1, 5, 8, 4096, 4097):
+            got = [api.sample_range(r, world, spp) for r in range(world)]
+            assert got == [sample_range(r, world, spp) for r in range(world)]
+            assert sum(c for _, c in got) == spp
+            pos = 0
+            for first, count in got:
+                assert first == pos
+                pos += count
+    with pytest.raises(_ffi.RayrsError):
+        api.sample_range(2, 2, 8)
+
+
+def test_single_device_communicator_needs_no_nccl():
+    lib = _ffi.cuda_lib()
+    comm = C.c_void_p()
+    devs = (C.c_int * 1)(0)
+    assert lib.rrs_comm_init_all(devs, 1, C.byref(comm)) == _ffi.RRS_OK and comm.value
+    lib.rrs_comm_destroy(comm)
+    two = (C.c_int * 2)(0, 0)
+    assert lib.rrs_comm_init_all(two, 2, C.byref(comm)) == _ffi.RRS_ERR_INVALID  # the same device twice
 
 
 def test_no_cpu_fallback_without_a_device():

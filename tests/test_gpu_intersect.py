@@ -4,15 +4,15 @@ relative).  GPU, through the C ABI (rrs_intersect).
  * precision=64 (literal fp64 traversal of the flattened tree): IDs equal on EVERY ray, t to 1e-12.
  * precision=32 (production traversal): IDs equal on every ray whose answer is stable under a
    2e-6 perturbation in the oracle (the others sit on a primitive edge / silhouette / t-tie where
-   fp32 may legitimately decide differently; their count is reported and bounded), t to 1e-5 —
-   except where the oracle's own t moves by more than 1e-4 under that perturbation (grazing hits):
-   there the bound is three fp32 ulps of backward error (0.1 x that movement).
+   fp32 may legitimately decide differently; their count is reported and bounded), t to a FLAT 1e-5 on
+   every stable hit: the fp32 traversal picks the hit, the accepted triangle hit's distance is re-evaluated in
+   f64 (triangle_t64, intersect.cuh), so grazing hits — where t is ill-conditioned — are inside the bound too.
 """
 import numpy as np
 import pytest
 
 import oracle
-from rayrs_b200 import scenes
+from rayrs_b200 import _ffi, scenes
 from rayrs_b200.api import BvhHeuristic
 
 pytestmark = pytest.mark.gpu
@@ -53,16 +53,14 @@ SCENES = {
 
 
 # sphere scenes take the brute-force small-scene path by default; "+bvh" runs the same scene through the
-# BVH traversal (RRS_NO_BRUTE is read at scene creation), which is what a ninth primitive would switch on
+# BVH traversal (RrsSceneDesc.flags = RRS_SCENE_NO_BRUTE), which is what a ninth primitive would switch on
 SCENES.update({k + "+bvh": v for k, v in list(SCENES.items()) if k in ("diffuse_single_sphere", "spheres_metallic", "material_test")})
 
 
 @pytest.mark.parametrize("name", sorted(SCENES))
-def test_ids_and_t_against_oracle(name, hdri_small, monkeypatch):
+def test_ids_and_t_against_oracle(name, hdri_small):
     spec = SCENES[name]()
-    if name.endswith("+bvh"):
-        monkeypatch.setenv("RRS_NO_BRUTE", "1")
-    sc = spec.scene(hdri_small)
+    sc = spec.scene(hdri_small, scene_flags=_ffi.RRS_SCENE_NO_BRUTE if name.endswith("+bvh") else 0)
     osc = oracle.OracleScene(spec.tables(), hdri_small.pixels, heuristic=(spec.heuristic.kind, spec.heuristic.splits), build_mode=1)
     rays = fixed_ray_set(spec, osc, N_RAYS)
     oid, ot = osc.intersect(rays)
@@ -85,18 +83,16 @@ def test_ids_and_t_against_oracle(name, hdri_small, monkeypatch):
     assert np.array_equal(gid[stable], oid[stable]), f"{int((gid[stable] != oid[stable]).sum())} stable rays differ"
     ok = stable & hit
     rel = np.abs(gt[ok] - ot[ok]) / ot[ok]
-    # north_star: t within 1e-5 relative.  tchange is how far the ORACLE's t moves when the ray is perturbed by 2e-6
-    # (its conditioning): beyond 1e-4 (grazing incidence on a triangle, |cos| ~ 0.01; ~2 % of the rays on the meshes)
-    # the bound is the movement under a 2e-7 perturbation instead, i.e. three fp32 ulps of backward error.
-    bound = np.maximum(1e-5, 0.1 * tchange[ok])
-    worst = int(np.argmax(rel / bound))
-    assert np.all(rel <= bound), (rel[worst], tchange[ok][worst])
-    well = tchange[ok] <= 1e-4
-    assert rel[well].max() <= 1e-5
+    # north_star: t within 1e-5 relative, flat, on every stable hit.  tchange (how far the ORACLE's t moves when the
+    # ray is perturbed by 2e-6, i.e. its conditioning) is only reported: the ill-conditioned grazing hits are held to
+    # the same bound.
+    worst = int(np.argmax(rel))
+    assert rel.max() <= 1e-5, (rel[worst], tchange[ok][worst])
+    ill = tchange[ok] > 1e-4
     print(f"[{name}] fp32: ids equal on all {int(stable.sum())} stable rays ({dropped} unstable dropped, "
-          f"{mism_all} of those differ), max rel t err {rel[well].max():.2e} on the {int(well.sum())} well-conditioned hits, "
-          f"{rel.max():.2e} overall ({int((~well).sum())} hits with t moving > 1e-4 under a 2e-6 perturbation, "
-          f"{int((rel > 1e-5).sum())} of them beyond 1e-5)")
+          f"{mism_all} of those differ), max rel t err {rel.max():.2e} over {int(ok.sum())} stable hits "
+          f"({int(ill.sum())} of them ill-conditioned: t moves > 1e-4 under a 2e-6 perturbation; max there "
+          f"{rel[ill].max() if ill.any() else 0.0:.2e})")
     sc.close()
 
 
@@ -120,7 +116,7 @@ def test_fp32_matches_fp64_at_full_size_1m_triangles(hdri_small):
     hit = agree & (did >= 0)
     assert hit.mean() > 0.3
     rel = np.abs(gt[hit] - dt[hit]) / dt[hit]
-    assert np.quantile(rel, 0.9999) <= 1e-5
+    assert rel.max() <= 1e-5, rel.max()
     # where they disagree it must be the neighbouring triangle at (almost) the same distance; a
     # different SURFACE (a ray leaking through a crack between triangles, or a silhouette graze)
     # must be vanishingly rare: the watertight edge test leaves only silhouette grazes
@@ -130,7 +126,7 @@ def test_fp32_matches_fp64_at_full_size_1m_triangles(hdri_small):
     far[both] = np.abs(gt[both] - dt[both]) / dt[both] > 1e-3
     far |= dis & ((gid < 0) != (did < 0))
     print(f"[torus 1M] fp32 == fp64 ids on {agree.mean() * 100:.4f}% of {n} rays; {int(dis.sum())} differ, of which "
-          f"{int(far.sum())} land on a different surface; p99.99 rel t err {np.quantile(rel, 0.9999):.2e}")
+          f"{int(far.sum())} land on a different surface; max rel t err {rel.max():.2e}")
     assert far.sum() <= 3e-5 * n, int(far.sum())
     # oracle spot check of the fp64 kernel on a subset (the oracle walks the pointer tree unpruned)
     osc = oracle.OracleScene(spec.tables(), hdri_small.pixels, build_mode=1)
@@ -139,6 +135,55 @@ def test_fp32_matches_fp64_at_full_size_1m_triangles(hdri_small):
     assert np.array_equal(oid, did[: 1 << 14])
     h = oid >= 0
     assert np.max(np.abs(ot[h] - dt[: 1 << 14][h]) / ot[h]) <= 1e-12
+    sc.close()
+
+
+def test_fp32_matches_fp64_at_full_size_config5(hdri_small):
+    """BASELINE config 5 scene at full size (4.0M triangles + 7 spheres + floor, SAH-1000) with the f64 twins
+    uploaded: the production traversal against the fp64 literal traversal of the same flattened tree on 2^20 rays
+    (half camera rays, half random rays through the scene), t flat 1e-5 where both pick the same primitive; plus an
+    oracle spot check of the fp64 kernel."""
+    spec = scenes.mixed_scene(2000, 1000, 3840, 2160)
+    sc = spec.scene(hdri_small, with_f64=True)
+    assert sc.n_prims == 4_000_008
+    cam = spec.camera()
+    rng = np.random.default_rng(13)
+    n = 1 << 20
+    h = n // 2
+    prim = oracle.primary_rays(cam.derived17(), 3840, 2160, rng.integers(0, 2160, h), rng.integers(0, 3840, h),
+                               rng.integers(0, 4096, h))
+    org = np.array([0.0, 1.7, -2.0]) + rng.uniform(-1.0, 1.0, (n - h, 3)) * np.array([8.0, 1.6, 4.0])
+    d = rng.normal(size=(n - h, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([prim, np.concatenate([org, d], axis=1)]).astype(np.float32).astype(np.float64)
+    gid, gt = sc.intersect(rays, 32)
+    did, dt = sc.intersect(rays, 64)
+    agree = gid == did
+    assert agree.mean() > 0.999
+    dis = ~agree
+    both = dis & (gid >= 0) & (did >= 0)
+    far = np.zeros(n, dtype=bool)
+    far[both] = np.abs(gt[both] - dt[both]) / dt[both] > 1e-3
+    far |= dis & ((gid < 0) != (did < 0))
+    assert far.sum() <= 3e-5 * n, int(far.sum())
+    # the oracle (pointer tree of the restatement, unpruned) on the SAME rays: IDs of the fp64 kernel everywhere, and
+    # the north-star bounds of the fp32 kernel on every ray whose answer is stable under a 2e-6 perturbation
+    osc = oracle.OracleScene(spec.tables(), hdri_small.pixels, build_mode=1)
+    oid, ot = osc.intersect(rays)
+    assert np.array_equal(oid, did)
+    oh = oid >= 0
+    assert oh.mean() > 0.3
+    assert np.max(np.abs(ot[oh] - dt[oh]) / ot[oh]) <= 1e-12
+    stable, tchange = osc.intersect_sensitivity(rays)
+    assert (~stable).sum() < 0.05 * n
+    assert np.array_equal(gid[stable], oid[stable]), f"{int((gid[stable] != oid[stable]).sum())} stable rays differ"
+    ok = stable & oh
+    rel = np.abs(gt[ok] - ot[ok]) / ot[ok]
+    assert rel.max() <= 1e-5, rel.max()
+    print(f"[config 5, {sc.n_prims} primitives] fp64 kernel == oracle on all {n} rays; fp32 ids equal on all {int(stable.sum())} stable "
+          f"rays ({int((~stable).sum())} unstable dropped, {int(dis.sum())} of them differ from fp64, {int(far.sum())} on a different "
+          f"surface); max rel t err {rel.max():.2e} over {int(ok.sum())} stable hits "
+          f"({int((tchange[ok] > 1e-4).sum())} of them ill-conditioned)")
     sc.close()
 
 
@@ -175,7 +220,7 @@ def test_edge_cases(hdri_small):
     sc.close()
 
 
-def test_sphere_group_box_never_changes_an_answer(hdri_small, monkeypatch):
+def test_sphere_group_box_never_changes_an_answer(hdri_small):
     """The brute-force path tests one padded box around its sphere group first (scene creation, api.cu).  It must
     be purely an accelerator: with and without it every ID and every t is bit-identical — including rays that
     graze the box, lie in its face planes, start inside it or on a sphere, and axis-parallel rays."""
@@ -197,9 +242,7 @@ def test_sphere_group_box_never_changes_an_answer(hdri_small, monkeypatch):
                             rng.normal(size=(4096, 2)) * [1.0, 1e-3], rng.normal(size=(4096, 1))], axis=1)
     rays = np.concatenate([rays, np.array(special), graze]).astype(np.float32).astype(np.float64)
     sc_on = spec.scene(hdri_small)
-    monkeypatch.setenv("RRS_NO_BRUTE_BOX", "1")
-    sc_off = spec.scene(hdri_small)
-    monkeypatch.delenv("RRS_NO_BRUTE_BOX")
+    sc_off = spec.scene(hdri_small, scene_flags=_ffi.RRS_SCENE_NO_BRUTE_BOX)
     id_on, t_on = sc_on.intersect(rays, 32)
     id_off, t_off = sc_off.intersect(rays, 32)
     assert np.array_equal(id_on, id_off)

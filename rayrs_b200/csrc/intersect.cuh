@@ -228,6 +228,13 @@ struct TravCounters {
 // of this thread lives at base + e * stride.  (As a generic pointer derived from threadIdx the compiler re-formed
 // the address — S2R tid, S2UR cta-in-cluster, 4 more — inside every divergent push and pop: 4 % of the warp
 // instructions of the traversal, profiles/r01n_c4.)
+// Per-thread traversal stack in shared memory, addressed by a 32-bit shared address held in a register: entry e
+// of this thread lives at base + e * stride.  (As a generic pointer derived from threadIdx the compiler re-formed
+// the address — S2R tid, S2UR cta-in-cluster, 4 more — inside every divergent push and pop: 4 % of the warp
+// instructions of the traversal, profiles/r01n_c4.)
+// Measured alternatives (round 2, profiles/ab_logs/ab_r02c_stack.log, ab_r02f_hybrid.log): the whole stack in local
+// memory (no shared memory, the SM's 256 KB almost all L1) -1.5 %; 15 entries in shared memory + local overflow
+// -3.4 % / -1.6 % (the bound check in every push / pop costs more than the extra 35 KB of L1 brings).
 struct SStack {
     uint32_t base;    // shared-window address of entry 0
     uint32_t stride;  // bytes between entries: 4 * threads per block
@@ -246,11 +253,19 @@ struct SStack {
     }
 };
 
+// The ray as the traversal keeps it in registers.
+// Measured alternatives (round 2): (1) slab distances as one FMA per plane, t = plane * (1/d) - o * (1/d), with a
+// PER-AXIS slack 2^-21 |o/d| folded into the near / far constants (round 1 had lost 36 % with one slack for all axes):
+// 12 instructions fewer per node step, the same 28.64 node visits per ray — and 5 % SLOWER: the six extra per-ray
+// constants doubled the kernel's spill traffic (local loads 326 M -> 635 M per launch), the L1 hit rate of the node
+// fetches fell from 45.9 % to 43.2 % and issue-active from 70 % to 63 % (profiles/ab_logs/ncu_light_r02e_*.csv).
+// (2) origin / direction / origin word parked in shared memory behind the stack and fetched back per leaf visit
+// (9 registers fewer in the node loop): -15 % (ab_r02b_fma.log, ab_r02f_hybrid.log).  The traversal is bound by the
+// latency of its scattered node fetches at 8 warps per scheduler, not by its instruction count.
 struct RayK {
     float3 o, d, idir;
     uint32_t selx, sely, selz;  // PRMT selectors: (near, far) = (lo, hi) or (hi, lo) by the sign of 1/d
-    uint32_t origin_prim;  // primitive the ray was spawned on, RRS_NO_PRIM for camera rays
-    const double* org64;   // f64 origin carried with the ray (transmissive spheres), or nullptr
+    uint32_t origin_word;       // RRS_NO_PRIM, or primitive index | RRS_ORG64 (the ray carries an f64 origin)
 };
 struct Trav {
     uint32_t cur;   // node index, leaf run reference, or TRAV_DONE
@@ -259,15 +274,19 @@ struct Trav {
     uint32_t best;
 };
 
-template <bool SPH64>
-__device__ __forceinline__ void trav_begin(const DScene& sc, float3 o, float3 d, uint32_t origin_word,
-                                           const double* __restrict__ org64, const SStack& stack, RayK& r, Trav& tv) {
-    // origin word: RRS_NO_PRIM, or primitive index | RRS_ORG64 (the ray carries its f64 origin in org64)
+// prmt.b32 without the selector mask __byte_perm adds (3 LOP3 per node step)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(a), "r"(sel));
+    return r;
+}
+
+__device__ __forceinline__ void trav_begin(const DScene& sc, float3 o, float3 d, uint32_t origin_word, const SStack& stack,
+                                           RayK& r, Trav& tv) {
     r.o = o;
     r.d = d;
     r.idir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    r.origin_prim = origin_word == RRS_NO_PRIM ? RRS_NO_PRIM : (origin_word & RRS_PRIM_MASK);
-    r.org64 = (SPH64 && origin_word != RRS_NO_PRIM && (origin_word & RRS_ORG64)) ? org64 : nullptr;
+    r.origin_word = origin_word;
     r.selx = r.idir.x < 0.f ? 0x1032u : 0x3210u;
     r.sely = r.idir.y < 0.f ? 0x1032u : 0x3210u;
     r.selz = r.idir.z < 0.f ? 0x1032u : 0x3210u;
@@ -289,29 +308,30 @@ __device__ __forceinline__ void trav_node_step(const DScene& sc, const RayK& r, 
     RRS_CHECK(tv.cur < sc.n_nodes);
     ldg256(sc.nodes + tv.cur, w);
     if (COUNT) cnt.nodes++;
-    const float3 o = r.o, idir = r.idir;
+    const float3 idir = r.idir;
     const uint32_t ref0 = w[6], ref1 = w[7];
     // Slab test as geometry.rs:458-513 writes it: the near/far plane is chosen by the sign of
     // 1/d (not by min/max of the two products), and max/min drop NaNs — so a ray lying in a
     // face plane of the box (0 * inf = NaN) is simply not constrained by that axis.
-    const float2 ax = __half22float2(u32_as_half2(__byte_perm(w[0], 0u, r.selx)));  // (near, far) planes
-    const float2 ay = __half22float2(u32_as_half2(__byte_perm(w[1], 0u, r.sely)));
-    const float2 az = __half22float2(u32_as_half2(__byte_perm(w[2], 0u, r.selz)));
-    const float2 bx = __half22float2(u32_as_half2(__byte_perm(w[3], 0u, r.selx)));
-    const float2 by = __half22float2(u32_as_half2(__byte_perm(w[4], 0u, r.sely)));
-    const float2 bz = __half22float2(u32_as_half2(__byte_perm(w[5], 0u, r.selz)));
+    const float2 ax = __half22float2(u32_as_half2(prmt(w[0], r.selx)));  // (near, far) planes
+    const float2 ay = __half22float2(u32_as_half2(prmt(w[1], r.sely)));
+    const float2 az = __half22float2(u32_as_half2(prmt(w[2], r.selz)));
+    const float2 bx = __half22float2(u32_as_half2(prmt(w[3], r.selx)));
+    const float2 by = __half22float2(u32_as_half2(prmt(w[4], r.sely)));
+    const float2 bz = __half22float2(u32_as_half2(prmt(w[5], r.selz)));
+    const float3 o = r.o;
     float ax0 = (ax.x - o.x) * idir.x, ax1 = (ax.y - o.x) * idir.x;
     float ay0 = (ay.x - o.y) * idir.y, ay1 = (ay.y - o.y) * idir.y;
     float az0 = (az.x - o.z) * idir.z, az1 = (az.y - o.z) * idir.z;
-    float n0 = fmaxf(fmaxf(ax0, ay0), fmaxf(az0, sc.tmin));
-    float f0 = fminf(fminf(ax1, ay1), fminf(az1, tv.tbest));
     float bx0 = (bx.x - o.x) * idir.x, bx1 = (bx.y - o.x) * idir.x;
     float by0 = (by.x - o.y) * idir.y, by1 = (by.y - o.y) * idir.y;
     float bz0 = (bz.x - o.z) * idir.z, bz1 = (bz.y - o.z) * idir.z;
+    float n0 = fmaxf(fmaxf(ax0, ay0), fmaxf(az0, sc.tmin));
+    float f0 = fminf(fminf(ax1, ay1), fminf(az1, tv.tbest));
     float n1 = fmaxf(fmaxf(bx0, by0), fmaxf(bz0, sc.tmin));
     float f1 = fminf(fminf(bx1, by1), fminf(bz1, tv.tbest));
-    // conservative acceptance: fp32 slab arithmetic is good to a few ulp, boxes are rounded
-    // outward, so anything the f64 test accepts is accepted here.  An RRS_REF_EMPTY child carries
+    // conservative acceptance: fp32 slab arithmetic is good to a few ulp, boxes are
+    // rounded outward, so anything the f64 test accepts is accepted here.  An RRS_REF_EMPTY child carries
     // an inverted infinite box (enforced at scene creation) and fails the test by itself.
     const bool go0 = n0 <= f0 * 1.000001f;
     const bool go1 = n1 <= f1 * 1.000001f;
@@ -365,10 +385,10 @@ __device__ __forceinline__ void test_prim(const DScene& sc, uint32_t pi, float4 
     }
 }
 
-// One leaf run (1..4 primitives, DFS order), then pop.
+// One leaf run (1..4 primitives, DFS order), then pop.  org64: the f64 origin slot of THIS ray in the queue (SPH64).
 template <bool COUNT, bool SPH64>
 __device__ __forceinline__ void trav_leaf_step(const DScene& sc, const RayK& r, Trav& tv, const SStack& stack,
-                                               TravCounters& cnt) {
+                                               const double* org64, TravCounters& cnt) {
     const uint32_t first = tv.cur & 0x0FFFFFFFu;
     const uint32_t count = ((tv.cur >> 28) & 7u) + 1u;
     // software-pipelined: the record of primitive k + 1 is in flight while primitive k is tested (the loads of a
@@ -377,10 +397,14 @@ __device__ __forceinline__ void trav_leaf_step(const DScene& sc, const RayK& r, 
     RRS_CHECK(first + count <= sc.n_prims && tv.sp >= 1u);
     ldg256(sc.prims + first, a, b);
     ldg256(reinterpret_cast<const char*>(sc.prims + first) + 32, c, pad);
+    const float3 o = r.o, d = r.d;
+    const uint32_t origin_word = r.origin_word;
+    const uint32_t origin_prim = origin_word == RRS_NO_PRIM ? RRS_NO_PRIM : (origin_word & RRS_PRIM_MASK);
+    const double* o64 = (SPH64 && origin_word != RRS_NO_PRIM && (origin_word & RRS_ORG64)) ? org64 : nullptr;
     // the shear rows are rebuilt per leaf visit (~3.5 per ray) instead of living in 6 registers for the
     // whole traversal (~30 node steps per ray); they overlap the first fetch
     RayProj proj;
-    if (sc.has_triangles) proj = make_proj(r.d);
+    if (sc.has_triangles) proj = make_proj(d);
     for (uint32_t k = 0; k < count; ++k) {
         const uint32_t pi = first + k;
         float4 na = a, nb = b, nc = c;
@@ -389,7 +413,7 @@ __device__ __forceinline__ void trav_leaf_step(const DScene& sc, const RayK& r, 
             ldg256(reinterpret_cast<const char*>(sc.prims + pi + 1) + 32, nc, pad);
         }
         if (COUNT) cnt.prims++;
-        test_prim<SPH64>(sc, pi, a, b, c, r.o, r.d, proj, r.origin_prim, r.org64, tv.tbest, tv.best);
+        test_prim<SPH64>(sc, pi, a, b, c, o, d, proj, origin_prim, o64, tv.tbest, tv.best);
         a = na;
         b = nb;
         c = nc;
@@ -496,10 +520,10 @@ __device__ __forceinline__ void closest_hit(const DScene& sc, float3 o, float3 d
                                             uint32_t& best, TravCounters& cnt) {
     RayK r;
     Trav tv;
-    trav_begin<SPH64>(sc, o, d, origin_word, org64, stack, r, tv);
+    trav_begin(sc, o, d, origin_word, stack, r, tv);
     while (tv.cur != TRAV_DONE) {
         while (trav_on_inner(tv)) trav_node_step<COUNT>(sc, r, tv, stack, cnt);
-        if (tv.cur != TRAV_DONE) trav_leaf_step<COUNT, SPH64>(sc, r, tv, stack, cnt);
+        if (tv.cur != TRAV_DONE) trav_leaf_step<COUNT, SPH64>(sc, r, tv, stack, org64, cnt);
     }
     tbest = tv.tbest;
     best = tv.best;

@@ -284,8 +284,7 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
             const uint32_t i = base + (uint32_t)__popc(idle & lt_mask);
             if (!has_ray && i < n) {
                 float4 o4 = ldq(ray_o + i), d4 = ldq(ray_d + i);
-                const double* o64 = (SPH64 && q.org64) ? q.org64 + 3 * (off + i) : nullptr;
-                trav_begin<SPH64>(sc, xyz(o4), xyz(d4), __float_as_uint(o4.w), o64, stack, r, tv);
+                trav_begin(sc, xyz(o4), xyz(d4), __float_as_uint(o4.w), stack, r, tv);
                 has_ray = true;
                 my_i = i;
             }
@@ -308,7 +307,8 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
             }
         }
         // ---- leaves ----
-        if (!trav_on_inner(tv) && tv.cur != TRAV_DONE) trav_leaf_step<COUNT, SPH64>(sc, r, tv, stack, cnt);
+        if (!trav_on_inner(tv) && tv.cur != TRAV_DONE)
+            trav_leaf_step<COUNT, SPH64>(sc, r, tv, stack, (SPH64 && q.org64) ? q.org64 + 3 * (off + my_i) : nullptr, cnt);
         if (has_ray && tv.cur == TRAV_DONE) {
             stq(hits + my_i, make_float2(tv.tbest, __uint_as_float(tv.best)));
             has_ray = false;
@@ -976,7 +976,7 @@ __global__ void k_rng_probe(uint64_t seed, uint32_t pixel, uint32_t sample, uint
 // host side
 // ---------------------------------------------------------------------------------------
 static size_t extend_smem_bytes(const DScene& d) {
-    return (size_t)d.stack_entries * kBlock * sizeof(uint32_t);
+    return (size_t)d.stack_entries * kBlock * sizeof(uint32_t);  // per thread: one traversal stack
 }
 
 static void free_queues(Wavefront& w) {

@@ -24,11 +24,15 @@ for key in keys:
         spp = spp_over or cfg.spp
         for mode in modes:
           for q in queues:
-            for it in range(3):
+            best = None
+            for it in range(6):  # the fastest of 6 renders (clock / thermal noise between renders is +-5 %)
                 t0 = time.time()
                 img = api.render_gpu(cam, sc, spp, cfg.max_bounces, queue_capacity=q, flags=mode)
                 dt = time.time() - t0
-                st = sc.stats()
+                st_i = sc.stats()
+                if best is None or st_i["device_ms"] < best["device_ms"]:
+                    best = st_i
+            st = best
             print("   flags %d queue %9d: wall %.1f ms device %.2f ms rays %.3e -> %.1f Mrays/s; iters %d; gen/ext/shade ms %.2f %.2f %.2f; nodes/ray %.2f prims/ray %.2f; mean %.6f census_miss %d" % (
                 mode, q, dt * 1e3, st["device_ms"], st["rays"], st["rays"] / st["device_ms"] / 1e3, st["iterations"],
                 st["generate_ms"], st["extend_ms"], st["shade_ms"], st["nodes_visited"] / max(1, st["rays"]), st["prims_tested"] / max(1, st["rays"]),

@@ -1,7 +1,10 @@
 """examples/render_c.c — a C99 host over the C ABI with nothing of this repo's Python or C++ host code in between (the
-shape of the Rust shim in INTEGRATION.md): it must compile against include/rayrs_b200.h as plain C, link against
-librayrs_b200.so, fail loudly without a device, and on a GPU render the image the Python face renders from the host
-mirror's own flattening of the same scene."""
+shape of the Rust shim in rust/gpu.rs): it must compile against include/rayrs_b200.h as plain C, link against
+librayrs_b200.so and fail loudly without a device.  Its `row7` scene goes through a tree build and the flattening
+algorithm written in C: the arrays it produces must equal the host mirror's bit for bit (CPU), and on a GPU its closest
+hits and its image must equal the ones rendered from the host mirror's flattening; with two GPUs the same binary renders
+through rrs_render_multi and must reproduce the one-GPU image."""
+import ctypes as C
 import subprocess
 from pathlib import Path
 
@@ -30,14 +33,55 @@ def _hdri_file(tmp_path, w=256, h=128):
     return hdri, path
 
 
+def _run(exe, scene, hpath, hw, hh, W, H, spp, ngpus, out, *extra):
+    return subprocess.run([str(exe), scene, str(hpath), str(hw), str(hh), str(W), str(H), str(spp), str(ngpus), str(out),
+                           *[str(e) for e in extra]], capture_output=True, text=True)
+
+
+def _row7_spec(W, H):
+    from rayrs_b200 import scenes
+    from rayrs_b200.api import BvhHeuristic
+    spec = scenes.cook_torrance_spheres_metallic(W, H)
+    spec.heuristic = BvhHeuristic.Midpoint()  # the C example restates BvhTree::build_midpoint
+    return spec
+
+
 def test_compiles_as_c99_and_refuses_to_run_without_a_device(render_c, tmp_path):
     import torch
     if torch.cuda.is_available():
         pytest.skip("a CUDA device is present")
     _, hpath = _hdri_file(tmp_path, 8, 4)
-    p = subprocess.run([str(render_c), str(hpath), "8", "4", "64", "64", "4", str(tmp_path / "o.f32")], capture_output=True, text=True)
+    p = _run(render_c, "single", hpath, 8, 4, 64, 64, 4, 1, tmp_path / "o.f32")
     assert p.returncode == 1
     assert "rrs_scene_create" in p.stderr and "no CPU fallback" in p.stderr
+
+
+def test_c_flattening_equals_the_host_mirrors(render_c, tmp_path):
+    """The flattening rules of INTEGRATION.md written in C (tree build over index ranges, DFS primitive order,
+    breadth-first node numbering behind a virtual root, bare-leaf flags, outward f32 rounding, max_depth) against the
+    C++ host mirror on the seven-sphere row: every byte of RrsPrim / RrsNode / RrsNodeF64 equal.  No GPU needed: the
+    example writes the arrays before it asks for a device."""
+    from rayrs_b200 import _ffi, scenes
+    hdri, hpath = _hdri_file(tmp_path, 8, 4)
+    flat = tmp_path / "flat.bin"
+    p = _run(render_c, "row7", hpath, 8, 4, 64, 32, 1, 1, tmp_path / "o.f32", flat)
+    assert flat.exists(), p.stderr
+    raw = flat.read_bytes()
+    n_prims, n_nodes, max_depth = np.frombuffer(raw[:12], dtype=np.uint32)
+    sc = _row7_spec(64, 32).scene(hdri, upload=False)
+    nodes, nodes64, order, topo, boxes, prims = sc.flat()
+    assert (n_prims, n_nodes, max_depth) == (sc.n_prims, sc.n_nodes, sc.max_depth) == (8, 4, 3)
+    off = 12
+    for arr, size in ((prims, C.sizeof(_ffi.RrsPrim) * sc.n_prims), (nodes, C.sizeof(_ffi.RrsNode) * sc.n_nodes),
+                      (nodes64, C.sizeof(_ffi.RrsNodeF64) * sc.n_nodes)):
+        assert raw[off:off + size] == bytes(arr), type(arr)
+        off += size
+    assert off == len(raw)
+    # the scene exercises the rules that matter: a bare LeafNode child (flagged) and leaf groups
+    flags = [nd.flags for nd in nodes]
+    refs = [r for nd in nodes for r in (nd.ref0, nd.ref1)]
+    assert any(flags) and any((r & _ffi.RRS_REF_LEAF) and r != _ffi.RRS_REF_EMPTY and ((r >> 28) & 7) >= 1 for r in refs)
+    sc.close()
 
 
 @pytest.mark.gpu
@@ -46,10 +90,10 @@ def test_c_host_renders_the_same_image_as_the_python_face(render_c, tmp_path):
     W, H, spp = 192, 128, 32
     hdri, hpath = _hdri_file(tmp_path)
     out = tmp_path / "out.f32"
-    p = subprocess.run([str(render_c), str(hpath), "256", "128", str(W), str(H), str(spp), str(out)], capture_output=True, text=True)
+    p = _run(render_c, "single", hpath, 256, 128, W, H, spp, 1, out)
     assert p.returncode == 0, p.stderr
     print(p.stdout.strip())
-    assert "axis ray hits object 1" in p.stdout and "nan 0 negative 0" in p.stdout
+    assert "axis ray hits object 1" in p.stdout and "nan 0 negative 0 census 0" in p.stdout
     img_c = np.fromfile(out, dtype=np.float32).reshape(H, W, 3)
     spec = scenes.diffuse_single_sphere(W, H)
     sc = spec.scene(hdri)
@@ -57,3 +101,55 @@ def test_c_host_renders_the_same_image_as_the_python_face(render_c, tmp_path):
     sc.close()
     # same flattening, same camera fields, same seed: the same paths (the accumulator's atomic order is the only freedom)
     assert np.allclose(img_c, img_py, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_c_flattened_row_of_spheres_matches_the_host_mirror_on_the_gpu(render_c, tmp_path):
+    """row7 from the C flattener: closest hits of 2^16 rays and the image equal the host mirror's scene."""
+    from rayrs_b200 import api
+    W, H, spp = 320, 128, 16
+    hdri, hpath = _hdri_file(tmp_path)
+    spec = _row7_spec(W, H)
+    sc = spec.scene(hdri)
+    cam = spec.camera()
+    rng = np.random.default_rng(3)
+    n = 1 << 16
+    org = np.array([0.0, 1.0, 0.0]) + rng.uniform(-1.0, 1.0, (n, 3)) * np.array([12.0, 1.5, 6.0])
+    d = rng.normal(size=(n, 3))
+    rays = np.concatenate([org, d], axis=1).astype(np.float32).astype(np.float64)
+    rays_path, hits_path, out = tmp_path / "rays.f64", tmp_path / "hits.bin", tmp_path / "out.f32"
+    rays.tofile(rays_path)
+    p = _run(render_c, "row7", hpath, 256, 128, W, H, spp, 1, out, tmp_path / "flat.bin", rays_path, n, hits_path)
+    assert p.returncode == 0, p.stderr
+    print(p.stdout.strip())
+    assert "census 0" in p.stdout
+    raw = hits_path.read_bytes()
+    ids_c = np.frombuffer(raw[:4 * n], dtype=np.int32)
+    t_c = np.frombuffer(raw[4 * n:], dtype=np.float64)
+    ids_py, t_py = sc.intersect(rays, 32)
+    assert np.array_equal(ids_c, ids_py) and np.array_equal(t_c, t_py)
+    assert (ids_c >= 1).mean() > 0.05 and (ids_c == 0).mean() > 0.05
+    img_c = np.fromfile(out, dtype=np.float32).reshape(H, W, 3)
+    img_py = api.render_gpu(cam, sc, spp, 50)
+    assert np.allclose(img_c, img_py, rtol=1e-5, atol=1e-6)
+    sc.close()
+
+
+@pytest.mark.gpu
+def test_c_host_renders_on_two_gpus_through_one_call(render_c, tmp_path):
+    """rrs_scene_create_multi + rrs_comm_init_all + rrs_render_multi from pure C: the two-GPU image equals the
+    one-GPU image (same global sample indices; fp32 summation order is the only freedom), census exact."""
+    from rayrs_b200 import _ffi
+    if _ffi.cuda_lib().rrs_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    W, H, spp = 320, 128, 16
+    _, hpath = _hdri_file(tmp_path)
+    o1, o2 = tmp_path / "o1.f32", tmp_path / "o2.f32"
+    p1 = _run(render_c, "row7", hpath, 256, 128, W, H, spp, 1, o1)
+    p2 = _run(render_c, "row7", hpath, 256, 128, W, H, spp, 2, o2)
+    assert p1.returncode == 0 and p2.returncode == 0, p1.stderr + p2.stderr
+    print(p2.stdout.strip())
+    assert "on 2 GPU(s)" in p2.stdout and "census 0" in p2.stdout
+    a = np.fromfile(o1, dtype=np.float32).reshape(H, W, 3)
+    b = np.fromfile(o2, dtype=np.float32).reshape(H, W, 3)
+    assert np.max(np.abs(a - b) / (np.abs(a) + 1e-3)) <= 1e-5

@@ -31,7 +31,11 @@ namespace rrs {
 #ifndef RRS_BLOCK_THREADS
 #define RRS_BLOCK_THREADS 128
 #endif
-static constexpr int kBlock = RRS_BLOCK_THREADS;  // threads per block of the persistent kernels
+static constexpr int kBlock = RRS_BLOCK_THREADS;
+// The f64 distance of the accepted triangle hit (triangle_t64, intersect.cuh) is what rrs_intersect reports.  The
+// render keeps the fp32 distance of the traversal: re-evaluating it in shade_hit would move the hit point by < 2e-6
+// relative — far below what the image can see — and it cost configuration 5 (SPH64 form, 72 registers) 4.7 %
+// (shade 17.6 -> 21.2 ms, profiles/ab_logs/ab_r02g_refine.log).  // threads per block of the persistent kernels
 #ifndef RRS_BLOCKS_PER_SM
 #define RRS_BLOCKS_PER_SM 8
 #endif
@@ -406,14 +410,6 @@ __device__ __forceinline__ NextRay shade_hit(const DScene& sc, const RenderConst
         nrm = normalize3(f3((float)(nx * inv_r), (float)(ny * inv_r), (float)(nz * inv_r)));
         pos = f3((float)p64x, (float)p64y, (float)p64z);
         carry64 = true;
-    } else if (prim_type(a) == RRS_TRIANGLE) {
-        // the accepted hit's distance in f64 (triangle_t64), then Ray::point lib.rs:41-43 and the flat normal of
-        // Triangle::new geometry.rs:341-355 from the same three vertices
-        const float4 b = __ldg(pp + 1), c = __ldg(pp + 2);
-        const float t = triangle_t64(sc, prim, a, b, c, o, d, h.x);
-        pos = madd3(d, t, o);
-        const float3 p1 = xyz(a);
-        nrm = normalize3(cross3(sub3(xyz(b), p1), sub3(xyz(c), p1)));
     } else {
         pos = madd3(d, h.x, o);  // Ray::point lib.rs:41-43
         nrm = prim_normal(sc.prims, prim, a, pos);

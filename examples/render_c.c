@@ -13,6 +13,9 @@
  *                as leaf runs, bare `LeafNode` children flagged and boxed by their primitive, zero-extent nodes
  *                dropped, outward f32 rounding, max_depth.  So a host that is NOT this repo's exercises every
  *                RrsNode rule.
+ *        X.bin   any object list through the same build + flattener: u32 n_objects, n_materials | n_objects x RrsPrim
+ *                (obj_id ignored: the position in the list) | n_materials x RrsMaterial | 7 doubles: camera origin,
+ *                lookat, fov (up = +y).  The tests use it for trees with bare LeafNode children and dead nodes.
  * NGPUS  1: rrs_scene_create + rrs_render.  >1: rrs_scene_create_multi + rrs_comm_init_all + rrs_render_multi
  *        (samples split over the GPUs, one NCCL reduce inside the library) — still one render call.
  * flat.bin   (optional) the flattened arrays, for comparison with the host mirror's:
@@ -290,10 +293,12 @@ static HostObject sphere(double radius, V3 c, unsigned material) {
 
 int main(int argc, char** argv) {
     if (argc != 10 && argc != 11 && argc != 14) {
-        fprintf(stderr, "usage: %s single|row7 hdri.f32 HDRI_W HDRI_H W H SPP NGPUS out.f32 [flat.bin [rays.f64 NRAYS hits.bin]]\n", argv[0]);
+        fprintf(stderr, "usage: %s single|row7|scene.bin hdri.f32 HDRI_W HDRI_H W H SPP NGPUS out.f32 [flat.bin [rays.f64 NRAYS hits.bin]]\n", argv[0]);
         return 2;
     }
     const int row7 = strcmp(argv[1], "row7") == 0;
+    const size_t name_len = strlen(argv[1]);
+    const int from_file = name_len > 4 && strcmp(argv[1] + name_len - 4, ".bin") == 0;
     const unsigned hw = (unsigned)atoi(argv[3]), hh = (unsigned)atoi(argv[4]);
     const unsigned W = (unsigned)atoi(argv[5]), H = (unsigned)atoi(argv[6]), spp = (unsigned)atoi(argv[7]);
     const int ngpus = atoi(argv[8]);
@@ -307,6 +312,7 @@ int main(int argc, char** argv) {
     fclose(f);
 
     RrsMaterial mats[8];
+    RrsMaterial* file_mats = NULL;
     RrsSceneDesc desc;
     memset(&desc, 0, sizeof desc);
     Flat flat;
@@ -315,7 +321,26 @@ int main(int argc, char** argv) {
     RrsNode node;
     RrsNodeF64 node64;
     RrsCamera cam;
-    if (!row7) {
+    if (from_file) {
+        /* ---- a caller's object list: tree build + flattener ---- */
+        uint32_t head[2];
+        double camf[7];
+        f = fopen(argv[1], "rb");
+        if (!f || fread(head, sizeof head, 1, f) != 1 || head[0] == 0 || head[1] == 0) { fprintf(stderr, "cannot read %s\n", argv[1]); return 2; }
+        HostObject* objs = (HostObject*)malloc(sizeof(HostObject) * head[0]);
+        file_mats = (RrsMaterial*)malloc(sizeof(RrsMaterial) * head[1]);
+        for (uint32_t i = 0; i < head[0]; ++i)
+            if (fread(&objs[i].prim, sizeof(RrsPrim), 1, f) != 1) { fprintf(stderr, "short object table\n"); return 2; }
+        if (fread(file_mats, sizeof(RrsMaterial), head[1], f) != head[1] || fread(camf, sizeof camf, 1, f) != 1) { fprintf(stderr, "short scene file\n"); return 2; }
+        fclose(f);
+        flat = build_and_flatten(objs, head[0]);
+        free(objs);
+        desc.n_prims = flat.n_prims; desc.prims = flat.prims;
+        desc.n_nodes = flat.n_nodes; desc.nodes = flat.nodes; desc.nodes_f64 = flat.nodes64;
+        desc.max_depth = flat.max_depth;
+        desc.n_materials = head[1];
+        cam = camera_new(v3(camf[0], camf[1], camf[2]), v3(0, 1, 0), v3(camf[3], camf[4], camf[5]), camf[6], (double)W / 254.0, (double)H / 254.0, 100);
+    } else if (!row7) {
         /* ---- diffuse_single_sphere, flattened by hand ---- */
         mats[0] = metal(0.5, 0.8);  /* floor: test_scenes.rs:15-21 */
         memset(&mats[1], 0, sizeof mats[1]);
@@ -361,7 +386,7 @@ int main(int argc, char** argv) {
         cam = camera_new(v3(0, 10, 20), v3(0, 1, 0), v3(0, 1, 0), 72.0, (double)W / 254.0, (double)H / 254.0, 100); /* :194-202 */
     }
     desc.abi_version = RRS_ABI_VERSION;
-    desc.materials = mats;
+    desc.materials = from_file ? file_mats : mats;
     desc.n_emissions = 0; desc.emissions = NULL;
     desc.hdri_width = hw; desc.hdri_height = hh; desc.hdri_rgb = hdri;
     desc.t_min = 1e-6; desc.t_max = 1e6; /* rayrs/src/main.rs:52 */
@@ -448,6 +473,6 @@ int main(int argc, char** argv) {
     if (comm) rrs_comm_destroy(comm);
     for (int i = 0; i < ngpus; ++i) rrs_scene_destroy(scenes[i]);
     free(rgb); free(hdri);
-    free(flat.prims); free(flat.nodes); free(flat.nodes64);
+    free(flat.prims); free(flat.nodes); free(flat.nodes64); free(file_mats);
     return 0;
 }

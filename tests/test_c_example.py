@@ -56,31 +56,99 @@ def test_compiles_as_c99_and_refuses_to_run_without_a_device(render_c, tmp_path)
     assert "rrs_scene_create" in p.stderr and "no CPU fallback" in p.stderr
 
 
+def _compare_flat(raw, sc):
+    """Every byte of the C example's arrays against the host mirror's — except the material INDEX of a primitive: the
+    host mirror numbers its material table in order of first use along the DFS primitive order, the example keeps the
+    caller's numbering; the two must be the same pairing under a one-to-one renaming."""
+    from rayrs_b200 import _ffi
+    nodes, nodes64, order, topo, boxes, prims = sc.flat()
+    n_prims, n_nodes, max_depth = (int(x) for x in np.frombuffer(raw[:12], dtype=np.uint32))
+    assert (n_prims, n_nodes, max_depth) == (sc.n_prims, sc.n_nodes, sc.max_depth)
+    off = 12
+    c_prims = (_ffi.RrsPrim * n_prims).from_buffer_copy(raw[off:off + C.sizeof(_ffi.RrsPrim) * n_prims])
+    off += C.sizeof(_ffi.RrsPrim) * n_prims
+    rename = {}
+    for a, b in zip(c_prims, prims):
+        assert (a.type, a.obj_id, a.emission, list(a.v)) == (b.type, b.obj_id, b.emission, list(b.v))
+        assert rename.setdefault(a.material, b.material) == b.material
+    assert len(set(rename.values())) == len(rename)
+    for arr, size in ((nodes, C.sizeof(_ffi.RrsNode) * sc.n_nodes), (nodes64, C.sizeof(_ffi.RrsNodeF64) * sc.n_nodes)):
+        assert raw[off:off + size] == bytes(arr), type(arr)
+        off += size
+    assert off == len(raw)
+    return nodes
+
+
+def _scene_file(path, spec):
+    """The object list of a SceneSpec in the example's .bin format (RrsPrim / RrsMaterial records + camera)."""
+    from rayrs_b200 import _ffi
+    t = spec.tables()
+    n, m = t.objs.shape[0], t.mats.shape[0]
+    prims = (_ffi.RrsPrim * n)()
+    for i, row in enumerate(t.objs):
+        p = prims[i]
+        p.type, p.obj_id, p.material, p.emission = int(row[0]), i, int(row[1]), int(row[2])
+        v = list(row[3:12])
+        if p.type == 0:      # sphere: the table carries the radius, RrsPrim the squared radius
+            v = [v[0] * v[0], v[1], v[2], v[3], 0, 0, 0, 0, 0]
+        p.v[:] = v
+    mats = (_ffi.RrsMaterial * m)()
+    for i, row in enumerate(t.mats):
+        q = mats[i]
+        q.tag, q.fresnel_kind = int(row[0]), int(row[6])
+        q.color[:] = list(row[1:4])
+        q.alpha, q.ior = float(row[4]), float(row[5])
+        q.spec_color[:] = list(row[7:10])
+    c = spec.camera_args
+    with open(path, "wb") as f:
+        f.write(np.array([n, m], dtype=np.uint32).tobytes())
+        f.write(bytes(prims))
+        f.write(bytes(mats))
+        f.write(np.array([*c["origin"], *c["lookat"], c["fov"]], dtype=np.float64).tobytes())
+
+
+def _awkward_spec(W, H):
+    """A tree with every flattening rule in it: 1-object sides (bare LeafNode children), a dead node (a group of
+    coplanar planes has a zero-extent box the reference can never enter), leaf groups, three levels."""
+    from rayrs_b200 import scenes
+    from rayrs_b200.api import Axis, BvhHeuristic, Emission, Fresnel, Material, Object
+    grey = Material.lambertian_diffuse((0.7, 0.7, 0.7))
+    metal = Material.cook_torrance((1, 1, 1), 0.1, Fresnel.schlick_metallic((0.8, 0.6, 0.3)))
+    objs = [Object.sphere(0.6, (-20.0, 0.6, 0.0), metal)]                                       # far left, alone: a bare LeafNode
+    objs += [Object.sphere(0.5, (1.5 * i, 0.5, 0.3 * i), grey if i % 2 else metal) for i in range(5)]
+    objs += [Object.plane(Axis.Y, 9.0 + i, 9.8 + i, -1.0, 1.0, 0.25, grey) for i in range(4)]    # coplanar: a dead group
+    objs += [Object.triangle((15 + i, 0.1, 3), (15.8 + i, 0.1, 3.2), (15.4 + i, 1.2 + 0.1 * i, 3.1), metal) for i in range(5)]
+    cam = dict(origin=(0.0, 8.0, 24.0), up=(0.0, 1.0, 0.0), lookat=(0.0, 0.5, 0.0), fov=80.0, width=W / 254.0, height=H / 254.0, ppi=100)
+    return scenes.SceneSpec("awkward", cam, objs, BvhHeuristic.Midpoint())
+
+
 def test_c_flattening_equals_the_host_mirrors(render_c, tmp_path):
     """The flattening rules of INTEGRATION.md written in C (tree build over index ranges, DFS primitive order,
-    breadth-first node numbering behind a virtual root, bare-leaf flags, outward f32 rounding, max_depth) against the
-    C++ host mirror on the seven-sphere row: every byte of RrsPrim / RrsNode / RrsNodeF64 equal.  No GPU needed: the
-    example writes the arrays before it asks for a device."""
-    from rayrs_b200 import _ffi, scenes
+    breadth-first node numbering behind a virtual root, bare-leaf flags, dead nodes, outward f32 rounding, max_depth)
+    against the C++ host mirror: every byte of RrsPrim / RrsNode / RrsNodeF64 equal — on the seven-sphere row and on a
+    scene built to contain every rule.  No GPU needed: the example writes the arrays before it asks for a device."""
+    from rayrs_b200 import _ffi
     hdri, hpath = _hdri_file(tmp_path, 8, 4)
     flat = tmp_path / "flat.bin"
     p = _run(render_c, "row7", hpath, 8, 4, 64, 32, 1, 1, tmp_path / "o.f32", flat)
     assert flat.exists(), p.stderr
-    raw = flat.read_bytes()
-    n_prims, n_nodes, max_depth = np.frombuffer(raw[:12], dtype=np.uint32)
     sc = _row7_spec(64, 32).scene(hdri, upload=False)
-    nodes, nodes64, order, topo, boxes, prims = sc.flat()
-    assert (n_prims, n_nodes, max_depth) == (sc.n_prims, sc.n_nodes, sc.max_depth) == (8, 4, 3)
-    off = 12
-    for arr, size in ((prims, C.sizeof(_ffi.RrsPrim) * sc.n_prims), (nodes, C.sizeof(_ffi.RrsNode) * sc.n_nodes),
-                      (nodes64, C.sizeof(_ffi.RrsNodeF64) * sc.n_nodes)):
-        assert raw[off:off + size] == bytes(arr), type(arr)
-        off += size
-    assert off == len(raw)
-    # the scene exercises the rules that matter: a bare LeafNode child (flagged) and leaf groups
-    flags = [nd.flags for nd in nodes]
+    _compare_flat(flat.read_bytes(), sc)
+    sc.close()
+    # the awkward scene, through the example's scene-file mode
+    spec = _awkward_spec(64, 32)
+    scene_bin = tmp_path / "awkward.bin"
+    _scene_file(scene_bin, spec)
+    flat2 = tmp_path / "flat2.bin"
+    p = _run(render_c, scene_bin, hpath, 8, 4, 64, 32, 1, 1, tmp_path / "o.f32", flat2)
+    assert flat2.exists(), p.stderr
+    sc = spec.scene(hdri, upload=False)
+    nodes = _compare_flat(flat2.read_bytes(), sc)
     refs = [r for nd in nodes for r in (nd.ref0, nd.ref1)]
-    assert any(flags) and any((r & _ffi.RRS_REF_LEAF) and r != _ffi.RRS_REF_EMPTY and ((r >> 28) & 7) >= 1 for r in refs)
+    assert any(nd.flags for nd in nodes), "no bare LeafNode child in the scene"
+    assert sc.dead_nodes >= 1 and refs.count(_ffi.RRS_REF_EMPTY) >= 2, "no dead node in the scene"
+    assert any((r & _ffi.RRS_REF_LEAF) and r != _ffi.RRS_REF_EMPTY and ((r >> 28) & 7) >= 1 for r in refs)
+    assert sc.max_depth >= 4
     sc.close()
 
 
@@ -132,6 +200,34 @@ def test_c_flattened_row_of_spheres_matches_the_host_mirror_on_the_gpu(render_c,
     img_c = np.fromfile(out, dtype=np.float32).reshape(H, W, 3)
     img_py = api.render_gpu(cam, sc, spp, 50)
     assert np.allclose(img_c, img_py, rtol=1e-5, atol=1e-6)
+    sc.close()
+
+
+@pytest.mark.gpu
+def test_c_flattened_awkward_scene_matches_the_host_mirror_on_the_gpu(render_c, tmp_path):
+    """bare LeafNode children, a dead node, triangles and planes: the C flattener's scene gives the host mirror's hits."""
+    W, H, spp = 256, 128, 8
+    hdri, hpath = _hdri_file(tmp_path)
+    spec = _awkward_spec(W, H)
+    scene_bin = tmp_path / "awkward.bin"
+    _scene_file(scene_bin, spec)
+    sc = spec.scene(hdri)
+    rng = np.random.default_rng(4)
+    n = 1 << 16
+    org = np.array([-2.0, 1.0, 1.0]) + rng.uniform(-1.0, 1.0, (n, 3)) * np.array([22.0, 1.5, 5.0])
+    rays = np.concatenate([org, rng.normal(size=(n, 3))], axis=1).astype(np.float32).astype(np.float64)
+    rays_path, hits_path, out = tmp_path / "rays.f64", tmp_path / "hits.bin", tmp_path / "out.f32"
+    rays.tofile(rays_path)
+    p = _run(render_c, scene_bin, hpath, 256, 128, W, H, spp, 1, out, tmp_path / "flat.bin", rays_path, n, hits_path)
+    assert p.returncode == 0, p.stderr
+    raw = hits_path.read_bytes()
+    ids_c = np.frombuffer(raw[:4 * n], dtype=np.int32)
+    t_c = np.frombuffer(raw[4 * n:], dtype=np.float64)
+    ids_py, t_py = sc.intersect(rays, 32)
+    assert np.array_equal(ids_c, ids_py) and np.array_equal(t_c, t_py)
+    dead = [i for i, o in enumerate(spec.tables().objs) if o[0] == 1 and o[8] == 0.25]
+    assert len(dead) == 4 and not np.isin(ids_c, dead).any()  # the coplanar planes are unreachable, as in the reference
+    assert len(np.unique(ids_c)) >= 10
     sc.close()
 
 

@@ -206,6 +206,7 @@ def test_c_flattened_row_of_spheres_matches_the_host_mirror_on_the_gpu(render_c,
 @pytest.mark.gpu
 def test_c_flattened_awkward_scene_matches_the_host_mirror_on_the_gpu(render_c, tmp_path):
     """bare LeafNode children, a dead node, triangles and planes: the C flattener's scene gives the host mirror's hits."""
+    from rayrs_b200 import _ffi
     W, H, spp = 256, 128, 8
     hdri, hpath = _hdri_file(tmp_path)
     spec = _awkward_spec(W, H)
@@ -225,8 +226,20 @@ def test_c_flattened_awkward_scene_matches_the_host_mirror_on_the_gpu(render_c, 
     t_c = np.frombuffer(raw[4 * n:], dtype=np.float64)
     ids_py, t_py = sc.intersect(rays, 32)
     assert np.array_equal(ids_c, ids_py) and np.array_equal(t_c, t_py)
-    dead = [i for i, o in enumerate(spec.tables().objs) if o[0] == 1 and o[8] == 0.25]
-    assert len(dead) == 4 and not np.isin(ids_c, dead).any()  # the coplanar planes are unreachable, as in the reference
+    # objects under the dead node are unreachable, as in the reference: no ray reports them
+    nodes, _, order, _, _, _ = sc.flat()
+    reach, todo = set(), [0]
+    while todo:
+        nd = nodes[todo.pop()]
+        for r in (nd.ref0, nd.ref1):
+            if r == _ffi.RRS_REF_EMPTY:
+                continue
+            if r & _ffi.RRS_REF_LEAF:
+                reach.update(int(order[(r & 0x0FFFFFFF) + k]) for k in range(((r >> 28) & 7) + 1))
+            else:
+                todo.append(r)
+    dead = sorted(set(range(sc.n_prims)) - reach)
+    assert dead and not np.isin(ids_c, dead).any(), dead
     assert len(np.unique(ids_c)) >= 10
     sc.close()
 

@@ -25,4 +25,29 @@ def test_nccl_sample_split_matches_single_gpu(native_built):
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=ROOT)
     print(p.stdout[-3000:])
     assert p.returncode == 0, p.stdout[-3000:]
-    assert p.stdout.count("PASS") == 2 and "FAIL" not in p.stdout
+    assert p.stdout.count("PASS") == 4 and "FAIL" not in p.stdout  # 2 scenes x (library call, torch reduce)
+
+
+def test_one_process_drives_two_gpus_through_one_render_call(native_built, hdri_small):
+    """A scene that lives on two GPUs (built and flattened once, uploaded twice: rrs_scene_create_multi) renders
+    through the same render_gpu call as a one-GPU scene — rrs_render_multi over an in-process communicator
+    (rrs_comm_init_all) — and gives the one-GPU image; census exact on both."""
+    import numpy as np
+    import torch
+    from rayrs_b200 import api, scenes
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    for spec, spp in ((scenes.cook_torrance_spheres_plastic(320, 128), 30), (scenes.mixed_scene(60, 60, 256, 144), 13)):
+        cam = spec.camera()
+        one = spec.scene(hdri_small, device=0, with_f64=False)
+        two = spec.scene(hdri_small, devices=[0, 1], with_f64=False)
+        a = api.render_gpu(cam, one, spp, 50).astype(np.float64)
+        b = api.render_gpu(cam, two, spp, 50).astype(np.float64)
+        s0, s1 = two.stats(0), two.stats(1)
+        assert one.stats()["census_mismatch_pixels"] == 0 and s0["census_mismatch_pixels"] == 0
+        assert s0["rays"] > 0 and s1["rays"] > 0 and abs(s0["rays"] + s1["rays"] - one.stats()["rays"]) <= 1e-3 * one.stats()["rays"]
+        err = float(np.max(np.abs(a - b) / (np.abs(a) + 1e-2)))
+        print(f"[{spec.name}] two GPUs in one process vs one GPU: max rel diff {err:.2e}; rays {s0['rays']} + {s1['rays']}")
+        assert err < 1e-4
+        one.close()
+        two.close()

@@ -312,6 +312,27 @@ int rrs_background(RrsScene* scene, const double* dirs, size_t n, float* out);
 /* The uniforms the device RNG hands to (pixel, sample, slot): 4 floats. */
 int rrs_rng_uniforms(RrsScene* scene, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, float* out4);
 
+/* ---- BvhTree::build_sah / build_midpoint (bvh.rs:227-389) on the device: the SAME tree as the reference's recursive
+ * build — same boxes bit for bit, same split indices, same primitive order — as a level-synchronous sweep (stable
+ * radix sort per level, segmented prefix / suffix box scans, the calculate_sah sweep over the splits the threshold
+ * loop reaches).  Scene setup for hosts whose own build is the bottleneck (4M triangles: seconds on the host);
+ * the host flattens the returned tree into RrsNode / RrsPrim exactly as it would its own.
+ *   boxes      n x 6 doubles, one object each: xmin, xmax, ymin, ymax, zmin, zmax (Hittable::bbox)
+ *   heuristic  0 = BvhHeuristic::Midpoint, 1 = BvhHeuristic::Sah { splits }
+ *   prim_order n entries out: object indices in DFS leaf order
+ *   nodes      capacity 2 n + 2 out: node 0 is the root; kind 0 = Node with two children (indices into nodes),
+ *              1 = Node holding <= 4 LeafNodes (objects prim_order[first .. first + count)), 2 = bare LeafNode
+ *              (object prim_order[first]; box = the object's own)
+ *   seconds    device time of the build (may be NULL) */
+typedef struct RrsBuildNode {
+    double box[6];
+    int32_t child[2];
+    uint32_t first, count;
+    uint32_t kind, pad;
+} RrsBuildNode;
+int rrs_bvh_build(const double* boxes, uint32_t n, uint32_t heuristic, uint32_t splits, int device, uint32_t* prim_order,
+                  RrsBuildNode* nodes, uint32_t* n_nodes, double* seconds);
+
 int rrs_stats(RrsScene* scene, RrsStats* out);
 const char* rrs_last_error(void);
 int rrs_abi_version(void);

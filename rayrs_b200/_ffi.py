@@ -75,6 +75,11 @@ class RrsUniqueId(C.Structure):
     _fields_ = [("bytes", C.c_char * 128)]
 
 
+class RrsBuildNode(C.Structure):
+    _fields_ = [("box", C.c_double * 6), ("child", C.c_int32 * 2), ("first", C.c_uint32), ("count", C.c_uint32),
+                ("kind", C.c_uint32), ("pad", C.c_uint32)]
+
+
 class RrsRay(C.Structure):
     _fields_ = [("origin", C.c_double * 3), ("direction", C.c_double * 3)]
 
@@ -111,6 +116,8 @@ CUDA_SYMBOLS = {
     "rrs_material_evaluate": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "rrs_background": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "rrs_rng_uniforms": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "rrs_bvh_build": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.POINTER(C.c_uint32), C.POINTER(C.c_double)]),
     "rrs_stats": (C.c_int, [C.c_void_p, C.POINTER(RrsStats)]),
     "rrs_last_error": (C.c_char_p, []),
     "rrs_abi_version": (C.c_int, []),
@@ -121,7 +128,7 @@ HOST_SYMBOLS = {
     "rrh_last_error": (C.c_char_p, []),
     "rrh_scene_new": (C.c_void_p, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int,
                                     C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_int,
-                                    C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_int), C.c_int]),
+                                    C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int]),
     "rrh_scene_free": (None, [C.c_void_p]),
     "rrh_scene_handle": (C.c_void_p, [C.c_void_p]),
     "rrh_scene_handle_at": (C.c_void_p, [C.c_void_p, C.c_uint32]),

@@ -258,10 +258,11 @@ class Scene:
 
     def __init__(self, objects: Sequence[Object], z_near: float, z_far: float, heuristic: BvhHeuristic, hdri: Image,
                  device: int = 0, with_f64: bool = True, upload: bool = True, devices: Sequence[int] | None = None,
-                 scene_flags: int = 0, refill_lanes: int = 0, bvh_threads: int = 0):
+                 scene_flags: int = 0, refill_lanes: int = 0, bvh_threads: int = 0, device_build: bool = False):
         """devices: the GPUs that hold the scene (default [device]); the BVH is built and flattened once and
         uploaded to each, and render_gpu() then splits the samples over them (rrs_render_multi).
-        scene_flags / refill_lanes: RrsSceneDesc.flags / .refill_lanes (measurement switches)."""
+        scene_flags / refill_lanes: RrsSceneDesc.flags / .refill_lanes (measurement switches).
+        device_build: build the reference tree on the GPU (rrs_bvh_build, the same tree) instead of on the host."""
         lib = _ffi.host_lib()
         flat = []
         for o in objects:
@@ -277,7 +278,7 @@ class Scene:
                                     t.emis.ctypes.data if t.emis.size else None, t.emis.shape[0], heuristic.kind,
                                     heuristic.splits, h.ctypes.data, hdri.width, hdri.height, float(z_near),
                                     float(z_far), int(device), int(with_f64), int(upload), int(scene_flags),
-                                    int(refill_lanes), int(bvh_threads), devs, len(self.devices))
+                                    int(refill_lanes), int(bvh_threads), devs, len(self.devices), int(device_build))
         if not self._p:
             raise ValueError(lib.rrh_last_error().decode())
         info = (C.c_uint64 * 7)()
@@ -286,9 +287,9 @@ class Scene:
         self.n_nodes, self.n_prims, self.max_depth, self.dead_nodes, self.n_materials, self._topo_len, self._n_boxes = (
             int(x) for x in info)
         self.build_seconds = bs.value
-        t6 = (C.c_double * 6)()
-        lib.rrh_scene_build_timing(self._p, t6)
-        self.build_timing = dict(zip(("boxes", "recursive", "numbering", "flatten", "depth", "topology"), (float(x) for x in t6)))
+        t7 = (C.c_double * 7)()
+        lib.rrh_scene_build_timing(self._p, t7)
+        self.build_timing = dict(zip(("boxes", "tree", "numbering", "flatten", "depth", "topology", "tree_device"), (float(x) for x in t7)))
         self.handle = lib.rrh_scene_handle(self._p) if upload else None
         self.handles = [lib.rrh_scene_handle_at(self._p, i) for i in range(len(self.devices))] if upload else []
 

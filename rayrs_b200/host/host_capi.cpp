@@ -50,7 +50,7 @@ const char* rrh_last_error(void) { return g_err.c_str(); }
 void* rrh_scene_new(const double* objs, uint64_t n_obj, const double* mats, uint64_t n_mat, const double* emis,
                     uint64_t n_emis, int heuristic, uint32_t splits, const double* hdri, uint64_t hw, uint64_t hh,
                     double tmin, double tmax, int device, int with_f64, int upload, uint32_t scene_flags,
-                    uint32_t refill_lanes, int bvh_threads, const int* devices, int n_devices) {
+                    uint32_t refill_lanes, int bvh_threads, const int* devices, int n_devices, int device_build) {
     try {
         std::vector<Material> mt;
         for (uint64_t i = 0; i < n_mat; ++i) mt.push_back(material_from_row(mats + 12 * i));
@@ -88,6 +88,7 @@ void* rrh_scene_new(const double* objs, uint64_t n_obj, const double* mats, uint
         opt.flags = scene_flags;
         opt.refill_lanes = refill_lanes;
         opt.bvh_threads = bvh_threads;
+        opt.device_build = device_build != 0;
         return new Scene(objects, tmin, tmax, h, img, opt);
     } catch (const std::exception& e) {
         g_err = e.what();
@@ -111,10 +112,11 @@ RrsComm* rrh_scene_comm(void* s) {
         return nullptr;
     }
 }
-// [boxes, recursive build, numbering, flatten, depth, topology dump] seconds of the host BVH build
-void rrh_scene_build_timing(void* s, double* out6) {
+// [boxes, tree build, numbering, flatten, depth, topology dump, device part of the tree build] seconds of the BVH build
+void rrh_scene_build_timing(void* s, double* out7) {
     const BvhBuildTiming& t = static_cast<Scene*>(s)->build_timing();
-    out6[0] = t.boxes; out6[1] = t.recursive; out6[2] = t.numbering; out6[3] = t.flatten; out6[4] = t.depth; out6[5] = t.topology;
+    out7[0] = t.boxes; out7[1] = t.recursive; out7[2] = t.numbering; out7[3] = t.flatten; out7[4] = t.depth; out7[5] = t.topology;
+    out7[6] = t.device;
 }
 
 // info: [n_nodes, n_prims, max_depth, dead_nodes, n_materials, topology_len, n_boxes]

@@ -548,7 +548,7 @@ void dump_topology(const std::vector<BNode>& bn, int32_t b, const std::vector<ui
 }  // namespace
 
 FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, uint32_t bfs_nodes, int threads,
-                   BvhBuildTiming* timing) {
+                   BvhBuildTiming* timing, int build_device) {
     if (objects.empty()) throw Panic("Having a BVH for 0 objects does not make sense");
     if (heuristic.kind == BvhHeuristic::kSah && heuristic.splits < 2) throw Panic("Sah needs at least 2 splits");
     const size_t n = objects.size();
@@ -569,10 +569,38 @@ FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, u
     out.prim_order.resize(n);
     for (size_t i = 0; i < n; ++i) out.prim_order[i] = (uint32_t)i;
     Builder b(boxes, centers, out.prim_order, heuristic);
-    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    b.spare_threads = threads - 1;
-    b.nodes.reserve(n);
-    const int32_t root = b.build(0, n, 0);
+    int32_t root = 0;
+    if (build_device >= 0) {
+        // the same tree from the GPU (csrc/bvh_build.cu); its records are the builder's BNodes
+        static_assert(sizeof(AxisAlignedBoundingBox) == 6 * sizeof(double), "boxes are handed over as n x 6 doubles");
+        for (size_t i = 0; i < n; ++i)
+            for (double v : {boxes[i].xmin, boxes[i].xmax, boxes[i].ymin, boxes[i].ymax, boxes[i].zmin, boxes[i].zmax})
+                if (std::isnan(v)) throw Panic("partial_cmp().unwrap() on NaN centre");  // bvh.rs:104
+        std::vector<RrsBuildNode> dn(2 * n + 2);
+        uint32_t n_nodes = 0;
+        double dev_s = 0.;
+        int rc = rrs_bvh_build(&boxes[0].xmin, (uint32_t)n, heuristic.kind == BvhHeuristic::kSah ? 1u : 0u, heuristic.splits, build_device,
+                               out.prim_order.data(), dn.data(), &n_nodes, &dev_s);
+        if (rc != RRS_OK) throw Panic(std::string("rrs_bvh_build failed: ") + rrs_last_error());
+        if (timing) timing->device = dev_s;
+        b.nodes.resize(n_nodes);
+        for (uint32_t i = 0; i < n_nodes; ++i) {
+            BNode& t = b.nodes[i];
+            const RrsBuildNode& s = dn[i];
+            t.box = AxisAlignedBoundingBox{s.box[0], s.box[1], s.box[2], s.box[3], s.box[4], s.box[5]};
+            t.child[0] = s.child[0];
+            t.child[1] = s.child[1];
+            t.first = s.first;
+            t.count = s.count;
+            t.kind = (uint8_t)s.kind;
+        }
+        root = 0;
+    } else {
+        if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+        b.spare_threads = threads - 1;
+        b.nodes.reserve(n);
+        root = b.build(0, n, 0);
+    }
     const std::vector<BNode>& bn = b.nodes;
     lap(&BvhBuildTiming::recursive);
 
@@ -717,7 +745,7 @@ void Scene::init(const std::vector<Object>& objects, double z_near, double z_far
     require(z_far > z_near, "Scene::new: z_far must be > z_near");
     require(!opt.devices.empty(), "Scene::new: no device");
     auto t0 = std::chrono::steady_clock::now();
-    bvh_ = Bvh::build(heuristic, objects, 1023, opt.bvh_threads, &timing_);
+    bvh_ = Bvh::build(heuristic, objects, 1023, opt.bvh_threads, &timing_, opt.device_build ? opt.devices[0] : -1);
     build_seconds_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
     // materials / emissions: objects carry them by value (mat.clone() in lib.rs:407-415);

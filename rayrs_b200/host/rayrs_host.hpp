@@ -138,13 +138,16 @@ struct FlatBvh {
 // where the build time goes (seconds), filled when a pointer is handed to Bvh::build
 struct BvhBuildTiming {
     double boxes = 0, recursive = 0, numbering = 0, flatten = 0, depth = 0, topology = 0;
+    double device = 0;  // of `recursive`: the device time of rrs_bvh_build when the tree was built on the GPU
 };
 
 struct Bvh {
     // Bvh::build bvh.rs:199-210.  threads: worker threads for independent subtrees and chunked sorts
     // (0 = one per hardware thread).
+    // build_device >= 0: the tree is built on that GPU (rrs_bvh_build: the same tree, level-synchronous) instead of
+    // by the recursive host build; numbering and flattening are the same code either way.
     static FlatBvh build(BvhHeuristic heuristic, const std::vector<Object>& objects, uint32_t bfs_nodes = 1023,
-                         int threads = 0, BvhBuildTiming* timing = nullptr);
+                         int threads = 0, BvhBuildTiming* timing = nullptr, int build_device = -1);
 };
 
 struct Image {
@@ -175,6 +178,7 @@ struct SceneOptions {
     uint32_t flags = 0;           // RRS_SCENE_*
     uint32_t refill_lanes = 0;    // 0 = library default
     int bvh_threads = 0;          // 0 = one per hardware thread
+    bool device_build = false;    // build the BVH on devices[0] (rrs_bvh_build) instead of on the host
 };
 
 class Scene {

@@ -361,9 +361,10 @@ def run_ours(args):
     specs = cfg.specs()
     hdri = scenes.synthetic_hdri(2048, 1024)
     t_setup = time.time()
-    built = [(spec, spec.scene(hdri, device=local, with_f64=False), spec.camera()) for spec in specs]
+    built = [(spec, spec.scene(hdri, device=local, with_f64=False, device_build=True, topology=False), spec.camera()) for spec in specs]
     t_setup = time.time() - t_setup
     build_s = sum(sc.build_seconds for _, sc, _ in built)
+    build_timing = [sc.build_timing for _, sc, _ in built]
     W, H = cfg.width, cfg.height
     stream = torch.cuda.current_stream(dev)
     sptr = stream.cuda_stream
@@ -548,7 +549,8 @@ def run_ours(args):
                        "max_bounces": cfg.max_bounces, "hdri": "synthetic 2048x1024",
                        "parallelism": f"sample-split x{world} inside rrs_render_multi, one ncclReduce(sum) of the fp32 radiance buffer",
                        "l2": "256 MB L2 flush between steps (inside the timed region)",
-                       "rays_per_step": rays_all / args.steps, "scene_setup_s": t_setup, "bvh_build_s": build_s},
+                       "rays_per_step": rays_all / args.steps, "scene_setup_s": t_setup, "bvh_build_s": build_s,
+                       "bvh_build": "same-tree build on the device (rrs_bvh_build), numbering + flattening on the host", "bvh_build_timing_s": build_timing},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cam_bytes,
                     "d2h_bytes_per_step": W * H * 3 * 4 * len(built), "steps": e2e_steps, "ms_per_step": e2e_step_ms,
                     "with_setup": {"value": float(e2e_r.item()) / e2e_steps / (float(e2e_s.item()) / e2e_steps + t_setup) / 1e6, "unit": UNIT,
@@ -578,7 +580,7 @@ def mini_record(key, scenes, api, _ffi, torch, dev, sptr, hdri, flush, clocks, s
     cfg = scenes.CONFIGS[key]
     specs = cfg.specs()
     t0 = time.time()
-    built = [(spec, spec.scene(hdri, device=dev.index, with_f64=False), spec.camera()) for spec in specs]
+    built = [(spec, spec.scene(hdri, device=dev.index, with_f64=False, device_build=True, topology=False), spec.camera()) for spec in specs]
     setup = time.time() - t0
     W, H = cfg.width, cfg.height
     acc = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)

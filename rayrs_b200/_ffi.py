@@ -128,7 +128,7 @@ HOST_SYMBOLS = {
     "rrh_last_error": (C.c_char_p, []),
     "rrh_scene_new": (C.c_void_p, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int,
                                     C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_int,
-                                    C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int]),
+                                    C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int]),
     "rrh_scene_free": (None, [C.c_void_p]),
     "rrh_scene_handle": (C.c_void_p, [C.c_void_p]),
     "rrh_scene_handle_at": (C.c_void_p, [C.c_void_p, C.c_uint32]),

@@ -188,7 +188,10 @@ class SceneTables:
 def build_tables(objects: Iterable[Object]) -> SceneTables:
     mats: list[Material] = []
     emis: list[Emission] = []
-    chunks = []
+    objects = list(objects)
+    total = sum(o.rows.shape[0] for o in objects)
+    objs = np.empty((total, 12), dtype=np.float64)  # filled slice by slice: no per-object temporaries, no concatenate
+    pos = 0
     for o in objects:
         if o.mat not in mats:
             mats.append(o.mat)
@@ -199,16 +202,12 @@ def build_tables(objects: Iterable[Object]) -> SceneTables:
                 emis.append(o.emission)
             ei = emis.index(o.emission)
         n = o.rows.shape[0]
-        rows = np.zeros((n, 12), dtype=np.float64)
+        rows = objs[pos:pos + n]
         rows[:, 0] = o.rows[:, 0]
         rows[:, 1] = mi
         rows[:, 2] = ei
         rows[:, 3:12] = o.rows[:, 1:10]
-        chunks.append(rows)
-    if not chunks:
-        objs = np.zeros((0, 12))
-    else:
-        objs = np.ascontiguousarray(np.concatenate(chunks, axis=0))
+        pos += n
     m = np.array([mm.row for mm in mats], dtype=np.float64).reshape(-1, 12)
     e = np.array([[em.strength, *em.color] for em in emis], dtype=np.float64).reshape(-1, 4)
     return SceneTables(objs, np.ascontiguousarray(m), np.ascontiguousarray(e))
@@ -258,11 +257,13 @@ class Scene:
 
     def __init__(self, objects: Sequence[Object], z_near: float, z_far: float, heuristic: BvhHeuristic, hdri: Image,
                  device: int = 0, with_f64: bool = True, upload: bool = True, devices: Sequence[int] | None = None,
-                 scene_flags: int = 0, refill_lanes: int = 0, bvh_threads: int = 0, device_build: bool = False):
+                 scene_flags: int = 0, refill_lanes: int = 0, bvh_threads: int = 0, device_build: bool = False,
+                 topology: bool = True):
         """devices: the GPUs that hold the scene (default [device]); the BVH is built and flattened once and
         uploaded to each, and render_gpu() then splits the samples over them (rrs_render_multi).
         scene_flags / refill_lanes: RrsSceneDesc.flags / .refill_lanes (measurement switches).
-        device_build: build the reference tree on the GPU (rrs_bvh_build, the same tree) instead of on the host."""
+        device_build: build the reference tree on the GPU (rrs_bvh_build, the same tree) instead of on the host.
+        topology: keep the oracle-format dump of the tree (flat()[3:5]); tests need it, a renderer does not."""
         lib = _ffi.host_lib()
         flat = []
         for o in objects:
@@ -278,7 +279,7 @@ class Scene:
                                     t.emis.ctypes.data if t.emis.size else None, t.emis.shape[0], heuristic.kind,
                                     heuristic.splits, h.ctypes.data, hdri.width, hdri.height, float(z_near),
                                     float(z_far), int(device), int(with_f64), int(upload), int(scene_flags),
-                                    int(refill_lanes), int(bvh_threads), devs, len(self.devices), int(device_build))
+                                    int(refill_lanes), int(bvh_threads), devs, len(self.devices), int(device_build), int(topology))
         if not self._p:
             raise ValueError(lib.rrh_last_error().decode())
         info = (C.c_uint64 * 7)()

@@ -295,15 +295,21 @@ __global__ void k_root(const Box6* __restrict__ root_box, uint32_t n, OutNode* _
     }
 }
 
-struct Scratch {  // freed on every return path
-    std::vector<void*> ptrs;
-    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+// One device allocation carved into the build's arrays (two dozen cudaMallocs of a few hundred MB each cost more than
+// the build itself); freed on every return path.
+struct Arena {
+    char* base = nullptr;
+    size_t size = 0, used = 0;
+    ~Arena() { if (base) cudaFree(base); }
     template <typename T>
-    cudaError_t alloc(T** p, size_t count) {
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), sizeof(T) * std::max<size_t>(count, 1));
-        if (e == cudaSuccess) ptrs.push_back(*p);
-        return e;
+    size_t reserve(size_t count) {  // first pass: sizes only
+        size = (size + 255) & ~(size_t)255;
+        size_t off = size;
+        size += sizeof(T) * std::max<size_t>(count, 1);
+        return off;
     }
+    template <typename T>
+    T* at(size_t off) const { return reinterpret_cast<T*>(base + off); }
 };
 
 #define BUILD_CHECK(expr)                                                                              \
@@ -334,67 +340,61 @@ extern "C" int rrs_bvh_build(const double* boxes, uint32_t n, uint32_t heuristic
     if (!(prop.major == 10 && prop.minor == 0)) return api_fail(RRS_ERR_NO_DEVICE, "device is not sm_100: kernels are built for sm_100a only");
     BUILD_CHECK(cudaSetDevice(device));
 
-    Scratch mem;
-    Box6 *d_boxes, *d_nb, *d_pre, *d_suf, *d_root;
-    uint32_t *d_order, *d_order2, *d_pos, *d_pos2, *d_rank, *d_rank_sorted, *d_rank_tmp, *d_unique, *d_nruns;
-    unsigned long long *d_keys, *d_keys2;
-    double* d_key;
-    int32_t* d_node_of;
-    uint32_t* d_flag;
-    Cand *d_cand, *d_best;
-    Active *d_act, *d_next;
-    OutNode* d_out;
-    Counters* d_cnt;
+    Arena mem;
     const size_t max_nodes = 2 * (size_t)n + 2;
-    BUILD_CHECK(mem.alloc(&d_boxes, n));
-    BUILD_CHECK(mem.alloc(&d_nb, n));
-    BUILD_CHECK(mem.alloc(&d_pre, n));
-    BUILD_CHECK(mem.alloc(&d_suf, n));
-    BUILD_CHECK(mem.alloc(&d_root, 1));
-    BUILD_CHECK(mem.alloc(&d_order, n));
-    BUILD_CHECK(mem.alloc(&d_order2, n));
-    BUILD_CHECK(mem.alloc(&d_pos, n));
-    BUILD_CHECK(mem.alloc(&d_pos2, n));
-    BUILD_CHECK(mem.alloc(&d_rank, n));
-    BUILD_CHECK(mem.alloc(&d_rank_sorted, n));
-    BUILD_CHECK(mem.alloc(&d_rank_tmp, n));
-    BUILD_CHECK(mem.alloc(&d_unique, n));
-    BUILD_CHECK(mem.alloc(&d_nruns, 1));
-    BUILD_CHECK(mem.alloc(&d_keys, n));
-    BUILD_CHECK(mem.alloc(&d_keys2, n));
-    BUILD_CHECK(mem.alloc(&d_key, n));
-    BUILD_CHECK(mem.alloc(&d_node_of, n));
-    BUILD_CHECK(mem.alloc(&d_flag, n));
-    BUILD_CHECK(mem.alloc(&d_cand, n));
-    BUILD_CHECK(mem.alloc(&d_best, (size_t)n + 1));
-    BUILD_CHECK(mem.alloc(&d_act, n / 5 + 2));
-    BUILD_CHECK(mem.alloc(&d_next, n / 5 + 2));
-    BUILD_CHECK(mem.alloc(&d_out, max_nodes));
-    BUILD_CHECK(mem.alloc(&d_cnt, 1));
+    const size_t o_boxes = mem.reserve<Box6>(n), o_nb = mem.reserve<Box6>(n), o_pre = mem.reserve<Box6>(n), o_suf = mem.reserve<Box6>(n);
+    const size_t o_root = mem.reserve<Box6>(1);
+    const size_t o_order = mem.reserve<uint32_t>(n), o_order2 = mem.reserve<uint32_t>(n), o_pos = mem.reserve<uint32_t>(n), o_pos2 = mem.reserve<uint32_t>(n);
+    const size_t o_rank = mem.reserve<uint32_t>(n), o_rank_sorted = mem.reserve<uint32_t>(n), o_rank_tmp = mem.reserve<uint32_t>(n);
+    const size_t o_unique = mem.reserve<uint32_t>(n), o_nruns = mem.reserve<uint32_t>(1);
+    const size_t o_keys = mem.reserve<unsigned long long>(n), o_keys2 = mem.reserve<unsigned long long>(n), o_key = mem.reserve<double>(n);
+    const size_t o_node_of = mem.reserve<int32_t>(n), o_flag = mem.reserve<uint32_t>(n);
+    const size_t o_cand = mem.reserve<Cand>(n), o_best = mem.reserve<Cand>((size_t)n + 1);
+    const size_t o_act = mem.reserve<Active>(n / 5 + 2), o_next = mem.reserve<Active>(n / 5 + 2);
+    const size_t o_out = mem.reserve<OutNode>(max_nodes), o_cnt = mem.reserve<Counters>(1);
 
-    // CUB scratch, sized once for the largest call
+    // CUB scratch, sized once for the largest call (size queries only read the pointer TYPES)
     size_t tmp_bytes = 0, b = 0;
     typedef thrust::reverse_iterator<const uint32_t*> RevKey;
     typedef thrust::reverse_iterator<const Box6*> RevIn;
     typedef thrust::reverse_iterator<Box6*> RevOut;
-    cub::DeviceRadixSort::SortPairs(nullptr, b, d_keys, d_keys2, d_pos, d_pos2, n, 0, 64);
-    tmp_bytes = std::max(tmp_bytes, b);
-    cub::DeviceRadixSort::SortPairs(nullptr, b, d_rank_tmp, d_rank_sorted, d_pos2, d_pos, n, 0, 32);
-    tmp_bytes = std::max(tmp_bytes, b);
-    cub::DeviceScan::InclusiveSum(nullptr, b, d_flag, d_rank, n);
-    tmp_bytes = std::max(tmp_bytes, b);
-    cub::DeviceScan::InclusiveScanByKey(nullptr, b, (const uint32_t*)d_rank, (const Box6*)d_nb, d_pre, BoxUnion(), n);
-    tmp_bytes = std::max(tmp_bytes, b);
-    cub::DeviceScan::InclusiveScanByKey(nullptr, b, RevKey(d_rank + n), RevIn(d_nb + n), RevOut(d_suf + n), BoxUnion(), n);
-    tmp_bytes = std::max(tmp_bytes, b);
-    cub::DeviceReduce::ReduceByKey(nullptr, b, (const uint32_t*)d_rank, d_unique, (const Cand*)d_cand, d_best, d_nruns, CandMin(), n);
-    tmp_bytes = std::max(tmp_bytes, b);
+    {
+        unsigned long long* k64 = nullptr;
+        uint32_t* u32 = nullptr;
+        Box6* bx = nullptr;
+        Cand* cd = nullptr;
+        cub::DeviceRadixSort::SortPairs(nullptr, b, k64, k64, u32, u32, n, 0, 64);
+        tmp_bytes = std::max(tmp_bytes, b);
+        cub::DeviceRadixSort::SortPairs(nullptr, b, u32, u32, u32, u32, n, 0, 32);
+        tmp_bytes = std::max(tmp_bytes, b);
+        cub::DeviceScan::InclusiveSum(nullptr, b, u32, u32, n);
+        tmp_bytes = std::max(tmp_bytes, b);
+        cub::DeviceScan::InclusiveScanByKey(nullptr, b, (const uint32_t*)u32, (const Box6*)bx, bx, BoxUnion(), n);
+        tmp_bytes = std::max(tmp_bytes, b);
+        cub::DeviceScan::InclusiveScanByKey(nullptr, b, RevKey(u32), RevIn(bx), RevOut(bx), BoxUnion(), n);
+        tmp_bytes = std::max(tmp_bytes, b);
+        cub::DeviceReduce::ReduceByKey(nullptr, b, (const uint32_t*)u32, u32, (const Cand*)cd, cd, u32, CandMin(), n);
+        tmp_bytes = std::max(tmp_bytes, b);
+    }
     Box6 init_box;
     for (int k = 0; k < 3; ++k) { init_box.v[2 * k] = INFINITY; init_box.v[2 * k + 1] = -INFINITY; }
-    cub::DeviceReduce::Reduce(nullptr, b, (const Box6*)d_boxes, d_root, n, BoxUnion(), init_box);
+    cub::DeviceReduce::Reduce(nullptr, b, (const Box6*)nullptr, (Box6*)nullptr, n, BoxUnion(), init_box);
     tmp_bytes = std::max(tmp_bytes, b);
-    void* d_tmp = nullptr;
-    BUILD_CHECK(mem.alloc(reinterpret_cast<char**>(&d_tmp), tmp_bytes));
+    const size_t o_tmp = mem.reserve<char>(tmp_bytes);
+    BUILD_CHECK(cudaMalloc(&mem.base, mem.size));
+    Box6 *d_boxes = mem.at<Box6>(o_boxes), *d_nb = mem.at<Box6>(o_nb), *d_pre = mem.at<Box6>(o_pre), *d_suf = mem.at<Box6>(o_suf), *d_root = mem.at<Box6>(o_root);
+    uint32_t *d_order = mem.at<uint32_t>(o_order), *d_order2 = mem.at<uint32_t>(o_order2), *d_pos = mem.at<uint32_t>(o_pos), *d_pos2 = mem.at<uint32_t>(o_pos2);
+    uint32_t *d_rank = mem.at<uint32_t>(o_rank), *d_rank_sorted = mem.at<uint32_t>(o_rank_sorted), *d_rank_tmp = mem.at<uint32_t>(o_rank_tmp);
+    uint32_t *d_unique = mem.at<uint32_t>(o_unique), *d_nruns = mem.at<uint32_t>(o_nruns);
+    unsigned long long *d_keys = mem.at<unsigned long long>(o_keys), *d_keys2 = mem.at<unsigned long long>(o_keys2);
+    double* d_key = mem.at<double>(o_key);
+    int32_t* d_node_of = mem.at<int32_t>(o_node_of);
+    uint32_t* d_flag = mem.at<uint32_t>(o_flag);
+    Cand *d_cand = mem.at<Cand>(o_cand), *d_best = mem.at<Cand>(o_best);
+    Active *d_act = mem.at<Active>(o_act), *d_next = mem.at<Active>(o_next);
+    OutNode* d_out = mem.at<OutNode>(o_out);
+    Counters* d_cnt = mem.at<Counters>(o_cnt);
+    void* d_tmp = mem.at<char>(o_tmp);
 
     cudaEvent_t ev0, ev1;
     cudaEventCreate(&ev0);

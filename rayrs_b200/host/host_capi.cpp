@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "mesh_io.hpp"
@@ -50,31 +51,40 @@ const char* rrh_last_error(void) { return g_err.c_str(); }
 void* rrh_scene_new(const double* objs, uint64_t n_obj, const double* mats, uint64_t n_mat, const double* emis,
                     uint64_t n_emis, int heuristic, uint32_t splits, const double* hdri, uint64_t hw, uint64_t hh,
                     double tmin, double tmax, int device, int with_f64, int upload, uint32_t scene_flags,
-                    uint32_t refill_lanes, int bvh_threads, const int* devices, int n_devices, int device_build) {
+                    uint32_t refill_lanes, int bvh_threads, const int* devices, int n_devices, int device_build, int topology) {
     try {
         std::vector<Material> mt;
         for (uint64_t i = 0; i < n_mat; ++i) mt.push_back(material_from_row(mats + 12 * i));
         std::vector<Emission> em;
         for (uint64_t i = 0; i < n_emis; ++i)
             em.push_back(Emission::Emissive(emis[4 * i], Vec3(emis[4 * i + 1], emis[4 * i + 2], emis[4 * i + 3])));
-        std::vector<Object> objects;
-        objects.reserve(n_obj);
-        for (uint64_t i = 0; i < n_obj; ++i) {
-            const double* r = objs + 12 * i;
-            int mi = (int)r[1], ei = (int)r[2];
-            if (mi < 0 || (uint64_t)mi >= n_mat) throw Panic("object material index out of range");
-            if (ei >= (int)n_emis) throw Panic("object emission index out of range");
-            Emission e = ei < 0 ? Emission::Dark() : em[ei];
-            switch ((int)r[0]) {
-                case 0: objects.push_back(Object::sphere(r[3], Vec3(r[4], r[5], r[6]), mt[mi], e)); break;
-                case 1: objects.push_back(Object::plane((Axis)(int)r[3], r[4], r[5], r[6], r[7], r[8], mt[mi], e)); break;
-                case 2:
-                    objects.push_back(Object::triangle(Vec3(r[3], r[4], r[5]), Vec3(r[6], r[7], r[8]),
-                                                       Vec3(r[9], r[10], r[11]), mt[mi], e));
-                    break;
-                default: throw Panic("unknown object type");
+        // one Object per table row; rows are independent, so large meshes are converted on all host threads
+        std::vector<Object> objects(n_obj);
+        std::mutex err_mu;
+        std::string err;
+        parallel_chunks(n_obj, 1 << 16, [&](size_t lo, size_t hi) {
+            try {
+                for (size_t i = lo; i < hi; ++i) {
+                    const double* r = objs + 12 * i;
+                    int mi = (int)r[1], ei = (int)r[2];
+                    if (mi < 0 || (uint64_t)mi >= n_mat) throw Panic("object material index out of range");
+                    if (ei >= (int)n_emis) throw Panic("object emission index out of range");
+                    Emission e = ei < 0 ? Emission::Dark() : em[ei];
+                    switch ((int)r[0]) {
+                        case 0: objects[i] = Object::sphere(r[3], Vec3(r[4], r[5], r[6]), mt[mi], e); break;
+                        case 1: objects[i] = Object::plane((Axis)(int)r[3], r[4], r[5], r[6], r[7], r[8], mt[mi], e); break;
+                        case 2:
+                            objects[i] = Object::triangle(Vec3(r[3], r[4], r[5]), Vec3(r[6], r[7], r[8]), Vec3(r[9], r[10], r[11]), mt[mi], e);
+                            break;
+                        default: throw Panic("unknown object type");
+                    }
+                }
+            } catch (const std::exception& ex) {
+                std::lock_guard<std::mutex> g(err_mu);
+                if (err.empty()) err = ex.what();
             }
-        }
+        });
+        if (!err.empty()) throw Panic(err);
         Image img;
         img.width = hw;
         img.height = hh;
@@ -89,6 +99,7 @@ void* rrh_scene_new(const double* objs, uint64_t n_obj, const double* mats, uint
         opt.refill_lanes = refill_lanes;
         opt.bvh_threads = bvh_threads;
         opt.device_build = device_build != 0;
+        opt.topology = topology != 0;
         return new Scene(objects, tmin, tmax, h, img, opt);
     } catch (const std::exception& e) {
         g_err = e.what();

@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <future>
 #include <limits>
 #include <mutex>
@@ -504,26 +505,27 @@ struct Flattener {
     }
 
     // reference of a child as seen from its parent (whose own box is `parent_box`)
-    void attach(uint32_t node, int ch, int32_t b, const AxisAlignedBoundingBox& parent_box,
-                const std::vector<int32_t>& flat_index) {
+    // returns 1 when the child was a dead node (dropped), else 0
+    uint32_t attach(uint32_t node, int ch, int32_t b, const AxisAlignedBoundingBox& parent_box,
+                    const std::vector<int32_t>& flat_index) {
         const BNode& c = bn[b];
         if (c.kind == 2) {
             // bare LeafNode: no box in the reference; cull with the primitive's own box when
             // that box is a real volume, else with the parent's
             const AxisAlignedBoundingBox* fb = c.box.degenerate() ? &parent_box : &c.box;
             set_child(node, ch, RRS_MAKE_LEAF(c.first, 1), true, &c.box, fb);
-            return;
+            return 0;
         }
         if (c.box.degenerate()) {  // slab test can never accept a zero-extent box
-            out.dead_nodes++;
             set_child(node, ch, RRS_REF_EMPTY, false, nullptr, nullptr);
-            return;
+            return 1;
         }
         if (c.kind == 1) {
             set_child(node, ch, RRS_MAKE_LEAF(c.first, c.count), false, &c.box, &c.box);
-            return;
+            return 0;
         }
         set_child(node, ch, (uint32_t)flat_index[b], false, &c.box, &c.box);
+        return 0;
     }
 };
 
@@ -548,7 +550,7 @@ void dump_topology(const std::vector<BNode>& bn, int32_t b, const std::vector<ui
 }  // namespace
 
 FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, uint32_t bfs_nodes, int threads,
-                   BvhBuildTiming* timing, int build_device) {
+                   BvhBuildTiming* timing, int build_device, bool want_topology) {
     if (objects.empty()) throw Panic("Having a BVH for 0 objects does not make sense");
     if (heuristic.kind == BvhHeuristic::kSah && heuristic.splits < 2) throw Panic("Sah needs at least 2 splits");
     const size_t n = objects.size();
@@ -560,10 +562,12 @@ FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, u
     };
     std::vector<AxisAlignedBoundingBox> boxes(n);
     std::vector<Vec3> centers(n);
-    for (size_t i = 0; i < n; ++i) {
-        boxes[i] = objects[i].bbox();
-        centers[i] = boxes[i].center();  // BvhData::new bvh.rs:87-98
-    }
+    parallel_chunks(n, 1 << 16, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            boxes[i] = objects[i].bbox();
+            centers[i] = boxes[i].center();  // BvhData::new bvh.rs:87-98
+        }
+    });
     lap(&BvhBuildTiming::boxes);
     FlatBvh out;
     out.prim_order.resize(n);
@@ -573,27 +577,26 @@ FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, u
     if (build_device >= 0) {
         // the same tree from the GPU (csrc/bvh_build.cu); its records are the builder's BNodes
         static_assert(sizeof(AxisAlignedBoundingBox) == 6 * sizeof(double), "boxes are handed over as n x 6 doubles");
-        for (size_t i = 0; i < n; ++i)
-            for (double v : {boxes[i].xmin, boxes[i].xmax, boxes[i].ymin, boxes[i].ymax, boxes[i].zmin, boxes[i].zmax})
-                if (std::isnan(v)) throw Panic("partial_cmp().unwrap() on NaN centre");  // bvh.rs:104
-        std::vector<RrsBuildNode> dn(2 * n + 2);
+        std::unique_ptr<RrsBuildNode[]> dn(new RrsBuildNode[2 * n + 2]);  // uninitialised: only n_nodes records get touched
         uint32_t n_nodes = 0;
         double dev_s = 0.;
         int rc = rrs_bvh_build(&boxes[0].xmin, (uint32_t)n, heuristic.kind == BvhHeuristic::kSah ? 1u : 0u, heuristic.splits, build_device,
-                               out.prim_order.data(), dn.data(), &n_nodes, &dev_s);
+                               out.prim_order.data(), dn.get(), &n_nodes, &dev_s);
         if (rc != RRS_OK) throw Panic(std::string("rrs_bvh_build failed: ") + rrs_last_error());
         if (timing) timing->device = dev_s;
         b.nodes.resize(n_nodes);
-        for (uint32_t i = 0; i < n_nodes; ++i) {
-            BNode& t = b.nodes[i];
-            const RrsBuildNode& s = dn[i];
-            t.box = AxisAlignedBoundingBox{s.box[0], s.box[1], s.box[2], s.box[3], s.box[4], s.box[5]};
-            t.child[0] = s.child[0];
-            t.child[1] = s.child[1];
-            t.first = s.first;
-            t.count = s.count;
-            t.kind = (uint8_t)s.kind;
-        }
+        parallel_chunks(n_nodes, 1 << 16, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) {
+                BNode& t = b.nodes[i];
+                const RrsBuildNode& s = dn[i];
+                t.box = AxisAlignedBoundingBox{s.box[0], s.box[1], s.box[2], s.box[3], s.box[4], s.box[5]};
+                t.child[0] = s.child[0];
+                t.child[1] = s.child[1];
+                t.first = s.first;
+                t.count = s.count;
+                t.kind = (uint8_t)s.kind;
+            }
+        });
         root = 0;
     } else {
         if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
@@ -653,10 +656,20 @@ FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, u
         }
         fl.set_child(0, 1, RRS_REF_EMPTY, false, nullptr, nullptr);
     }
-    for (size_t f = 1; f < flat_to_build.size(); ++f) {
-        const BNode& nd = bn[flat_to_build[f]];
-        fl.attach((uint32_t)f, 0, nd.child[0], nd.box, flat_index);
-        fl.attach((uint32_t)f, 1, nd.child[1], nd.box, flat_index);
+    {
+        // every flat node is written by exactly one iteration; dead subtrees are counted per chunk
+        std::atomic<uint32_t> dead{0};
+        parallel_chunks(flat_to_build.size() - 1, 1 << 15, [&](size_t lo, size_t hi) {
+            Flattener part{bn, out};
+            uint32_t mine = 0;
+            for (size_t f = lo + 1; f < hi + 1; ++f) {
+                const BNode& nd = bn[flat_to_build[f]];
+                mine += part.attach((uint32_t)f, 0, nd.child[0], nd.box, flat_index);
+                mine += part.attach((uint32_t)f, 1, nd.child[1], nd.box, flat_index);
+            }
+            dead += mine;
+        });
+        out.dead_nodes += dead.load();
     }
     lap(&BvhBuildTiming::flatten);
     // depth (stack bound): longest chain of flat nodes
@@ -680,7 +693,7 @@ FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, u
         out.max_depth = mx;
     }
     lap(&BvhBuildTiming::depth);
-    dump_topology(bn, root, out.prim_order, out);
+    if (want_topology) dump_topology(bn, root, out.prim_order, out);
     lap(&BvhBuildTiming::topology);
     return out;
 }
@@ -745,7 +758,7 @@ void Scene::init(const std::vector<Object>& objects, double z_near, double z_far
     require(z_far > z_near, "Scene::new: z_far must be > z_near");
     require(!opt.devices.empty(), "Scene::new: no device");
     auto t0 = std::chrono::steady_clock::now();
-    bvh_ = Bvh::build(heuristic, objects, 1023, opt.bvh_threads, &timing_, opt.device_build ? opt.devices[0] : -1);
+    bvh_ = Bvh::build(heuristic, objects, 1023, opt.bvh_threads, &timing_, opt.device_build ? opt.devices[0] : -1, opt.topology);
     build_seconds_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
     // materials / emissions: objects carry them by value (mat.clone() in lib.rs:407-415);

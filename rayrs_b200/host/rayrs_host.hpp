@@ -20,6 +20,8 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "../../include/rayrs_b200.h"
@@ -146,8 +148,9 @@ struct Bvh {
     // (0 = one per hardware thread).
     // build_device >= 0: the tree is built on that GPU (rrs_bvh_build: the same tree, level-synchronous) instead of
     // by the recursive host build; numbering and flattening are the same code either way.
+    // want_topology: also produce the pre-order dump (FlatBvh::topology / boxes) the tests compare with the oracle's.
     static FlatBvh build(BvhHeuristic heuristic, const std::vector<Object>& objects, uint32_t bfs_nodes = 1023,
-                         int threads = 0, BvhBuildTiming* timing = nullptr, int build_device = -1);
+                         int threads = 0, BvhBuildTiming* timing = nullptr, int build_device = -1, bool want_topology = true);
 };
 
 struct Image {
@@ -179,7 +182,22 @@ struct SceneOptions {
     uint32_t refill_lanes = 0;    // 0 = library default
     int bvh_threads = 0;          // 0 = one per hardware thread
     bool device_build = false;    // build the BVH on devices[0] (rrs_bvh_build) instead of on the host
+    bool topology = true;         // keep the oracle-format dump of the tree (tests); a renderer does not need it
 };
+
+// f(begin, end) over [0, n) on up to one thread per hardware thread (chunks of at least min_chunk items)
+template <typename F>
+void parallel_chunks(size_t n, size_t min_chunk, F f) {
+    size_t threads = std::max<size_t>(1, std::thread::hardware_concurrency());
+    threads = std::min(threads, std::max<size_t>(1, n / std::max<size_t>(1, min_chunk)));
+    if (threads <= 1) {
+        f((size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < threads; ++t) pool.emplace_back([=]() { f(n * t / threads, n * (t + 1) / threads); });
+    for (auto& th : pool) th.join();
+}
 
 class Scene {
 public:

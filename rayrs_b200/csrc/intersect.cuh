@@ -313,12 +313,15 @@ __device__ __forceinline__ void trav_node_step(const DScene& sc, const RayK& r, 
     // Slab test as geometry.rs:458-513 writes it: the near/far plane is chosen by the sign of
     // 1/d (not by min/max of the two products), and max/min drop NaNs — so a ray lying in a
     // face plane of the box (0 * inf = NaN) is simply not constrained by that axis.
-    const float2 ax = __half22float2(u32_as_half2(prmt(w[0], r.selx)));  // (near, far) planes
-    const float2 ay = __half22float2(u32_as_half2(prmt(w[1], r.sely)));
-    const float2 az = __half22float2(u32_as_half2(prmt(w[2], r.selz)));
-    const float2 bx = __half22float2(u32_as_half2(prmt(w[3], r.selx)));
-    const float2 by = __half22float2(u32_as_half2(prmt(w[4], r.sely)));
-    const float2 bz = __half22float2(u32_as_half2(prmt(w[5], r.selz)));
+    // (selectors rebuilt here from the sign bits of 1/d — three registers fewer per ray — measured +-0:
+    // profiles/ab_logs/ab_r02l_regs.log)
+    const uint32_t selx = r.selx, sely = r.sely, selz = r.selz;
+    const float2 ax = __half22float2(u32_as_half2(prmt(w[0], selx)));  // (near, far) planes
+    const float2 ay = __half22float2(u32_as_half2(prmt(w[1], sely)));
+    const float2 az = __half22float2(u32_as_half2(prmt(w[2], selz)));
+    const float2 bx = __half22float2(u32_as_half2(prmt(w[3], selx)));
+    const float2 by = __half22float2(u32_as_half2(prmt(w[4], sely)));
+    const float2 bz = __half22float2(u32_as_half2(prmt(w[5], selz)));
     const float3 o = r.o;
     float ax0 = (ax.x - o.x) * idir.x, ax1 = (ax.y - o.x) * idir.x;
     float ay0 = (ay.x - o.y) * idir.y, ay1 = (ay.y - o.y) * idir.y;
@@ -385,6 +388,13 @@ __device__ __forceinline__ void test_prim(const DScene& sc, uint32_t pi, float4 
     }
 }
 
+// Software pipelining of the leaf loop (record k + 1 fetched while record k is tested) held 12 more registers across
+// the primitive test; without it the kernel spills less and runs 4 % faster on configurations 4 and 5
+// (profiles/ab_logs/ab_r02k_leafpf.log) — the opposite of round 1's measurement, taken before the kernel was this
+// close to its register limit.
+#ifndef RRS_LEAF_PREFETCH
+#define RRS_LEAF_PREFETCH 0
+#endif
 // One leaf run (1..4 primitives, DFS order), then pop.  org64: the f64 origin slot of THIS ray in the queue (SPH64).
 template <bool COUNT, bool SPH64>
 __device__ __forceinline__ void trav_leaf_step(const DScene& sc, const RayK& r, Trav& tv, const SStack& stack,
@@ -397,14 +407,15 @@ __device__ __forceinline__ void trav_leaf_step(const DScene& sc, const RayK& r, 
     RRS_CHECK(first + count <= sc.n_prims && tv.sp >= 1u);
     ldg256(sc.prims + first, a, b);
     ldg256(reinterpret_cast<const char*>(sc.prims + first) + 32, c, pad);
+    // the shear rows are rebuilt per leaf visit (~3.5 per ray) instead of living in 6 registers for the
+    // whole traversal (~30 node steps per ray); they overlap the first fetch
     const float3 o = r.o, d = r.d;
     const uint32_t origin_word = r.origin_word;
     const uint32_t origin_prim = origin_word == RRS_NO_PRIM ? RRS_NO_PRIM : (origin_word & RRS_PRIM_MASK);
     const double* o64 = (SPH64 && origin_word != RRS_NO_PRIM && (origin_word & RRS_ORG64)) ? org64 : nullptr;
-    // the shear rows are rebuilt per leaf visit (~3.5 per ray) instead of living in 6 registers for the
-    // whole traversal (~30 node steps per ray); they overlap the first fetch
     RayProj proj;
     if (sc.has_triangles) proj = make_proj(d);
+#if RRS_LEAF_PREFETCH
     for (uint32_t k = 0; k < count; ++k) {
         const uint32_t pi = first + k;
         float4 na = a, nb = b, nc = c;
@@ -418,6 +429,15 @@ __device__ __forceinline__ void trav_leaf_step(const DScene& sc, const RayK& r, 
         b = nb;
         c = nc;
     }
+#else
+    for (uint32_t pi = first, end = first + count;;) {
+        if (COUNT) cnt.prims++;
+        test_prim<SPH64>(sc, pi, a, b, c, o, d, proj, origin_prim, o64, tv.tbest, tv.best);
+        if (++pi == end) break;
+        ldg256(sc.prims + pi, a, b);
+        ldg256(reinterpret_cast<const char*>(sc.prims + pi) + 32, c, pad);
+    }
+#endif
     --tv.sp;
     tv.cur = stack.get(tv.sp);
 }

@@ -275,24 +275,24 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
     tv.sp = 1;
     tv.tbest = 0.f;
     tv.best = RRS_NO_PRIM;
-    bool has_ray = false, exhausted = false;
-    uint32_t my_i = 0;
+    bool exhausted = false;
+    constexpr uint32_t kNoRay = 0xFFFFFFFFu;
+    uint32_t my_i = kNoRay;  // queue slot of the lane's ray; kNoRay while the lane is idle
     for (;;) {
         // ---- refill ----
-        uint32_t idle = __ballot_sync(FULL, !has_ray);
+        uint32_t idle = __ballot_sync(FULL, my_i == kNoRay);
         if (!exhausted && (uint32_t)__popc(idle) >= sc.refill_lanes) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(s_cursor, (uint32_t)__popc(idle));
             base = __shfl_sync(FULL, base, 0);
             exhausted = base + (uint32_t)__popc(idle) >= n;
             const uint32_t i = base + (uint32_t)__popc(idle & lt_mask);
-            if (!has_ray && i < n) {
+            if (my_i == kNoRay && i < n) {
                 float4 o4 = ldq(ray_o + i), d4 = ldq(ray_d + i);
                 trav_begin(sc, xyz(o4), xyz(d4), __float_as_uint(o4.w), stack, r, tv);
-                has_ray = true;
                 my_i = i;
             }
-            idle = __ballot_sync(FULL, !has_ray);
+            idle = __ballot_sync(FULL, my_i == kNoRay);
         }
         if (idle == FULL) {
             if (exhausted) break;
@@ -313,9 +313,9 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
         // ---- leaves ----
         if (!trav_on_inner(tv) && tv.cur != TRAV_DONE)
             trav_leaf_step<COUNT, SPH64>(sc, r, tv, stack, (SPH64 && q.org64) ? q.org64 + 3 * (off + my_i) : nullptr, cnt);
-        if (has_ray && tv.cur == TRAV_DONE) {
+        if (my_i != kNoRay && tv.cur == TRAV_DONE) {  // finished (in a node step or in the leaf step)
             stq(hits + my_i, make_float2(tv.tbest, __uint_as_float(tv.best)));
-            has_ray = false;
+            my_i = kNoRay;
         }
     }
     flush_trav_counters<COUNT>(c, cnt);

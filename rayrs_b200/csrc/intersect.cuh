@@ -141,22 +141,27 @@ struct RayProj {
     float3 P, Q;
 };
 __device__ __forceinline__ RayProj make_proj(float3 d) {
-    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-    const int kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
-    int kx = kz == 2 ? 0 : kz + 1;
-    int ky = kx == 2 ? 0 : kx + 1;
-    const float dz = kz == 0 ? d.x : (kz == 1 ? d.y : d.z);
-    if (dz < 0.f) {  // preserve winding
-        int t = kx;
-        kx = ky;
-        ky = t;
-    }
-    const float sz = 1.0f / dz;
-    const float sx = (kx == 0 ? d.x : (kx == 1 ? d.y : d.z)) * sz;
-    const float sy = (ky == 0 ? d.x : (ky == 1 ? d.y : d.z)) * sz;
+    // kz = the dominant axis of d, (kx, ky) = the next two axes cyclically, swapped when d[kz] < 0 (winding);
+    // P = e_kx - (d[kx] / d[kz]) e_kz, Q = e_ky - (d[ky] / d[kz]) e_kz.  Written as one short arm per dominant axis
+    // (a dozen instructions each, a warp takes at most three) instead of per-component selects (95 instructions).
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
     RayProj r;
-    r.P = f3(kx == 0 ? 1.f : (kz == 0 ? -sx : 0.f), kx == 1 ? 1.f : (kz == 1 ? -sx : 0.f), kx == 2 ? 1.f : (kz == 2 ? -sx : 0.f));
-    r.Q = f3(ky == 0 ? 1.f : (kz == 0 ? -sy : 0.f), ky == 1 ? 1.f : (kz == 1 ? -sy : 0.f), ky == 2 ? 1.f : (kz == 2 ? -sy : 0.f));
+    if (ax > ay && ax > az) {         // kz = 0: (kx, ky) = (1, 2)
+        const float sz = 1.0f / d.x, a = -d.y * sz, b = -d.z * sz;
+        const float3 u = f3(a, 1.f, 0.f), v = f3(b, 0.f, 1.f);
+        r.P = d.x < 0.f ? v : u;
+        r.Q = d.x < 0.f ? u : v;
+    } else if (!(ax > ay) && ay > az) {  // kz = 1: (kx, ky) = (2, 0)
+        const float sz = 1.0f / d.y, a = -d.z * sz, b = -d.x * sz;
+        const float3 u = f3(0.f, a, 1.f), v = f3(1.f, b, 0.f);
+        r.P = d.y < 0.f ? v : u;
+        r.Q = d.y < 0.f ? u : v;
+    } else {                          // kz = 2: (kx, ky) = (0, 1)
+        const float sz = 1.0f / d.z, a = -d.x * sz, b = -d.y * sz;
+        const float3 u = f3(1.f, 0.f, a), v = f3(0.f, 1.f, b);
+        r.P = d.z < 0.f ? v : u;
+        r.Q = d.z < 0.f ? u : v;
+    }
     return r;
 }
 __device__ __forceinline__ float proj3(float3 p, float3 v) {  // fixed association: part of the watertightness argument
@@ -262,8 +267,14 @@ struct SStack {
 // (2) origin / direction / origin word parked in shared memory behind the stack and fetched back per leaf visit
 // (9 registers fewer in the node loop): -15 % (ab_r02b_fma.log, ab_r02f_hybrid.log).  The traversal is bound by the
 // latency of its scattered node fetches at 8 warps per scheduler, not by its instruction count.
+#ifndef RRS_TRAV_FMA
+#define RRS_TRAV_FMA 0
+#endif
 struct RayK {
     float3 o, d, idir;
+#if RRS_TRAV_FMA
+    float3 an, af;  // -(o/d) -/+ 2^-21 |o/d|: t_near = fma(plane, 1/d, an), t_far = fma(plane, 1/d, af)
+#endif
     uint32_t selx, sely, selz;  // PRMT selectors: (near, far) = (lo, hi) or (hi, lo) by the sign of 1/d
     uint32_t origin_word;       // RRS_NO_PRIM, or primitive index | RRS_ORG64 (the ray carries an f64 origin)
 };
@@ -287,6 +298,14 @@ __device__ __forceinline__ void trav_begin(const DScene& sc, float3 o, float3 d,
     r.d = d;
     r.idir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     r.origin_word = origin_word;
+#if RRS_TRAV_FMA
+    {
+        const float3 op = f3(o.x * r.idir.x, o.y * r.idir.y, o.z * r.idir.z);
+        const float k = 4.76837158e-7f;  // 2^-21
+        r.an = f3(-op.x - fabsf(op.x) * k, -op.y - fabsf(op.y) * k, -op.z - fabsf(op.z) * k);
+        r.af = f3(-op.x + fabsf(op.x) * k, -op.y + fabsf(op.y) * k, -op.z + fabsf(op.z) * k);
+    }
+#endif
     r.selx = r.idir.x < 0.f ? 0x1032u : 0x3210u;
     r.sely = r.idir.y < 0.f ? 0x1032u : 0x3210u;
     r.selz = r.idir.z < 0.f ? 0x1032u : 0x3210u;
@@ -322,6 +341,15 @@ __device__ __forceinline__ void trav_node_step(const DScene& sc, const RayK& r, 
     const float2 bx = __half22float2(u32_as_half2(prmt(w[3], selx)));
     const float2 by = __half22float2(u32_as_half2(prmt(w[4], sely)));
     const float2 bz = __half22float2(u32_as_half2(prmt(w[5], selz)));
+#if RRS_TRAV_FMA
+    const float3 an = r.an, af = r.af;
+    float ax0 = fmaf(ax.x, idir.x, an.x), ax1 = fmaf(ax.y, idir.x, af.x);
+    float ay0 = fmaf(ay.x, idir.y, an.y), ay1 = fmaf(ay.y, idir.y, af.y);
+    float az0 = fmaf(az.x, idir.z, an.z), az1 = fmaf(az.y, idir.z, af.z);
+    float bx0 = fmaf(bx.x, idir.x, an.x), bx1 = fmaf(bx.y, idir.x, af.x);
+    float by0 = fmaf(by.x, idir.y, an.y), by1 = fmaf(by.y, idir.y, af.y);
+    float bz0 = fmaf(bz.x, idir.z, an.z), bz1 = fmaf(bz.y, idir.z, af.z);
+#else
     const float3 o = r.o;
     float ax0 = (ax.x - o.x) * idir.x, ax1 = (ax.y - o.x) * idir.x;
     float ay0 = (ay.x - o.y) * idir.y, ay1 = (ay.y - o.y) * idir.y;
@@ -329,6 +357,7 @@ __device__ __forceinline__ void trav_node_step(const DScene& sc, const RayK& r, 
     float bx0 = (bx.x - o.x) * idir.x, bx1 = (bx.y - o.x) * idir.x;
     float by0 = (by.x - o.y) * idir.y, by1 = (by.y - o.y) * idir.y;
     float bz0 = (bz.x - o.z) * idir.z, bz1 = (bz.y - o.z) * idir.z;
+#endif
     float n0 = fmaxf(fmaxf(ax0, ay0), fmaxf(az0, sc.tmin));
     float f0 = fminf(fminf(ax1, ay1), fminf(az1, tv.tbest));
     float n1 = fmaxf(fmaxf(bx0, by0), fmaxf(bz0, sc.tmin));

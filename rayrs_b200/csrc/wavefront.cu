@@ -32,6 +32,8 @@ namespace rrs {
 #define RRS_BLOCK_THREADS 128
 #endif
 static constexpr int kBlock = RRS_BLOCK_THREADS;
+// (The extend and shade phases as separate, not inlined device functions — so that the register allocation of one
+// cannot cost the other spills — crash the compiler of this toolkit: nvcc 12.9 segfaults on the file.)
 // The f64 distance of the accepted triangle hit (triangle_t64, intersect.cuh) is what rrs_intersect reports.  The
 // render keeps the fp32 distance of the traversal: re-evaluating it in shade_hit would move the hit point by < 2e-6
 // relative — far below what the image can see — and it cost configuration 5 (SPH64 form, 72 registers) 4.7 %

@@ -267,7 +267,9 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
         flush_trav_counters<COUNT>(c, cnt);
         return;
     }
-    constexpr uint32_t kNodeSteps = 4;  // inner-node steps a lane takes per ballot round (swept 1..8: 3-4 best, gpurun_out/sweep_tune*.log)
+    // inner-node steps a lane takes per ballot round (round 1 swept 1..8: 3-4 best, profiles/ab_logs/sweep_tune*.log;
+    // round 2, after the register diet: 2 / 3 / 4 / 6 within +-0.5 %, ab_r02n_sweep.log)
+    constexpr uint32_t kNodeSteps = 4;
     SStack stack;
     stack.init(s_stack + threadIdx.x, blockDim.x);
     TravCounters cnt{0, 0};

@@ -13,12 +13,13 @@ queues = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
 spp_over = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 modes = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0]  # render flags: 1 count, 4 split kernels, 32 no L2 window
 scene_flags = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+refill = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 hdri = scenes.synthetic_hdri(2048, 1024)
 for key in keys:
     cfg = scenes.CONFIGS[key]
     for spec in cfg.specs():
         t0 = time.time()
-        sc = spec.scene(hdri, with_f64=False, scene_flags=scene_flags)
+        sc = spec.scene(hdri, with_f64=False, scene_flags=scene_flags, refill_lanes=refill, device_build=True, topology=False)
         print(key, spec.name, "scene build+upload %.2f s (bvh %.2f s) nodes %d depth %d" % (time.time() - t0, sc.build_seconds, sc.n_nodes, sc.max_depth), flush=True)
         cam = spec.camera()
         spp = spp_over or cfg.spp

@@ -264,17 +264,22 @@ class ClockSampler:
 # reference arm: the reference's own CPU implementation of the path, timed on the host cores.
 # The Rust crate cannot be built in this image (no cargo/rustc), so it is the oracle port.
 # ---------------------------------------------------------------------------------------------
-def cpu_render_sample(cfg, specs, hdri, spp, threads):
+def cpu_scenes(specs, hdri):
+    """The oracle's scenes of a workload, built ONCE (the restated reference build of the 4M-triangle tree takes about a
+    minute; like the reference's own timer, main.rs:59-100, the samples below time the tile loop only)."""
+    import oracle
+    return [(spec, oracle.OracleScene(spec.tables(), hdri.pixels, heuristic=(spec.heuristic.kind, spec.heuristic.splits), build_mode=1),
+             oracle.camera_new(**spec.camera_args)) for spec in specs]
+
+
+def cpu_render_sample(cfg, scenes_, spp, threads):
     """Render every scene of the workload at `spp` samples with the oracle; returns (rays, seconds)."""
     import oracle
     rays, secs = 0, 0.0
-    for spec in specs:
-        osc = oracle.OracleScene(spec.tables(), hdri.pixels, heuristic=(spec.heuristic.kind, spec.heuristic.splits), build_mode=1)
-        cam17 = oracle.camera_new(**spec.camera_args)
+    for spec, osc, cam17 in scenes_:
         _, st = osc.render(cam17, cfg.width, cfg.height, spp, max_bounces=cfg.max_bounces, rng_mode=oracle.RNG_WIDE, nthreads=threads)
         rays += st["rays"]
         secs += st["seconds"]  # the tile loop only, like rayrs/src/main.rs:59-100
-        osc.close()
     return rays, secs
 
 
@@ -289,15 +294,16 @@ def run_reference(args):
     specs = cfg.specs()
     hdri = scenes.synthetic_hdri(2048, 1024)
     threads = oracle.hardware_threads()
+    osc = cpu_scenes(specs, hdri)
     # size the per-step sample from a 1-spp probe so that the whole run ends within a few minutes
-    r1, s1 = cpu_render_sample(cfg, specs, hdri, 1, threads)
+    r1, s1 = cpu_render_sample(cfg, osc, 1, threads)
     budget = args.ref_seconds / max(1, args.steps + args.warmup)
     spp = int(max(1, min(cfg.spp, budget / max(s1, 1e-3))))
     for _ in range(args.warmup):
-        cpu_render_sample(cfg, specs, hdri, spp, threads)
+        cpu_render_sample(cfg, osc, spp, threads)
     rays, secs = 0, 0.0
     for _ in range(args.steps):
-        r, s = cpu_render_sample(cfg, specs, hdri, spp, threads)
+        r, s = cpu_render_sample(cfg, osc, spp, threads)
         rays += r
         secs += s
     value = rays / secs / 1e6
@@ -531,9 +537,10 @@ def run_ours(args):
             import oracle  # cpu_baseline leg: the one place bench.py may execute oracle/
             oracle.build()
             threads = oracle.hardware_threads()
-            r1, s1 = cpu_render_sample(cfg, specs, hdri, 1, threads)
+            osc = cpu_scenes(specs, hdri)
+            r1, s1 = cpu_render_sample(cfg, osc, 1, threads)
             s_spp = int(max(1, min(cfg.spp, args.cpu_seconds / max(s1, 1e-3))))
-            r, s = cpu_render_sample(cfg, specs, hdri, s_spp, threads) if s_spp > 1 else (r1, s1)
+            r, s = cpu_render_sample(cfg, osc, s_spp, threads) if s_spp > 1 else (r1, s1)
             cpu = {"value": r / s / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{args.workload}: all {len(specs)} scene(s) at {W}x{H}, {s_spp} of {cfg.spp} spp, {r} rays in {s:.1f} s"}
         cam_bytes = (len(bytes(_ffi.RrsCamera())) + len(bytes(_ffi.RrsRenderParams()))) * len(built)

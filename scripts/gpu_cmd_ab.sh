@@ -5,7 +5,7 @@ cp rayrs_b200/librayrs_b200.so /tmp/keep.so
 for round in 1 2; do
 for v in "$@"; do
 cp _variants/lib_$v.so rayrs_b200/librayrs_b200.so
-python scripts/gpu_dev.py $CFG 0 $SPP 0 2>&1 | grep -v "scene build" | sed "s/^/[$v] /"
+timeout 120 python scripts/gpu_dev.py $CFG 0 $SPP 0 2>&1 | grep -v "scene build" | sed "s/^/[$v] /"
 done
 done | tee gpurun_out/ab_$TAG.log
 cp /tmp/keep.so rayrs_b200/librayrs_b200.so

@@ -329,6 +329,10 @@ __device__ __forceinline__ void trav_node_step(const DScene& sc, const RayK& r, 
     if (COUNT) cnt.nodes++;
     const float3 idir = r.idir;
     const uint32_t ref0 = w[6], ref1 = w[7];
+    // (Requesting BOTH children's records here — prefetch.global.L1 the moment their references arrive, so that the box
+    // tests below cover the fetch the next step depends on — halves the speed: -45 % on configurations 4 and 5,
+    // profiles/ab_logs/ab_r02p_prefetch.log.  The loop is bound by the rate at which L1 accepts scattered 32-byte
+    // requests, one tag lookup per lane per node, not by the latency of any single one.)
     // Slab test as geometry.rs:458-513 writes it: the near/far plane is chosen by the sign of
     // 1/d (not by min/max of the two products), and max/min drop NaNs — so a ray lying in a
     // face plane of the box (0 * inf = NaN) is simply not constrained by that axis.

@@ -55,7 +55,7 @@ def lib() -> C.CDLL:
         L.orc_aabb_intersect.argtypes = [vp, vp, dbl, dbl]
         L.orc_scene_bbox.argtypes = [vp, vp]
         L.orc_orthonormal_basis.argtypes = [vp, vp]
-        L.orc_philox.argtypes = [vp, vp, vp]
+        L.orc_philox.argtypes = [vp, vp, vp, i32]
         L.orc_rng_uniforms.argtypes = [u64, u32, u32, u32, i32, vp]
         L.orc_traversal_counts.argtypes = [vp, vp, u64, vp, vp, vp]
         L.orc_collect_path_rays.restype = u64
@@ -230,11 +230,12 @@ def orthonormal_basis(n3):
     return out[:3], out[3:]
 
 
-def philox(ctr4, key2) -> np.ndarray:
+def philox(ctr4, key2, rounds: int = 0) -> np.ndarray:
+    """Philox4x32 with `rounds` rounds (0 = the render stream's round count, 7)."""
     c = np.ascontiguousarray(ctr4, dtype=np.uint32)
     k = np.ascontiguousarray(key2, dtype=np.uint32)
     out = np.zeros(4, dtype=np.uint32)
-    lib().orc_philox(c.ctypes.data, k.ctypes.data, out.ctypes.data)
+    lib().orc_philox(c.ctypes.data, k.ctypes.data, out.ctypes.data, int(rounds))
     return out
 
 

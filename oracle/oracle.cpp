@@ -24,7 +24,7 @@
 //
 // One deliberate deviation: rand::random::<f64>() (thread_rng, OS seeded, not
 // reproducible; lib.rs:206-207,539 and material.rs call sites) is replaced by a
-// counter-based Philox4x32-10 stream keyed by (seed; pixel, sample, slot) so that
+// counter-based Philox4x32-7 stream keyed by (seed; pixel, sample, slot) so that
 // results are reproducible and can be sample-matched with the GPU backend.
 //
 // Build: see oracle/Makefile (g++ -O3 -ffp-contract=off: Rust never contracts a*b+c).
@@ -104,15 +104,18 @@ struct Ray {
 };
 
 // ------------------------------------------------------------------------------------
-// RNG: Philox4x32-10 (Salmon et al., SC'11; Random123 reference constants).
+// RNG: Philox4x32 (Salmon et al., SC'11; Random123 reference constants), kPhiloxRounds = 7 rounds for the render
+// stream — the smallest round count the paper reports as passing BigCrush, and what the GPU backend draws; orc_philox
+// exposes the round count so that both 7 and 10 are pinned on Random123's published known answers.
 // counter = (pixel, sample, slot, block), key = (seed_lo, seed_hi).
 // slot 0: camera jitter (word0 -> x, word1 -> y).  slot b+1: bounce b, words 0..2 are the
 // material's draws in call order, word 3 is the Russian-roulette draw.
 // ------------------------------------------------------------------------------------
-static inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                 uint32_t k1, uint32_t out[4]) {
+static const int kPhiloxRounds = 7;
+static inline void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                              uint32_t k1, uint32_t out[4], int rounds = kPhiloxRounds) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < rounds; ++r) {
         uint64_t p0 = (uint64_t)M0 * c0;
         uint64_t p1 = (uint64_t)M1 * c2;
         uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
@@ -136,12 +139,12 @@ struct Rng {
     double u[4];
     void load(uint32_t slot) {
         uint32_t a[4];
-        philox4x32_10(pixel, sample, slot, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), a);
+        philox4x32(pixel, sample, slot, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), a);
         if (mode == 1) {
             for (int i = 0; i < 4; ++i) u[i] = (double)(a[i] >> 8) * (1.0 / 16777216.0);
         } else {
             uint32_t b[4];
-            philox4x32_10(pixel, sample, slot, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), b);
+            philox4x32(pixel, sample, slot, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), b);
             for (int i = 0; i < 4; ++i) {
                 uint64_t hi = a[i] >> 5, lo = b[i] >> 6;
                 u[i] = ((double)hi * 67108864.0 + (double)lo) * (1.0 / 9007199254740992.0);
@@ -1294,8 +1297,8 @@ void orc_orthonormal_basis(const double* n3, double* e1e2) {
     double v[6] = {e1.x, e1.y, e1.z, e2.x, e2.y, e2.z};
     std::memcpy(e1e2, v, sizeof(v));
 }
-void orc_philox(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4) {
-    philox4x32_10(ctr4[0], ctr4[1], ctr4[2], ctr4[3], key2[0], key2[1], out4);
+void orc_philox(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4, int rounds) {
+    philox4x32(ctr4[0], ctr4[1], ctr4[2], ctr4[3], key2[0], key2[1], out4, rounds > 0 ? rounds : kPhiloxRounds);
 }
 // the uniforms of one RNG slot (4 doubles)
 void orc_rng_uniforms(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, int mode, double* out4) {

@@ -124,6 +124,14 @@ def test_background_matches_oracle(scene, hdri_small):
     assert not osc.background(axes[:2]).any()
 
 
+def test_device_rng_reproduces_the_published_philox_7_vector(scene):
+    """Random123 kat_vectors, philox4x32 7, counter 0 key 0 -> 5f6fb709 0d893f64 4f121f81 4f730a48: the device stream's
+    uniforms are the top 24 bits of those words (the counter's 4th word is always 0 in the render stream)."""
+    u = scene.rng_uniforms(0, 0, 0, 0)
+    expect = [float(w >> 8) / 16777216.0 for w in (0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48)]
+    assert list(u.astype(np.float64)) == expect
+
+
 def test_rng_is_bit_identical_to_oracle(scene):
     rng = np.random.default_rng(3)
     for _ in range(64):

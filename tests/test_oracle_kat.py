@@ -11,15 +11,31 @@ def _built(native_built):
     return native_built
 
 
-# ---- RNG: Random123 known answers for Philox4x32-10 (kat_vectors of the Random123 distribution)
-@pytest.mark.parametrize("ctr,key,expect", [
-    ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
-    ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
-    ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
-     [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
-])
-def test_philox_known_answers(ctr, key, expect):
-    assert list(oracle.philox(ctr, key)) == expect
+# ---- RNG: Random123 known answers (kat_vectors of the Random123 distribution): Philox4x32 with 7 rounds — what the render
+# stream draws — and with 10 rounds, the paper's default
+PHILOX_KATS = [
+    (7, [0, 0, 0, 0], [0, 0], [0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48]),
+    (7, [0xffffffff] * 4, [0xffffffff] * 2, [0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662]),
+    (7, [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0], [0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a]),
+    (10, [0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+    (10, [0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+    (10, [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0], [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+]
+
+
+@pytest.mark.parametrize("rounds,ctr,key,expect", PHILOX_KATS)
+def test_philox_known_answers(rounds, ctr, key, expect):
+    assert list(oracle.philox(ctr, key, rounds)) == expect
+    if rounds == 7:
+        assert list(oracle.philox(ctr, key)) == expect  # the render stream's default
+
+
+def test_render_stream_is_philox_7():
+    """rng_uniforms(seed, pixel, sample, slot) = the top 24 bits of Philox4x32-7(counter (pixel, sample, slot, 0), key seed)"""
+    seed, pixel, sample, slot = 0x299f31d0a4093822, 0x243f6a88, 0x85a308d3, 0x13198a2e
+    w = oracle.philox([pixel, sample, slot, 0], [seed & 0xFFFFFFFF, seed >> 32], 7)
+    u = oracle.rng_uniforms(seed, pixel, sample, slot, oracle.RNG_MATCHED)
+    assert [float(x >> 8) / 16777216.0 for x in w] == list(u)
 
 
 def test_rng_uniform_ranges():

@@ -104,6 +104,15 @@ __device__ __forceinline__ bool sphere_intersect64(double4 s, double ox, double 
     return true;
 }
 
+__device__ __forceinline__ bool sphere_reentry64(const DScene& sc, uint32_t sphere_index, const double* org64, float3 d, float* t) {
+    double t64;
+    const double4 s64 = sc.sphere64[sphere_index];
+    const bool hit = sphere_intersect64(s64, org64[0], org64[1], org64[2], (double)d.x, (double)d.y, (double)d.z, t64) &&
+                     t64 > sc.tmin64 && t64 < sc.tmax64;
+    *t = (float)t64;
+    return hit;
+}
+
 // Plane: a = (pos, umin, umax, meta), b = (vmin, vmax, axis, obj).  Half-open ranges, any
 // sign of t is returned (the leaf filter removes t <= tmin).
 __device__ __forceinline__ bool hit_plane(float4 a, float4 b, float3 o, float3 d, float& t) {
@@ -399,13 +408,8 @@ __device__ __forceinline__ void test_prim(const DScene& sc, uint32_t pi, float4 
         hit = hit_triangle(a, b, c, o, d, proj, t);
     } else if (type == RRS_SPHERE) {
         if (SPH64 && pi == origin_prim && org64 != nullptr) {
-            // re-entry: the reference's f64 arithmetic on the f64 hit point, then the
-            // leaf filter of bvh.rs:404-413 in f64
-            double t64;
-            double4 s64 = sc.sphere64[__float_as_uint(b.y)];
-            hit = sphere_intersect64(s64, org64[0], org64[1], org64[2], (double)d.x, (double)d.y, (double)d.z, t64) &&
-                  t64 > sc.tmin64 && t64 < sc.tmax64;
-            t = (float)t64;
+            // re-entry: the reference's f64 arithmetic on the f64 hit point, then the leaf filter of bvh.rs:404-413 in f64
+            hit = sphere_reentry64(sc, __float_as_uint(b.y), org64, d, &t);
         } else {
             hit = hit_sphere(a, b, o, d, pi == origin_prim, t);
         }

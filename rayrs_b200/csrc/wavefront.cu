@@ -342,10 +342,52 @@ __global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DCounters* __restr
 // One path vertex: Material::evaluate + emission + Russian roulette (lib.rs:532-551) for a ray that hit
 // `prim` at distance t.  Shared by the queue-based shade phase and the register-resident path loop.
 // ---------------------------------------------------------------------------------------
+// Sphere::intersect, Ray::point, Sphere::normal in the reference's f64 arithmetic for a hit on a transmissive sphere
+// (intersect.cuh, "sphere re-entry").  (Kept out of line — __noinline__, so that its f64 temporaries would not count
+// against every path's registers — it costs config 3 31 % and config 5 5 %: the call's register save / restore and the
+// hit point passed through local memory outweigh the spills it removes; profiles/ab_logs/ab_r02r_outline.log.)
+__device__ __forceinline__ void sphere_hit_point64(const DScene& sc, const RenderConst& rc, uint32_t pixel, uint32_t sample, float4 o4, float4 d4,
+                                    float t32, uint32_t sphere_index, const double* o64_in, double* p64, float3* pos, float3* nrm) {
+    const uint32_t ow = __float_as_uint(o4.w);
+    double ox = o4.x, oy = o4.y, oz = o4.z;
+    if (ow != RRS_NO_PRIM && (ow & RRS_ORG64) && o64_in) {
+        ox = o64_in[0]; oy = o64_in[1]; oz = o64_in[2];
+    }
+    double dx = d4.x, dy = d4.y, dz = d4.z;
+    if (ow == RRS_NO_PRIM) {
+        // primary ray: Camera::generate_primary_ray (lib.rs:202-210) in f64.  The loss
+        // probability of the re-entry quirk depends on the f64 rounding of the FIRST hit,
+        // and an fp32-exact direction makes that arithmetic atypically exact (measured:
+        // 81 % instead of 71 % for the outer spheres), so the direction is rebuilt here.
+        const RrsCamera& c64 = rc.cam64;
+        uint32_t row = pixel / rc.cam.W, col = pixel - row * rc.cam.W;
+        float4 u0 = rng_uniforms(rc.seed, pixel, sample, 0u);
+        double fj = (double)(rc.cam.W - col), fi = (double)(rc.cam.H - row), ppc = (double)c64.ppc;
+        double x = __dsub_rn(__ddiv_rn(__dadd_rn(fj, (double)u0.x), ppc), __ddiv_rn(c64.width, 2.));
+        double y = __dsub_rn(__ddiv_rn(__dadd_rn(fi, (double)u0.y), ppc), __ddiv_rn(c64.height, 2.));
+        dx = __dadd_rn(__dadd_rn(c64.z_scaled[0], __dmul_rn(x, c64.e_x[0])), __dmul_rn(y, c64.e_y[0]));
+        dy = __dadd_rn(__dadd_rn(c64.z_scaled[1], __dmul_rn(x, c64.e_x[1])), __dmul_rn(y, c64.e_y[1]));
+        dz = __dadd_rn(__dadd_rn(c64.z_scaled[2], __dmul_rn(x, c64.e_x[2])), __dmul_rn(y, c64.e_y[2]));
+        ox = c64.origin[0]; oy = c64.origin[1]; oz = c64.origin[2];
+    }
+    const double4 s64 = sc.sphere64[sphere_index];
+    double t64;
+    const bool ok = sphere_intersect64(s64, ox, oy, oz, dx, dy, dz, t64);
+    if (!ok || fabs(t64 - (double)t32) > 1e-3 * (double)t32) t64 = (double)t32;  // rim: keep the fp32 root
+    const double px = __dadd_rn(ox, __dmul_rn(dx, t64)), py = __dadd_rn(oy, __dmul_rn(dy, t64)), pz = __dadd_rn(oz, __dmul_rn(dz, t64));
+    p64[0] = px; p64[1] = py; p64[2] = pz;
+    const double nx = __dsub_rn(px, s64.x), ny = __dsub_rn(py, s64.y), nz = __dsub_rn(pz, s64.z);
+    // Sphere::normal (geometry.rs:134-136) is only ever consumed in fp32 here: scale by 1/r in f64 (one multiply
+    // per component; |p - c| = r to 1e-16) so the fp32 normalisation below starts from O(1) components
+    const double inv_r = (double)rsqrtf((float)s64.w);
+    *nrm = normalize3(f3((float)(nx * inv_r), (float)(ny * inv_r), (float)(nz * inv_r)));
+    *pos = f3((float)px, (float)py, (float)pz);
+}
+
 struct NextRay {
     bool alive, carry64;
     float4 no, nd, ns;           // origin + origin word, direction + pixel, throughput + (sample << 8 | bounce)
-    double p64x, p64y, p64z;     // f64 hit point (transmissive spheres)
+    double p64[3];               // f64 hit point (transmissive spheres; written only when carry64)
 };
 
 template <bool SPH64, bool STAGED>
@@ -354,11 +396,9 @@ __device__ __forceinline__ NextRay shade_hit(const DScene& sc, const RenderConst
     NextRay nr;
     nr.alive = false;
     nr.carry64 = false;
-    nr.p64x = nr.p64y = nr.p64z = 0.;
     bool& alive = nr.alive;
     bool& carry64 = nr.carry64;
     float4 &no = nr.no, &nd = nr.nd, &ns = nr.ns;
-    double &p64x = nr.p64x, &p64y = nr.p64y, &p64z = nr.p64z;
     uint32_t prim = __float_as_uint(h.y);
     uint32_t pixel = __float_as_uint(d4.w);
     RRS_CHECK(prim < sc.n_prims && pixel < rc.cam.W * rc.cam.H);
@@ -377,42 +417,7 @@ __device__ __forceinline__ NextRay shade_hit(const DScene& sc, const RenderConst
                               mtag == RRS_MAT_COOK_TORRANCE_REFRACT || mtag == RRS_MAT_COOK_TORRANCE_GLASS;
     if (SPH64 && sc.sphere64 != nullptr && prim_type(a) == RRS_SPHERE && transmissive) {
         // hit point on a transmissive sphere in the reference's f64 arithmetic
-        // (intersect.cuh, "sphere re-entry"): Sphere::intersect, Ray::point, Sphere::normal
-        const uint32_t ow = __float_as_uint(o4.w);
-        double ox = o.x, oy = o.y, oz = o.z;
-        if (ow != RRS_NO_PRIM && (ow & RRS_ORG64) && o64_in) {
-            ox = o64_in[0]; oy = o64_in[1]; oz = o64_in[2];
-        }
-        double dx = d.x, dy = d.y, dz = d.z;
-        if (ow == RRS_NO_PRIM) {
-            // primary ray: Camera::generate_primary_ray (lib.rs:202-210) in f64.  The loss
-            // probability of the re-entry quirk depends on the f64 rounding of the FIRST hit,
-            // and an fp32-exact direction makes that arithmetic atypically exact (measured:
-            // 81 % instead of 71 % for the outer spheres), so the direction is rebuilt here.
-            const RrsCamera& c64 = rc.cam64;
-            uint32_t row = pixel / rc.cam.W, col = pixel - row * rc.cam.W;
-            float4 u0 = rng_uniforms(rc.seed, pixel, sample, 0u);
-            double fj = (double)(rc.cam.W - col), fi = (double)(rc.cam.H - row), ppc = (double)c64.ppc;
-            double x = __dsub_rn(__ddiv_rn(__dadd_rn(fj, (double)u0.x), ppc), __ddiv_rn(c64.width, 2.));
-            double y = __dsub_rn(__ddiv_rn(__dadd_rn(fi, (double)u0.y), ppc), __ddiv_rn(c64.height, 2.));
-            dx = __dadd_rn(__dadd_rn(c64.z_scaled[0], __dmul_rn(x, c64.e_x[0])), __dmul_rn(y, c64.e_y[0]));
-            dy = __dadd_rn(__dadd_rn(c64.z_scaled[1], __dmul_rn(x, c64.e_x[1])), __dmul_rn(y, c64.e_y[1]));
-            dz = __dadd_rn(__dadd_rn(c64.z_scaled[2], __dmul_rn(x, c64.e_x[2])), __dmul_rn(y, c64.e_y[2]));
-            ox = c64.origin[0]; oy = c64.origin[1]; oz = c64.origin[2];
-        }
-        double4 s64 = sc.sphere64[__float_as_uint(__ldg(pp + 1).y)];
-        double t64;
-        bool ok = sphere_intersect64(s64, ox, oy, oz, dx, dy, dz, t64);
-        if (!ok || fabs(t64 - (double)h.x) > 1e-3 * (double)h.x) t64 = (double)h.x;  // rim: keep the fp32 root
-        p64x = __dadd_rn(ox, __dmul_rn(dx, t64));
-        p64y = __dadd_rn(oy, __dmul_rn(dy, t64));
-        p64z = __dadd_rn(oz, __dmul_rn(dz, t64));
-        double nx = __dsub_rn(p64x, s64.x), ny = __dsub_rn(p64y, s64.y), nz = __dsub_rn(p64z, s64.z);
-        // Sphere::normal (geometry.rs:134-136) is only ever consumed in fp32 here: scale by 1/r in f64 (one multiply
-        // per component; |p - c| = r to 1e-16) so the fp32 normalisation below starts from O(1) components
-        const double inv_r = (double)rsqrtf((float)s64.w);
-        nrm = normalize3(f3((float)(nx * inv_r), (float)(ny * inv_r), (float)(nz * inv_r)));
-        pos = f3((float)p64x, (float)p64y, (float)p64z);
+        sphere_hit_point64(sc, rc, pixel, sample, o4, d4, h.x, __float_as_uint(__ldg(pp + 1).y), o64_in, nr.p64, &pos, &nrm);
         carry64 = true;
     } else {
         pos = madd3(d, h.x, o);  // Ray::point lib.rs:41-43
@@ -520,7 +525,7 @@ __device__ __forceinline__ void phase_shade(const DScene& sc, const RenderConst&
                 stq(out_state + slot, nr.ns);
                 if (SPH64 && nr.carry64 && q.org64) {
                     double* o64 = q.org64 + 3 * (ooff + slot);
-                    o64[0] = nr.p64x; o64[1] = nr.p64y; o64[2] = nr.p64z;
+                    o64[0] = nr.p64[0]; o64[1] = nr.p64[1]; o64[2] = nr.p64[2];
                 }
             }
         }
@@ -645,7 +650,7 @@ __device__ __forceinline__ bool small_scene_iteration(const DScene& sc, const Re
                 stq(out_state + slot, nr.ns);
                 if (SPH64 && nr.carry64 && q.org64) {
                     double* w64 = q.org64 + 3 * (ooff + slot);
-                    w64[0] = nr.p64x; w64[1] = nr.p64y; w64[2] = nr.p64z;
+                    w64[0] = nr.p64[0]; w64[1] = nr.p64[1]; w64[2] = nr.p64[2];
                 }
             }
         }
@@ -798,7 +803,7 @@ k_pathloop(DScene sc, RenderConst rc, DCounters* __restrict__ c, float4* __restr
                     d4 = nr.nd;
                     st = nr.ns;
                     if (SPH64 && nr.carry64) {
-                        o64[0] = nr.p64x; o64[1] = nr.p64y; o64[2] = nr.p64z;
+                        o64[0] = nr.p64[0]; o64[1] = nr.p64[1]; o64[2] = nr.p64[2];
                     }
                     stage = ST_ISECT;
                 } else {

@@ -125,7 +125,8 @@ def roofline_block(workload, kname, rays, kernel_ms, n_launch, step_ms_total, cl
                         "peak": peak_hbm, "unit": "GB/s", "frac": c["dram_bytes_per_ray"] * rays / (kms * 1e-3) / 1e9 / peak_hbm,
                         "peak_source": peak_src}
         roof["counters_source"] = c.get("source", COUNTERS_FILE)
-        for k in ("l2_hit_pct", "issue_active_pct", "captured"):
+        for k in ("l1tex_throughput_pct", "l1_global_load_sectors_per_ray", "l1_global_load_hit_pct", "l2_hit_pct", "issue_active_pct",
+                  "long_scoreboard_stall_per_issue", "captured"):
             if k in c:
                 roof[k] = c[k]
     model = bytes_per_ray_model(workload)

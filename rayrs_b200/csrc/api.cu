@@ -391,7 +391,8 @@ void convert_desc(const RrsSceneDesc* desc, HostScene& h) {
         d.root = (vr.ref1 == RRS_REF_EMPTY && vr.ref0 != RRS_REF_EMPTY && !(vr.ref0 & RRS_REF_LEAF)) ? vr.ref0 : 0u;
     }
     // rays of a deep tree differ widely in length: refill early; a tiny scene amortises the fetch over more lanes
-    d.refill_lanes = desc->refill_lanes ? desc->refill_lanes : (desc->max_depth > 6 ? 4u : 12u);
+    // (deep trees: 2 / 4 / 6 / 8 / 12 / 16 idle lanes measured, 8 is +1 % over round 1's 4: profiles/ab_logs/ab_r02u_refill.log)
+    d.refill_lanes = desc->refill_lanes ? desc->refill_lanes : (desc->max_depth > 6 ? 8u : 12u);
 }
 
 int upload_scene(const RrsSceneDesc* desc, const HostScene& h, int device, RrsScene** out, std::string& err) {

@@ -48,6 +48,10 @@ entry = {
     "local_load_requests_per_ray": tot("l1tex__t_requests_pipe_lsu_mem_local_op_ld.sum") / rays,
     "global_load_requests_per_ray": tot("l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum") / rays,
     "long_scoreboard_stall_per_issue": avg("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
+    "l1tex_throughput_pct": avg("l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
+    "l1_lsu_wavefronts_pct": avg("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+    "l1_global_load_sectors_per_ray": tot("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum") / rays,
+    "l2_throughput_pct": avg("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
     "captured": {"command": f"bench.py --workload {key} --spp {bench['config']['spp_total']}", "launches": n_scenes, "rays": rays,
                  "launch_ms_under_ncu": t_ns / 1e6, "spp": bench["config"]["spp_total"]},
     "source": f"profiles/r02/counters_{key}.csv (ncu of bench.py, scripts/ncu_counters.py)",

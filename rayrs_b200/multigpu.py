@@ -8,6 +8,11 @@ the set of paths — and, up to fp32 summation order, the image — is independe
 
 torch is plumbing here (device buffers, streams, torch.distributed); the rendering is the CUDA
 backend behind the C ABI.
+
+The PRODUCT path for several GPUs is inside the library: rrs_render_multi over an RrsComm (api.render_multi,
+api.Comm, Scene(devices=[...]); csrc/multi.cu) — one call, NCCL bound by the library itself; bench.py and the
+C / Rust hosts use that.  This module keeps the same split driven from Python (render_distributed): it is what the
+gloo tests on CPU exercise (tests/test_multigpu_cpu.py) and the torch-side cross-check of scripts/multigpu_check.py.
 """
 from __future__ import annotations
 

@@ -117,7 +117,8 @@ class Emission:
 @dataclass
 class Object:
     """One object or a batch of objects sharing material and emission.
-    rows: n x 10 float64 = [type, payload x 9] in the host table layout (host_capi.cpp)."""
+    rows: n x 12 float64 = [type, 0, 0, payload x 9] — the host table layout (host_capi.cpp) with the material / emission
+    index columns left for build_tables to fill, so a mesh goes into the table as one contiguous copy."""
     rows: np.ndarray
     mat: Material
     emission: Emission
@@ -125,28 +126,32 @@ class Object:
     @staticmethod
     def sphere(radius, origin, mat, emission=Emission()):
         o = _v3(origin)
-        return Object(np.array([[0, radius, o[0], o[1], o[2], 0, 0, 0, 0, 0]], dtype=np.float64), mat, emission)
+        return Object(np.array([[0, 0, 0, radius, o[0], o[1], o[2], 0, 0, 0, 0, 0]], dtype=np.float64), mat, emission)
 
     @staticmethod
     def plane(axis, umin, umax, vmin, vmax, pos, mat, emission=Emission()):
-        return Object(np.array([[1, axis, umin, umax, vmin, vmax, pos, 0, 0, 0]], dtype=np.float64), mat, emission)
+        return Object(np.array([[1, 0, 0, axis, umin, umax, vmin, vmax, pos, 0, 0, 0]], dtype=np.float64), mat, emission)
 
     @staticmethod
     def triangle(p1, p2, p3, mat, emission=Emission()):
-        return Object(np.concatenate([[2.0], _v3(p1), _v3(p2), _v3(p3)])[None, :], mat, emission)
+        return Object(np.concatenate([[2.0, 0.0, 0.0], _v3(p1), _v3(p2), _v3(p3)])[None, :], mat, emission)
 
     @staticmethod
     def from_triangles(tris, mat, emission=Emission()):
         """tris: (n, 3, 3) vertex positions, counter-clockwise (lib.rs:407-415)."""
         t = np.asarray(tris, dtype=np.float64).reshape(-1, 9)
-        return Object(np.concatenate([np.full((t.shape[0], 1), 2.0), t], axis=1), mat, emission)
+        rows = np.empty((t.shape[0], 12))
+        rows[:, 0] = 2.0
+        rows[:, 1:3] = 0.0
+        rows[:, 3:12] = t
+        return Object(rows, mat, emission)
 
     @staticmethod
     def from_spheres(centers, radius, mat, emission=Emission()):
         c = np.asarray(centers, dtype=np.float64).reshape(-1, 3)
-        rows = np.zeros((c.shape[0], 10))
-        rows[:, 1] = radius
-        rows[:, 2:5] = c
+        rows = np.zeros((c.shape[0], 12))
+        rows[:, 3] = radius
+        rows[:, 4:7] = c
         return Object(rows, mat, emission)
 
     @staticmethod
@@ -203,10 +208,9 @@ def build_tables(objects: Iterable[Object]) -> SceneTables:
             ei = emis.index(o.emission)
         n = o.rows.shape[0]
         rows = objs[pos:pos + n]
-        rows[:, 0] = o.rows[:, 0]
+        rows[...] = o.rows
         rows[:, 1] = mi
         rows[:, 2] = ei
-        rows[:, 3:12] = o.rows[:, 1:10]
         pos += n
     m = np.array([mm.row for mm in mats], dtype=np.float64).reshape(-1, 12)
     e = np.array([[em.strength, *em.color] for em in emis], dtype=np.float64).reshape(-1, 4)

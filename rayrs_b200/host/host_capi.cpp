@@ -12,6 +12,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
+#include <new>
+#include <memory>
 #include <string>
 
 #include "mesh_io.hpp"
@@ -58,8 +61,13 @@ void* rrh_scene_new(const double* objs, uint64_t n_obj, const double* mats, uint
         std::vector<Emission> em;
         for (uint64_t i = 0; i < n_emis; ++i)
             em.push_back(Emission::Emissive(emis[4 * i], Vec3(emis[4 * i + 1], emis[4 * i + 2], emis[4 * i + 3])));
-        // one Object per table row; rows are independent, so large meshes are converted on all host threads
-        std::vector<Object> objects(n_obj);
+        // one Object per table row; rows are independent, so large meshes are converted on all host threads — into raw
+        // storage, so that the first touch of the 190 B x n buffer is spread over the threads too (Object is trivially
+        // destructible: releasing the storage is all the clean-up there is)
+        static_assert(std::is_trivially_destructible<Object>::value, "the object buffer is released without destructor calls");
+        struct RawFree { void operator()(Object* p) const { ::operator delete(static_cast<void*>(p)); } };
+        std::unique_ptr<Object, RawFree> storage(static_cast<Object*>(::operator new(std::max<uint64_t>(n_obj, 1) * sizeof(Object))));
+        Object* objects = storage.get();
         std::mutex err_mu;
         std::string err;
         parallel_chunks(n_obj, 1 << 16, [&](size_t lo, size_t hi) {
@@ -71,10 +79,10 @@ void* rrh_scene_new(const double* objs, uint64_t n_obj, const double* mats, uint
                     if (ei >= (int)n_emis) throw Panic("object emission index out of range");
                     Emission e = ei < 0 ? Emission::Dark() : em[ei];
                     switch ((int)r[0]) {
-                        case 0: objects[i] = Object::sphere(r[3], Vec3(r[4], r[5], r[6]), mt[mi], e); break;
-                        case 1: objects[i] = Object::plane((Axis)(int)r[3], r[4], r[5], r[6], r[7], r[8], mt[mi], e); break;
+                        case 0: new (objects + i) Object(Object::sphere(r[3], Vec3(r[4], r[5], r[6]), mt[mi], e)); break;
+                        case 1: new (objects + i) Object(Object::plane((Axis)(int)r[3], r[4], r[5], r[6], r[7], r[8], mt[mi], e)); break;
                         case 2:
-                            objects[i] = Object::triangle(Vec3(r[3], r[4], r[5]), Vec3(r[6], r[7], r[8]), Vec3(r[9], r[10], r[11]), mt[mi], e);
+                            new (objects + i) Object(Object::triangle(Vec3(r[3], r[4], r[5]), Vec3(r[6], r[7], r[8]), Vec3(r[9], r[10], r[11]), mt[mi], e));
                             break;
                         default: throw Panic("unknown object type");
                     }
@@ -100,7 +108,7 @@ void* rrh_scene_new(const double* objs, uint64_t n_obj, const double* mats, uint
         opt.bvh_threads = bvh_threads;
         opt.device_build = device_build != 0;
         opt.topology = topology != 0;
-        return new Scene(objects, tmin, tmax, h, img, opt);
+        return new Scene(ObjectSpan(objects, n_obj), tmin, tmax, h, img, opt);
     } catch (const std::exception& e) {
         g_err = e.what();
         return nullptr;

@@ -549,7 +549,7 @@ void dump_topology(const std::vector<BNode>& bn, int32_t b, const std::vector<ui
 
 }  // namespace
 
-FlatBvh Bvh::build(BvhHeuristic heuristic, const std::vector<Object>& objects, uint32_t bfs_nodes, int threads,
+FlatBvh Bvh::build(BvhHeuristic heuristic, ObjectSpan objects, uint32_t bfs_nodes, int threads,
                    BvhBuildTiming* timing, int build_device, bool want_topology) {
     if (objects.empty()) throw Panic("Having a BVH for 0 objects does not make sense");
     if (heuristic.kind == BvhHeuristic::kSah && heuristic.splits < 2) throw Panic("Sah needs at least 2 splits");
@@ -738,8 +738,8 @@ RrsCamera Camera::derived() const {
 // ---------------------------------------------------------------------------------------
 // Scene (lib.rs:227-245)
 // ---------------------------------------------------------------------------------------
-Scene::Scene(const std::vector<Object>& objects, double z_near, double z_far, BvhHeuristic heuristic, const Image& hdri,
-             int device, bool with_f64, bool upload) {
+Scene::Scene(ObjectSpan objects, double z_near, double z_far, BvhHeuristic heuristic, const Image& hdri, int device, bool with_f64,
+             bool upload) {
     SceneOptions opt;
     opt.devices = {device};
     opt.with_f64 = with_f64;
@@ -747,13 +747,11 @@ Scene::Scene(const std::vector<Object>& objects, double z_near, double z_far, Bv
     init(objects, z_near, z_far, heuristic, hdri, opt);
 }
 
-Scene::Scene(const std::vector<Object>& objects, double z_near, double z_far, BvhHeuristic heuristic, const Image& hdri,
-             const SceneOptions& opt) {
+Scene::Scene(ObjectSpan objects, double z_near, double z_far, BvhHeuristic heuristic, const Image& hdri, const SceneOptions& opt) {
     init(objects, z_near, z_far, heuristic, hdri, opt);
 }
 
-void Scene::init(const std::vector<Object>& objects, double z_near, double z_far, BvhHeuristic heuristic, const Image& hdri,
-                 const SceneOptions& opt) {
+void Scene::init(ObjectSpan objects, double z_near, double z_far, BvhHeuristic heuristic, const Image& hdri, const SceneOptions& opt) {
     require(z_near >= 0., "Scene::new: z_near must be >= 0");
     require(z_far > z_near, "Scene::new: z_far must be > z_near");
     require(!opt.devices.empty(), "Scene::new: no device");
@@ -761,39 +759,87 @@ void Scene::init(const std::vector<Object>& objects, double z_near, double z_far
     bvh_ = Bvh::build(heuristic, objects, 1023, opt.bvh_threads, &timing_, opt.device_build ? opt.devices[0] : -1, opt.topology);
     build_seconds_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
-    // materials / emissions: objects carry them by value (mat.clone() in lib.rs:407-415);
-    // identical ones share one table entry
-    auto mat_index = [&](const RrsMaterial& m) -> uint32_t {
-        for (size_t i = 0; i < materials_.size(); ++i)
-            if (std::memcmp(&materials_[i], &m, sizeof(RrsMaterial)) == 0) return (uint32_t)i;
-        materials_.push_back(m);
-        return (uint32_t)materials_.size() - 1;
+    // materials / emissions: objects carry them by value (mat.clone() in lib.rs:407-415); identical ones share one table
+    // entry, numbered by first appearance in primitive (DFS leaf) order.  Three passes so that the two over all objects
+    // run on every host thread: (1) per chunk of objects, the chunk's distinct materials / emissions and each object's
+    // index into them; (2) the chunk tables merged into canonical ones and renumbered by first appearance along
+    // prim_order; (3) the primitive table filled (a random gather over the object list).
+    const size_t n = objects.size();
+    constexpr size_t kChunk = 1 << 16;
+    const size_t n_chunks = (n + kChunk - 1) / kChunk;
+    struct ChunkTables {
+        std::vector<RrsMaterial> mats;
+        std::vector<RrsEmission> emis;
+        std::vector<uint32_t> mat_canon, emi_canon;
     };
-    auto emi_index = [&](const Emission& e) -> int32_t {
-        if (e.dark) return -1;
-        RrsEmission r{e.strength, {e.color.x, e.color.y, e.color.z}};
-        for (size_t i = 0; i < emissions_.size(); ++i)
-            if (std::memcmp(&emissions_[i], &r, sizeof(RrsEmission)) == 0) return (int32_t)i;
-        emissions_.push_back(r);
-        return (int32_t)emissions_.size() - 1;
+    std::vector<ChunkTables> chunk(n_chunks);
+    std::unique_ptr<uint32_t[]> local_mat(new uint32_t[n]);
+    std::unique_ptr<int32_t[]> local_emi(new int32_t[n]);
+    auto find_or_add = [](auto& table, const auto& rec) -> uint32_t {
+        for (size_t i = 0; i < table.size(); ++i)
+            if (std::memcmp(&table[i], &rec, sizeof(rec)) == 0) return (uint32_t)i;
+        table.push_back(rec);
+        return (uint32_t)table.size() - 1;
     };
-    prims_.resize(objects.size());
-    uint32_t last_mat = 0;
-    const RrsMaterial* last_ptr = nullptr;
-    for (size_t k = 0; k < bvh_.prim_order.size(); ++k) {
-        const Object& o = objects[bvh_.prim_order[k]];
-        RrsPrim& p = prims_[k];
-        p.type = o.geom.type;
-        p.obj_id = bvh_.prim_order[k];
-        // fast path for meshes: consecutive objects usually share the material
-        if (!last_ptr || std::memcmp(last_ptr, &o.mat.m, sizeof(RrsMaterial)) != 0) {
-            last_mat = mat_index(o.mat.m);
-            last_ptr = &o.mat.m;
+    parallel_chunks(n_chunks, 1, [&](size_t c_lo, size_t c_hi) {
+        for (size_t c = c_lo; c < c_hi; ++c) {
+            ChunkTables& ct = chunk[c];
+            uint32_t last = 0;
+            const RrsMaterial* last_ptr = nullptr;  // meshes: consecutive objects usually share the material
+            for (size_t i = c * kChunk, e = std::min(n, (c + 1) * kChunk); i < e; ++i) {
+                const Object& o = objects[i];
+                if (!last_ptr || std::memcmp(last_ptr, &o.mat.m, sizeof(RrsMaterial)) != 0) {
+                    last = find_or_add(ct.mats, o.mat.m);
+                    last_ptr = &o.mat.m;
+                }
+                local_mat[i] = last;
+                local_emi[i] = o.emission.dark ? -1
+                                               : (int32_t)find_or_add(ct.emis, RrsEmission{o.emission.strength,
+                                                                                           {o.emission.color.x, o.emission.color.y, o.emission.color.z}});
+            }
         }
-        p.material = last_mat;
-        p.emission = emi_index(o.emission);
-        std::memcpy(p.v, o.geom.v, sizeof(p.v));
+    });
+    std::vector<RrsMaterial> canon_mats;
+    std::vector<RrsEmission> canon_emis;
+    for (ChunkTables& ct : chunk) {
+        for (const RrsMaterial& m : ct.mats) ct.mat_canon.push_back(find_or_add(canon_mats, m));
+        for (const RrsEmission& e : ct.emis) ct.emi_canon.push_back(find_or_add(canon_emis, e));
     }
+    constexpr uint32_t kUnseen = 0xFFFFFFFFu;
+    std::vector<uint32_t> mat_final(canon_mats.size(), kUnseen), emi_final(canon_emis.size(), kUnseen);
+    size_t unseen = canon_mats.size() + canon_emis.size();
+    for (size_t k = 0; k < n && unseen; ++k) {
+        const uint32_t obj = bvh_.prim_order[k];
+        const ChunkTables& ct = chunk[obj / kChunk];
+        const uint32_t cm = ct.mat_canon[local_mat[obj]];
+        if (mat_final[cm] == kUnseen) {
+            mat_final[cm] = (uint32_t)materials_.size();
+            materials_.push_back(canon_mats[cm]);
+            --unseen;
+        }
+        if (local_emi[obj] >= 0) {
+            const uint32_t ce = ct.emi_canon[local_emi[obj]];
+            if (emi_final[ce] == kUnseen) {
+                emi_final[ce] = (uint32_t)emissions_.size();
+                emissions_.push_back(canon_emis[ce]);
+                --unseen;
+            }
+        }
+    }
+    prims_.resize(n);
+    parallel_chunks(n, kChunk, [&](size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; ++k) {
+            const uint32_t obj = bvh_.prim_order[k];
+            const Object& o = objects[obj];
+            const ChunkTables& ct = chunk[obj / kChunk];
+            RrsPrim& p = prims_[k];
+            p.type = o.geom.type;
+            p.obj_id = obj;
+            p.material = mat_final[ct.mat_canon[local_mat[obj]]];
+            p.emission = local_emi[obj] < 0 ? -1 : (int32_t)emi_final[ct.emi_canon[local_emi[obj]]];
+            std::memcpy(p.v, o.geom.v, sizeof(p.v));
+        }
+    });
     if (!opt.upload) return;
     std::vector<float> rgb(hdri.pixels.size() * 3);
     for (size_t i = 0; i < hdri.pixels.size(); ++i) {

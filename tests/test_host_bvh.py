@@ -165,6 +165,29 @@ def test_zero_extent_group_is_dead():
     assert ids[0] == -1
 
 
+def test_primitive_tables_number_materials_by_first_appearance():
+    """Scene::init builds the primitive / material / emission tables on all host threads (chunk tables merged, then
+    renumbered): the result must be what the one-thread walk gives — primitives in DFS leaf order, identical materials
+    sharing one entry, entries numbered by first appearance along that order.  mixed_scene(400, 200) spans three
+    65536-object chunks with eight materials."""
+    for spec in (scenes.material_test(), scenes.emissive_room(), scenes.mixed_scene(400, 200, 64, 64)):
+        host = spec.scene(HDRI, upload=False)
+        t = build_tables(spec.objects)
+        _, _, order, _, _, prims = host.flat()
+        rec = np.frombuffer(prims, dtype=np.dtype([("type", "<u4"), ("obj", "<u4"), ("mat", "<u4"), ("emi", "<i4"), ("v", "<f8", 9)]))
+        assert (rec["obj"] == order).all()
+        assert (rec["type"] == t.objs[order, 0]).all()
+        tri = rec["type"] == 2  # a triangle's nine values are its vertices as given; spheres / planes keep derived values
+        assert (rec["v"][tri] == t.objs[order, 3:12][tri]).all()
+        seen_m, seen_e = {}, {}
+        for k, o in enumerate(order):
+            key = tuple(t.mats[int(t.objs[o, 1])])
+            assert rec["mat"][k] == seen_m.setdefault(key, len(seen_m))
+            ei = int(t.objs[o, 2])
+            assert rec["emi"][k] == (-1 if ei < 0 else seen_e.setdefault(tuple(t.emis[ei]), len(seen_e)))
+        assert host.n_materials == len(seen_m)
+
+
 def test_constructor_panics_mirror_reference():
     m = Material.no_reflect()
     with pytest.raises(ValueError):  # geometry.rs:97

@@ -156,7 +156,8 @@ typedef struct RrsSceneDesc {
 /* RrsSceneDesc.flags (measurement switches: every one keeps the results identical) */
 #define RRS_SCENE_NO_BRUTE 1u      /* scenes of <= 8 primitives: traverse the BVH instead of testing every primitive */
 #define RRS_SCENE_NO_BRUTE_BOX 2u  /* ... keep the brute-force list but drop the box around its sphere group */
-#define RRS_SCENE_NO_L2_PERSIST 4u /* do not pin the node / primitive arrays in L2 (access-policy window) */
+#define RRS_SCENE_NO_L2_PERSIST 4u /* never pin the node / primitive arrays in L2, and leave the device's persisting-L2 set-aside alone
+                                      (by default a BVH render claims it and a small-scene render releases it) */
 
 /* Derived camera fields exactly as Camera::new computes them (lib.rs:113-132), so that the
  * FOV quirk (z scaled by width/tan(fov/2)) stays on the host. */

@@ -449,12 +449,15 @@ int upload_scene(const RrsSceneDesc* desc, const HostScene& h, int device, RrsSc
         if (rc == RRS_OK) rc = upload(&s.prims_f64, desc->prims, desc->n_prims, err);
     }
     if (rc == RRS_OK && !(desc->flags & RRS_SCENE_NO_L2_PERSIST)) {
-        // L2 residency: set aside as much of L2 as the device allows for persisting lines; the render pins the
-        // node (+ primitive) array in it through an access-policy window on its stream
+        // L2 residency: how much of L2 the device lets a process set aside for persisting lines, and the largest
+        // access-policy window.  The set-aside itself follows the RENDER (wf_render_accumulate): a render of the BVH
+        // form claims it and pins the node (+ primitive) array through a window on its stream; a render of the
+        // small-scene form hands it back — the carve-out is device-wide, and left in place it took 60 % of L2 away from
+        // the queues of scenes that have no tree to pin (glass series -12 … -26 %, profiles/ab_logs/l2limit_r02v_c3.log).
         int max_persist = 0, max_window = 0;
         cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
-        if (max_persist > 0 && max_window > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess) {
+        if (max_persist > 0 && max_window > 0) {
             s.l2_persist_bytes = (size_t)max_persist;
             s.l2_window_max = (size_t)max_window;
         }

@@ -18,6 +18,7 @@
 // k_generate / k_extend / k_shade (+ k_plan) are the same phases as separate launches (RRS_FLAG_SPLIT_KERNELS, for
 // per-phase profiling); k_pathloop is the register-resident alternative for small scenes (RRS_FLAG_FORCE_PATHLOOP).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -46,6 +47,11 @@ static constexpr int kBlock = RRS_BLOCK_THREADS;
 #endif
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// the persisting-L2 set-aside (cudaLimitPersistingL2CacheSize) as this library last set it, per device
+static constexpr int kMaxDevices = 64;
+static constexpr size_t kUnknownSetAside = ~(size_t)0;
+static std::atomic<size_t> g_l2_set_aside[kMaxDevices];  // zero-initialised = the driver's default (no set-aside)
 
 // Queue traffic streams (every ray / state / hit record is written once and read once): ld/st.global.cs marks the
 // lines evict-first so that they do not push the BVH out of L2 (see "L2 residency" in wf_render_accumulate).
@@ -1135,8 +1141,22 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     // 126 MB L2) ran at a 56 % L2 hit rate and 181 B of DRAM reads per ray (profiles/r01o_c4_wavefront_metrics.csv).
     // An access-policy window marks the tree persisting: over [nodes | primitives] when most of it fits the
     // persisting carve-out, over the nodes alone otherwise.
+    // The set-aside is a device-wide limit: claimed for a render that pins a tree, released for one that does not
+    // (small scenes: their queues want the whole L2).  Touched only when the kind of render on the device changes.
     bool window_set = false;
-    if (!brute && s->l2_persist_bytes && s->geom_blob && !(p->flags & RRS_FLAG_NO_L2_WINDOW)) {
+    const bool want_window = !brute && s->l2_persist_bytes && s->geom_blob && !(p->flags & RRS_FLAG_NO_L2_WINDOW);
+    bool set_aside_ok = false;
+    if (s->l2_persist_bytes && s->device >= 0 && s->device < kMaxDevices) {
+        const size_t want = want_window ? s->l2_persist_bytes : 0;
+        std::atomic<size_t>& cur = g_l2_set_aside[s->device];
+        if (cur.load() != want) {
+            const bool ok = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess;
+            cudaGetLastError();
+            cur.store(ok ? want : kUnknownSetAside);
+        }
+        set_aside_ok = cur.load() == want;
+    }
+    if (want_window && set_aside_ok) {
         size_t bytes = s->geom_bytes;
         if ((double)s->l2_persist_bytes < 0.6 * (double)bytes) bytes = s->node_bytes;
         bytes = std::min(bytes, s->l2_window_max);

@@ -55,6 +55,13 @@ static std::atomic<size_t> g_l2_set_aside[kMaxDevices];  // zero-initialised = t
 
 // Queue traffic streams (every ray / state / hit record is written once and read once): ld/st.global.cs marks the
 // lines evict-first so that they do not push the BVH out of L2 (see "L2 residency" in wf_render_accumulate).
+// Samples of one 8x4 pixel tile generated back to back (log2; see primary_ray).  Measured against sample-major order
+// (profiles/ab_logs/ab_r02y_sample_block_*.log, ab_r02z_sample_block_large.log): 16 / 64 / 256 samples per block give
+// configuration 4 +5.2 / +6.9 / +7.5 %, configuration 5 +3.6 / +4.0 / +4.3 %, the sphere series +1.5 … 3 %; 1024 is
+// 1.6 % / 0.6 % behind 256 (too few tiles in flight: the float4 atomics of a pixel start to queue).
+#ifndef RRS_SAMPLE_BLOCK_LOG2
+#define RRS_SAMPLE_BLOCK_LOG2 8
+#endif
 #ifndef RRS_QUEUE_STREAMING
 #define RRS_QUEUE_STREAMING 1
 #endif
@@ -112,30 +119,40 @@ __global__ void k_plan(DCounters* c) {
 
 // ---------------------------------------------------------------------------------------
 // Camera::generate_primary_ray (lib.rs:202-210) for padded path index p.  Paths are numbered
-// sample-major over 8x4 pixel tiles (one tile per 32 consecutive indices), so a warp that takes 32
-// consecutive indices starts coherent.
+// over 8x4 pixel tiles (one tile per 32 consecutive indices), so a warp that takes 32 consecutive indices starts
+// coherent; a block of samples of one tile, then the next tile (see below).
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ bool primary_ray(const RenderConst& rc, unsigned long long p, uint32_t& pixel, uint32_t& sample,
                                             float3& d) {
-    // (sample, tile, lane) from the path index without 64-bit or 32-bit hardware division where the host could
-    // prove the multiply-high forms exact (rc.small_index): p < 2^32, and tiles * tiles_x < 2^32
-    uint32_t s_local, pq, ty;
+    // path index -> (sample block, tile, sample within the block, lane): a warp is one 8x4 tile at one sample, the
+    // 2^sblk_shift samples of a block follow each other, then the next tile; the next block starts after the last tile.
+    // (Sample-major order — the whole image once per sample — keeps every pixel of a 4K image in flight at once: 133 MB
+    // of accumulator lines visited by scattered float4 atomics, in an L2 the queues and the tree want; and the warps an
+    // SM generates one after the other then start in different parts of the tree instead of on the same nodes.)
+    // No 64-bit or 32-bit hardware division where the host could prove the multiply-high forms exact
+    // (rc.small_index): p < 2^32.
+    uint32_t s_local, tile, ty;
+    const uint32_t l = (uint32_t)p & 31u;
     if (rc.small_index) {
-        const uint32_t p32 = (uint32_t)p;
-        s_local = __umulhi(p32, rc.magic_npix);
-        pq = p32 - s_local * (uint32_t)rc.npix_pad;
-        if (pq >= (uint32_t)rc.npix_pad) {  // the magic quotient can be one short
-            pq -= (uint32_t)rc.npix_pad;
-            ++s_local;
+        const uint32_t q = (uint32_t)p >> 5;
+        const uint32_t q2 = q >> rc.sblk_shift;
+        uint32_t s_blk = __umulhi(q2, rc.magic_tiles);
+        tile = q2 - s_blk * rc.tiles;
+        if (tile >= rc.tiles) {  // the magic quotient can be one short
+            tile -= rc.tiles;
+            ++s_blk;
         }
-        ty = __umulhi(pq >> 5, rc.magic_tiles_x);
-        if ((pq >> 5) - ty * rc.tiles_x >= rc.tiles_x) ++ty;
+        s_local = (s_blk << rc.sblk_shift) | (q & ((1u << rc.sblk_shift) - 1u));
+        ty = __umulhi(tile, rc.magic_tiles_x);
+        if (tile - ty * rc.tiles_x >= rc.tiles_x) ++ty;
     } else {
-        s_local = (uint32_t)(p / rc.npix_pad);
-        pq = (uint32_t)(p - (unsigned long long)s_local * rc.npix_pad);
-        ty = (pq >> 5) / rc.tiles_x;
+        const unsigned long long q = p >> 5;
+        const unsigned long long q2 = q >> rc.sblk_shift;
+        const uint32_t s_blk = (uint32_t)(q2 / rc.tiles);
+        tile = (uint32_t)(q2 - (unsigned long long)s_blk * rc.tiles);
+        s_local = (s_blk << rc.sblk_shift) | ((uint32_t)q & ((1u << rc.sblk_shift) - 1u));
+        ty = tile / rc.tiles_x;
     }
-    const uint32_t tile = pq >> 5, l = pq & 31u;
     const uint32_t tx = tile - ty * rc.tiles_x;
     const uint32_t col = tx * 8u + (l & 7u);
     const uint32_t row = ty * 4u + (l >> 3);
@@ -1095,7 +1112,9 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     if (!(p->flags & RRS_FLAG_SPLIT_KERNELS)) occ_ext = occ_shade = occ_fused;
     // one wave of the most register-hungry kernel: all stripes are resident at once
     const uint32_t regions = (uint32_t)s->num_sms * (uint32_t)std::min(occ_ext, occ_shade);
-    uint32_t want = p->queue_capacity ? p->queue_capacity : (1u << 22);
+    // rays in flight: 4M for the small-scene form, 8M for the BVH form (fewer, longer iterations: configuration 5 +2 %,
+    // configuration 4 +1.5 % over 4M; 16M / 32M within 1 % of 8M — profiles/ab_logs/queue_r02x.log)
+    uint32_t want = p->queue_capacity ? p->queue_capacity : (brute ? (1u << 22) : (1u << 23));
     uint32_t region_cap = std::max(32u, ((want + regions - 1) / regions + 31u) & ~31u);
     int rc_ = ensure_wavefront(s, regions, region_cap, err);
     if (rc_ != RRS_OK) return rc_;
@@ -1121,7 +1140,11 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     rc.npix_pad = (unsigned long long)rc.tiles_x * rc.tiles_y * 32ull;
     // floor(2^32 / d): __umulhi(n, magic) is floor(n / d) or one less for every n < 2^32 (corrected on the device)
     rc.small_index = (rc.npix_pad * (unsigned long long)p->spp < (1ull << 32)) ? 1u : 0u;
-    rc.magic_npix = (uint32_t)std::min<unsigned long long>((1ull << 32) / rc.npix_pad, 0xFFFFFFFFull);
+    rc.tiles = rc.tiles_x * rc.tiles_y;
+    rc.magic_tiles = (uint32_t)std::min<unsigned long long>((1ull << 32) / rc.tiles, 0xFFFFFFFFull);
+    // samples of one tile generated back to back: the largest power of two <= 2^RRS_SAMPLE_BLOCK_LOG2 that divides spp
+    rc.sblk_shift = 0;
+    while (rc.sblk_shift < RRS_SAMPLE_BLOCK_LOG2 && (p->spp >> rc.sblk_shift) % 2u == 0u && (p->spp >> rc.sblk_shift) > 1u) ++rc.sblk_shift;
     rc.magic_tiles_x = (uint32_t)std::min<unsigned long long>((1ull << 32) / rc.tiles_x, 0xFFFFFFFFull);
     rc.spp = p->spp;
     rc.sample_offset = p->sample_offset;
@@ -1139,15 +1162,21 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     // (written once, read once, ld/st.global.cs) and the accumulator is touched once per path.  Without help the
     // queue streams evict the tree: the 1M-triangle scene (20 MB of nodes + 64 MB of primitives, smaller than the
     // 126 MB L2) ran at a 56 % L2 hit rate and 181 B of DRAM reads per ray (profiles/r01o_c4_wavefront_metrics.csv).
-    // An access-policy window marks the tree persisting: over [nodes | primitives] when most of it fits the
-    // persisting carve-out, over the nodes alone otherwise.
-    // The set-aside is a device-wide limit: claimed for a render that pins a tree, released for one that does not
-    // (small scenes: their queues want the whole L2).  Touched only when the kind of render on the device changes.
+    // An access-policy window marks the top of the tree persisting: the first kL2PinBytes of the node array (numbered
+    // breadth-first at the top, depth-first below), with a set-aside of exactly that size.
+    // The set-aside (cudaLimitPersistingL2CacheSize) is a device-wide limit and every byte of it is lost to all other
+    // traffic, so it is sized to what is pinned, claimed by a render that pins a tree and released by one that does
+    // not (small scenes: their queues want the whole L2); it is touched only when its size on the device changes.
+    // Measured (profiles/ab_logs/ab_r02x_l2_set_aside_size.log, l2window_r02x_window_vs_none.log): round 2's first
+    // form — the device maximum set aside, [nodes | primitives] or all nodes pinned — was 1.3 % (config 4) and 7.7 %
+    // (config 5) SLOWER than no window at all; 8 / 24 / 48 MB set aside and pinned are +0.2 % / +0.6 % over none.
+    constexpr size_t kL2PinBytes = 32u << 20;
     bool window_set = false;
     const bool want_window = !brute && s->l2_persist_bytes && s->geom_blob && !(p->flags & RRS_FLAG_NO_L2_WINDOW);
+    const size_t pin_bytes = std::min(std::min(s->node_bytes, kL2PinBytes), std::min(s->l2_persist_bytes, s->l2_window_max));
     bool set_aside_ok = false;
     if (s->l2_persist_bytes && s->device >= 0 && s->device < kMaxDevices) {
-        const size_t want = want_window ? s->l2_persist_bytes : 0;
+        const size_t want = want_window ? pin_bytes : 0;
         std::atomic<size_t>& cur = g_l2_set_aside[s->device];
         if (cur.load() != want) {
             const bool ok = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess;
@@ -1156,14 +1185,11 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
         }
         set_aside_ok = cur.load() == want;
     }
-    if (want_window && set_aside_ok) {
-        size_t bytes = s->geom_bytes;
-        if ((double)s->l2_persist_bytes < 0.6 * (double)bytes) bytes = s->node_bytes;
-        bytes = std::min(bytes, s->l2_window_max);
+    if (want_window && set_aside_ok && pin_bytes) {
         cudaStreamAttrValue av{};
         av.accessPolicyWindow.base_ptr = s->geom_blob;
-        av.accessPolicyWindow.num_bytes = bytes;
-        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)s->l2_persist_bytes / (double)bytes);
+        av.accessPolicyWindow.num_bytes = pin_bytes;
+        av.accessPolicyWindow.hitRatio = 1.f;
         av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         window_set = cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;

@@ -62,6 +62,12 @@ static std::atomic<size_t> g_l2_set_aside[kMaxDevices];  // zero-initialised = t
 #ifndef RRS_SAMPLE_BLOCK_LOG2
 #define RRS_SAMPLE_BLOCK_LOG2 8
 #endif
+// Width (log2, in 8x4 tiles) of the vertical stripes the tiles are walked in: 1 / 4 / 16 / 64 tiles wide give
+// configuration 5 +0.7 / +0.9 / +1.0 / +0.9 % and configuration 4 +0.3 / +0.3 / +0.7 / +0.7 % over row-major order
+// (profiles/ab_logs/ab_r03a_tile_stripes.log).
+#ifndef RRS_TILE_STRIPE_LOG2
+#define RRS_TILE_STRIPE_LOG2 4
+#endif
 #ifndef RRS_QUEUE_STREAMING
 #define RRS_QUEUE_STREAMING 1
 #endif
@@ -126,12 +132,14 @@ __device__ __forceinline__ bool primary_ray(const RenderConst& rc, unsigned long
                                             float3& d) {
     // path index -> (sample block, tile, sample within the block, lane): a warp is one 8x4 tile at one sample, the
     // 2^sblk_shift samples of a block follow each other, then the next tile; the next block starts after the last tile.
+    // Tiles run row by row inside vertical stripes 2^ws_shift tiles wide, stripe after stripe: the ~1000 tiles in
+    // flight are a compact patch of the image (128 x 256 pixels), not a line 8 pixels high across its whole width.
     // (Sample-major order — the whole image once per sample — keeps every pixel of a 4K image in flight at once: 133 MB
     // of accumulator lines visited by scattered float4 atomics, in an L2 the queues and the tree want; and the warps an
     // SM generates one after the other then start in different parts of the tree instead of on the same nodes.)
     // No 64-bit or 32-bit hardware division where the host could prove the multiply-high forms exact
     // (rc.small_index): p < 2^32.
-    uint32_t s_local, tile, ty;
+    uint32_t s_local, tile, ty, stripe;
     const uint32_t l = (uint32_t)p & 31u;
     if (rc.small_index) {
         const uint32_t q = (uint32_t)p >> 5;
@@ -143,17 +151,24 @@ __device__ __forceinline__ bool primary_ray(const RenderConst& rc, unsigned long
             ++s_blk;
         }
         s_local = (s_blk << rc.sblk_shift) | (q & ((1u << rc.sblk_shift) - 1u));
-        ty = __umulhi(tile, rc.magic_tiles_x);
-        if (tile - ty * rc.tiles_x >= rc.tiles_x) ++ty;
+        const uint32_t a = tile >> rc.ws_shift;
+        stripe = __umulhi(a, rc.magic_tiles_y);
+        ty = a - stripe * rc.tiles_y;
+        if (ty >= rc.tiles_y) {
+            ty -= rc.tiles_y;
+            ++stripe;
+        }
     } else {
         const unsigned long long q = p >> 5;
         const unsigned long long q2 = q >> rc.sblk_shift;
         const uint32_t s_blk = (uint32_t)(q2 / rc.tiles);
         tile = (uint32_t)(q2 - (unsigned long long)s_blk * rc.tiles);
         s_local = (s_blk << rc.sblk_shift) | ((uint32_t)q & ((1u << rc.sblk_shift) - 1u));
-        ty = tile / rc.tiles_x;
+        const uint32_t a = tile >> rc.ws_shift;
+        stripe = a / rc.tiles_y;
+        ty = a - stripe * rc.tiles_y;
     }
-    const uint32_t tx = tile - ty * rc.tiles_x;
+    const uint32_t tx = (stripe << rc.ws_shift) | (tile & ((1u << rc.ws_shift) - 1u));
     const uint32_t col = tx * 8u + (l & 7u);
     const uint32_t row = ty * 4u + (l >> 3);
     if (!rc.exact_tiles && !(col < rc.cam.W && row < rc.cam.H)) return false;  // padded tile lane outside the image
@@ -1145,7 +1160,10 @@ int wf_render_accumulate(SceneImpl* s, const RrsCamera* cam, const RrsRenderPara
     // samples of one tile generated back to back: the largest power of two <= 2^RRS_SAMPLE_BLOCK_LOG2 that divides spp
     rc.sblk_shift = 0;
     while (rc.sblk_shift < RRS_SAMPLE_BLOCK_LOG2 && (p->spp >> rc.sblk_shift) % 2u == 0u && (p->spp >> rc.sblk_shift) > 1u) ++rc.sblk_shift;
-    rc.magic_tiles_x = (uint32_t)std::min<unsigned long long>((1ull << 32) / rc.tiles_x, 0xFFFFFFFFull);
+    rc.magic_tiles_y = (uint32_t)std::min<unsigned long long>((1ull << 32) / rc.tiles_y, 0xFFFFFFFFull);
+    // stripe width in tiles: the largest power of two <= 2^RRS_TILE_STRIPE_LOG2 that divides tiles_x
+    rc.ws_shift = 0;
+    while (rc.ws_shift < RRS_TILE_STRIPE_LOG2 && (rc.tiles_x >> rc.ws_shift) % 2u == 0u && (rc.tiles_x >> rc.ws_shift) > 1u) ++rc.ws_shift;
     rc.spp = p->spp;
     rc.sample_offset = p->sample_offset;
     rc.max_bounces = p->max_bounces;

@@ -32,8 +32,9 @@ struct RenderConst {
     DCamera cam;
     RrsCamera cam64;  // the f64 camera, for the f64 sphere path (primary directions as lib.rs:202-210 computes them)
     uint32_t tiles_x, tiles_y;
-    uint32_t small_index, magic_tiles, magic_tiles_x;  // division-free index math (primary_ray)
+    uint32_t small_index, magic_tiles, magic_tiles_y;  // division-free index math (primary_ray)
     uint32_t tiles, sblk_shift;   // tiles_x * tiles_y; log2 of the samples of one tile that are generated back to back
+    uint32_t ws_shift;            // log2 of the width, in tiles, of the vertical stripes the tiles are walked in
     uint32_t exact_tiles;         // 1: the image is a whole number of 8x4 tiles (no padded lanes)
     unsigned long long npix_pad;  // tiles_x * tiles_y * 32
     uint32_t spp, sample_offset, max_bounces;

@@ -36,7 +36,10 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
-# stdout carries the one JSON line and nothing else: NCCL's own banner ("NCCL version ...") goes to stderr
+# stdout carries the one JSON line and nothing else: NCCL's own banner ("NCCL version ...") goes to stderr.  NCCL honours
+# NCCL_DEBUG_FILE only above the VERSION level, where the banner is printed straight to stdout.
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402

@@ -307,6 +307,24 @@ int rrs_intersect(RrsScene* scene, const RrsRay* rays, size_t n, int32_t* obj_id
 int rrs_material_evaluate(RrsScene* scene, uint32_t material, const double* normal_view, const double* u,
                           size_t n, float* out);
 
+/* Material::evaluate WITH a caller's pdf — the reference's dormant next-event-estimation hook.  material.rs:91-109 hands
+ * `pdf: Option<Pdf>` to every Bsdf::scatter; the one arm that looks at it is LambertianDiffuse::scatter (material.rs:259-281),
+ * reached directly or as Plastic's diffuse lobe (:588): it samples and weights the lobe with
+ * Pdf::Mix(MixKind::Constant(0.5), pdf, Pdf::Cosine) (generate :1028-1034, value :951-959).  Here pdf =
+ * Pdf::Hittable(&geometry of `light`) (value :943-950, generate :1027; Hittable::area / sample geometry.rs:138-152,
+ * 284-299,381-387), `light` being the caller's f64 record of the sampled primitive (any entry of RrsSceneDesc.prims).
+ *   pos_normal_view  n x 9 doubles: shaded position, unit normal, unit view
+ *   u                n x 4 uniforms in call order (Lambertian: side of the mix, then the two draws of the chosen
+ *                    generator; Plastic: its lobe choice first)
+ *   out              n x 7 doubles [scatter flag, color rgb, direction xyz]
+ * radiance() passes None (lib.rs:532): no render reaches this, the reference's or ours.  The hook is therefore
+ * evaluated in f64 with the reference's operation order (held to the oracle at rounding level); materials and lobes
+ * that ignore the pdf return what rrs_material_evaluate returns (fp32 production shading, draws u[0..2]).
+ * Reference quirks kept as written: Sphere::sample is not uniform (its own FIXME), Triangle::sample returns the
+ * origin, Pdf::Hittable::value divides by the cosine at the shaded point. */
+int rrs_material_evaluate_pdf(RrsScene* scene, uint32_t material, const RrsPrim* light, const double* pos_normal_view,
+                              const double* u, size_t n, double* out);
+
 /* Scene::background (lib.rs:254-285) for a batch of directions (n x 3 doubles) -> n x 3 floats. */
 int rrs_background(RrsScene* scene, const double* dirs, size_t n, float* out);
 

@@ -44,6 +44,8 @@ def lib() -> C.CDLL:
         L.orc_primary_rays.argtypes = [vp, u32, u32, vp, vp, vp, u64, u64, i32, vp]
         L.orc_render.argtypes = [vp, vp, u32, u32, u32, u32, u32, u64, i32, i32, vp, vp]
         L.orc_material_evaluate.argtypes = [vp, vp, vp, u64, vp]
+        L.orc_material_evaluate_pdf.argtypes = [vp, vp, vp, vp, u64, vp]
+        L.orc_hittable_area_sample.argtypes = [vp, vp, vp]
         L.orc_background.argtypes = [vp, vp, u64, vp]
         L.orc_sphere_intersect.restype = i32
         L.orc_sphere_intersect.argtypes = [dbl, vp, vp, vp]
@@ -194,6 +196,23 @@ def material_evaluate(mat_row, normal_view, u) -> np.ndarray:
     out = np.zeros((nv.shape[0], 7))
     lib().orc_material_evaluate(m.ctypes.data, nv.ctypes.data, uu.ctypes.data, nv.shape[0], out.ctypes.data)
     return out
+
+
+def material_evaluate_pdf(mat_row, obj_row, pos_normal_view, u) -> np.ndarray:
+    """Material::evaluate with pdf = Some(Pdf::Hittable(geometry of obj_row)) — material.rs:91-109,259-281,943-959,1027-1034.
+    obj_row: 12 doubles as the scene tables carry them; pos_normal_view: n x 9; u: n x 4 draws in call order."""
+    m, g, q, uu = _d(mat_row), _d(obj_row), _d(pos_normal_view).reshape(-1, 9), _d(u).reshape(-1, 4)
+    out = np.zeros((q.shape[0], 7))
+    lib().orc_material_evaluate_pdf(m.ctypes.data, g.ctypes.data, q.ctypes.data, uu.ctypes.data, q.shape[0], out.ctypes.data)
+    return out
+
+
+def hittable_area_sample(obj_row, u2):
+    """(Hittable::area, Hittable::sample with the two draws u2) of one object row — geometry.rs:138-152,284-299,381-387"""
+    g, uu = _d(obj_row), _d(u2)
+    out = np.zeros(4)
+    lib().orc_hittable_area_sample(g.ctypes.data, uu.ctypes.data, out.ctypes.data)
+    return float(out[0]), out[1:].copy()
 
 
 def sphere_intersect(radius, origin, ray6):

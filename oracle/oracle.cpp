@@ -206,13 +206,23 @@ struct AABB {
 
 enum Axis { AX_X = 0, AX_XREV = 1, AX_Y = 2, AX_YREV = 3, AX_Z = 4, AX_ZREV = 5 };
 
-// trait Hittable, geometry.rs:15-38 (intersect / normal / bbox; area+sample are never
-// reached from radiance() because it passes pdf=None, lib.rs:532).
+struct DrawSrc {
+    // hands out the material draws of one bounce in call order (words 0..2; a fourth for Plastic's diffuse lobe under a caller's pdf)
+    const double* u;
+    int next;
+    double draw() { return u[next++]; }
+};
+
+// trait Hittable, geometry.rs:15-38.  area + sample serve Pdf::Hittable only (material.rs:943-950,1027), which
+// radiance() never reaches because it passes pdf=None (lib.rs:532); they are restated for the dormant
+// next-event-estimation hook, material_evaluate(..., light) below.
 struct Hittable {
     virtual ~Hittable() {}
     virtual bool intersect(const Ray& ray, double& t) const = 0;
     virtual V3 normal(V3 p) const = 0;
     virtual AABB bbox() const = 0;
+    virtual double area() const = 0;
+    virtual V3 sample(DrawSrc& rs) const = 0;
 };
 
 struct Sphere final : Hittable {
@@ -240,6 +250,17 @@ struct Sphere final : Hittable {
         return false;
     }
     V3 normal(V3 p) const override { return unit(p - origin); }
+    // geometry.rs:138-140
+    double area() const override { return 4. * PI * radius2; }
+    // geometry.rs:142-152 ("FIXME: This is not uniform on the unit sphere..." — restated as written)
+    V3 sample(DrawSrc& rs) const override {
+        double u = rs.draw();
+        double phi = 2. * PI * rs.draw();
+        double x = std::cos(phi) * 2. * std::sqrt(u * (1. - u));
+        double y = std::sin(phi) * 2. * std::sqrt(u * (1. - u));
+        double z = 1. - 2. * u;
+        return v3(x, y, z) * std::sqrt(radius2) + origin;
+    }
     // geometry.rs:687-696
     AABB bbox() const override {
         double r = std::sqrt(radius2);
@@ -291,6 +312,18 @@ struct Plane final : Hittable {
             default: return v3(0., 0., -1.);
         }
     }
+    // geometry.rs:284-286
+    double area() const override { return (umax - umin) * (vmax - vmin); }
+    // geometry.rs:288-299
+    V3 sample(DrawSrc& rs) const override {
+        double u = rs.draw() * (umax - umin) + umin;
+        double v = rs.draw() * (vmax - vmin) + vmin;
+        switch (axis) {
+            case AX_X: case AX_XREV: return v3(pos, u, v);
+            case AX_Y: case AX_YREV: return v3(u, pos, v);
+            default: return v3(u, v, pos);
+        }
+    }
     // geometry.rs:699-718
     AABB bbox() const override {
         switch (axis) {
@@ -303,14 +336,14 @@ struct Plane final : Hittable {
 
 struct Triangle final : Hittable {
     V3 p1, p2, p3, e1, e2, n;
-    double area;
+    double tri_area;
     // geometry.rs:341-355
     Triangle(V3 a, V3 b, V3 c) : p1(a), p2(b), p3(c) {
         e1 = p2 - p1;
         e2 = p3 - p1;
         V3 nn = cross(e1, e2);
         n = unit(nn);
-        area = mag(nn) / 2.;
+        tri_area = mag(nn) / 2.;
     }
     // geometry.rs:359-375
     bool intersect(const Ray& ray, double& t) const override {
@@ -326,6 +359,10 @@ struct Triangle final : Hittable {
         return true;
     }
     V3 normal(V3) const override { return n; }
+    // geometry.rs:381-383 (area = |e1 x e2| / 2, set by Triangle::new)
+    double area() const override { return tri_area; }
+    // geometry.rs:385-387: the reference's stub returns the origin and draws nothing
+    V3 sample(DrawSrc&) const override { return v3(0., 0., 0.); }
     // geometry.rs:721-733
     AABB bbox() const override {
         return AABB{rmin(p1.x, rmin(p2.x, p3.x)), rmax(p1.x, rmax(p2.x, p3.x)),
@@ -412,13 +449,6 @@ static inline V3 fresnel_value(const Material& m, int kind, V3 n, V3 v, Directio
     }
     return schlick_vec(m.r0, n, v);
 }
-
-struct DrawSrc {
-    // hands out the material draws of one bounce in call order (words 0..2)
-    const double* u;
-    int next;
-    double draw() { return u[next++]; }
-};
 
 // Pdf::Cosine generate material.rs:982-993
 static inline V3 cosine_generate(V3 n, DrawSrc& rs) {
@@ -544,6 +574,29 @@ static inline ScatterEvent lambert_scatter(V3 color, V3 position, V3 n, DrawSrc&
     return ScatterEvent{true, c, Ray{position, l}};
 }
 
+// Pdf::Hittable value / generate, material.rs:943-950 and :1027 — the caller's pdf of the dormant next-event-estimation hook
+static inline double pdf_hittable_value(const Hittable& g, V3 position, V3 n, V3 l) {
+    Ray ray{position, l};
+    double t;
+    if (g.intersect(ray, t)) return mag2(position - ray.point(t)) / (dot(n, l) * g.area());
+    return 0.;
+}
+static inline V3 pdf_hittable_generate(const Hittable& g, V3 position, DrawSrc& rs) { return unit(g.sample(rs) - position); }
+
+// LambertianDiffuse::scatter with pdf=Some(Pdf::Hittable(light)) material.rs:259-281: the lobe is sampled from and weighted with
+// Pdf::Mix(MixKind::Constant(0.5), pdf, Pdf::Cosine) — generate :1028-1034 (one draw picks the side), value :951-959
+// (INFINITY below the surface, else the blend of the two densities).
+static inline ScatterEvent lambert_scatter_mix(V3 color, V3 position, V3 n, const Hittable& light, DrawSrc& rs) {
+    const double factor = 0.5;  // MixKind::Constant(0.5).value, material.rs:1529-1534
+    V3 l = rs.draw() < factor ? pdf_hittable_generate(light, position, rs) : cosine_generate(n, rs);
+    double pdfv;
+    if (dot(n, l) < 0.) pdfv = std::numeric_limits<double>::infinity();
+    else pdfv = factor * pdf_hittable_value(light, position, n, l) + (1. - factor) * (dot(n, l) * FRAC_1_PI);
+    V3 brdf = color * FRAC_1_PI;  // :1233-1243
+    V3 c = brdf * dot(n, l) / pdfv;
+    return ScatterEvent{true, c, Ray{position, l}};
+}
+
 // CookTorrance::scatter material.rs:403-424
 static inline ScatterEvent ct_scatter(const Material& m, int fresnel_kind, V3 color, V3 position,
                                       V3 n, V3 v, DrawSrc& rs) {
@@ -553,10 +606,14 @@ static inline ScatterEvent ct_scatter(const Material& m, int fresnel_kind, V3 co
                                   beckmann_pdf_value_reflect(m.alpha2, n, l, v));
 }
 
-// Material::evaluate material.rs:91-109 (pdf = None always, lib.rs:532)
-static ScatterEvent material_evaluate(const Material& m, V3 position, V3 normal, V3 view, DrawSrc& rs) {
+// Material::evaluate material.rs:91-109.  radiance() always passes pdf = None (lib.rs:532): light == nullptr.  A caller's
+// pdf (light != nullptr: Pdf::Hittable(light)) is handed to every Bsdf::scatter, and only LambertianDiffuse::scatter
+// — reached directly or as Plastic's diffuse lobe — looks at it; every other arm names its parameter `_pdf`.
+static ScatterEvent material_evaluate(const Material& m, V3 position, V3 normal, V3 view, DrawSrc& rs,
+                                      const Hittable* light = nullptr) {
     switch (m.tag) {
         case MAT_LAMBERTIAN:
+            if (light) return lambert_scatter_mix(m.color, position, normal, *light, rs);
             return lambert_scatter(m.color, position, normal, rs);
         case MAT_REFLECT: {  // material.rs:283-303
             V3 l = reflect(normal, view);
@@ -648,6 +705,7 @@ static ScatterEvent material_evaluate(const Material& m, V3 position, V3 normal,
                 if (e.scatter) e.color = e.color / fresnel;
                 return e;
             }
+            if (light) return lambert_scatter_mix(m.color, position, normal, *light, rs);  // :588 forwards the pdf
             return lambert_scatter(m.color, position, normal, rs);
         }
         default:
@@ -1249,6 +1307,43 @@ void orc_material_evaluate(const double* mat_row, const double* nv, const double
         o[1] = e.color.x; o[2] = e.color.y; o[3] = e.color.z;
         o[4] = e.ray.d.x; o[5] = e.ray.d.y; o[6] = e.ray.d.z;
     }
+}
+
+// Material::evaluate with pdf = Some(Pdf::Hittable(light)) for a batch (the dormant next-event-estimation hook).
+// obj_row: 12 doubles as orc_scene_create takes them (the light's geometry).  pnv: n x 9 (position, unit normal, unit view).
+// u: n x 4 draws in call order.  out: n x 7 as orc_material_evaluate.
+void orc_material_evaluate_pdf(const double* mat_row, const double* obj_row, const double* pnv, const double* u, uint64_t n,
+                               double* out) {
+    Material m = material_from_row(mat_row);
+    std::unique_ptr<Hittable> g;
+    const double* r = obj_row;
+    int type = (int)r[0];
+    if (type == 0) g.reset(new Sphere(r[3], v3(r[4], r[5], r[6])));
+    else if (type == 1) g.reset(new Plane((int)r[3], r[4], r[5], r[6], r[7], r[8]));
+    else g.reset(new Triangle(v3(r[3], r[4], r[5]), v3(r[6], r[7], r[8]), v3(r[9], r[10], r[11])));
+    for (uint64_t i = 0; i < n; ++i) {
+        const double* q = pnv + i * 9;
+        double uu[4] = {u[i * 4], u[i * 4 + 1], u[i * 4 + 2], u[i * 4 + 3]};
+        DrawSrc rs{uu, 0};
+        ScatterEvent e = material_evaluate(m, v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]), v3(q[6], q[7], q[8]), rs, g.get());
+        double* o = out + i * 7;
+        o[0] = e.scatter ? 1. : 0.;
+        o[1] = e.color.x; o[2] = e.color.y; o[3] = e.color.z;
+        o[4] = e.ray.d.x; o[5] = e.ray.d.y; o[6] = e.ray.d.z;
+    }
+}
+// Hittable::area and one Hittable::sample of the same row (u2: the two draws) -> out4 = [area, point xyz]
+void orc_hittable_area_sample(const double* obj_row, const double* u2, double* out4) {
+    const double* r = obj_row;
+    std::unique_ptr<Hittable> g;
+    int type = (int)r[0];
+    if (type == 0) g.reset(new Sphere(r[3], v3(r[4], r[5], r[6])));
+    else if (type == 1) g.reset(new Plane((int)r[3], r[4], r[5], r[6], r[7], r[8]));
+    else g.reset(new Triangle(v3(r[3], r[4], r[5]), v3(r[6], r[7], r[8]), v3(r[9], r[10], r[11])));
+    double uu[2] = {u2[0], u2[1]};
+    DrawSrc rs{uu, 0};
+    V3 p = g->sample(rs);
+    out4[0] = g->area(); out4[1] = p.x; out4[2] = p.y; out4[3] = p.z;
 }
 
 // Scene::background for a batch of directions (n x 3) -> n x 3

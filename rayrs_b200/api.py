@@ -348,6 +348,18 @@ class Scene:
                                                          nv.shape[0], out.ctypes.data))
         return out
 
+    def material_evaluate_pdf(self, material: int, light, pos_normal_view: np.ndarray, u: np.ndarray) -> np.ndarray:
+        """Material::evaluate(position, normal, view, Some(Pdf::Hittable(light))) — material.rs:91-109,259-281,943-959,1027-1034:
+        the reference's dormant next-event-estimation hook.  `light`: the _ffi.RrsPrim record of the sampled primitive
+        (an entry of flat()[5]); pos_normal_view n x 9; u n x 4 draws in call order -> n x 7 doubles."""
+        self._need_gpu()
+        q = np.ascontiguousarray(pos_normal_view, dtype=np.float64).reshape(-1, 9)
+        uu = np.ascontiguousarray(u, dtype=np.float64).reshape(-1, 4)
+        out = np.zeros((q.shape[0], 7), dtype=np.float64)
+        _ffi.check(_ffi.cuda_lib().rrs_material_evaluate_pdf(self.handle, int(material), C.byref(light), q.ctypes.data, uu.ctypes.data,
+                                                             q.shape[0], out.ctypes.data))
+        return out
+
     def background(self, dirs: np.ndarray) -> np.ndarray:
         self._need_gpu()
         d = np.ascontiguousarray(dirs, dtype=np.float64).reshape(-1, 3)

@@ -27,7 +27,7 @@ NVCC_FLAGS = GENCODE + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
 # wavefront.cu: approximate fp32 division / square root (<= 2 ulp) — every fp32 result on this path is
 # compared against an f64 oracle at 1e-5 relative, and the decisions that must be exact (watertight
 # edge functions, the f64 sphere path) use explicit round-to-nearest intrinsics
-EXTRA = {"verify_f64.cu": ["-fmad=false"], "bvh_build.cu": ["-fmad=false"], "wavefront.cu": ["-prec-div=false", "-prec-sqrt=false"]}
+EXTRA = {"verify_f64.cu": ["-fmad=false"], "nee.cu": ["-fmad=false"], "bvh_build.cu": ["-fmad=false"], "wavefront.cu": ["-prec-div=false", "-prec-sqrt=false"]}
 
 CUDA_LIB = ROOT / "librayrs_b200.so"
 HOST_LIB = ROOT / "librayrs_host.so"

@@ -595,6 +595,14 @@ int rrs_material_evaluate(RrsScene* scene, uint32_t material, const double* norm
     return rc == RRS_OK ? rc : fail(rc, err);
 }
 
+int rrs_material_evaluate_pdf(RrsScene* scene, uint32_t material, const RrsPrim* light, const double* pos_normal_view,
+                              const double* u, size_t n, double* out) {
+    if (!scene || !light || (n && (!pos_normal_view || !u || !out))) return fail(RRS_ERR_INVALID, "null argument");
+    std::string err;
+    int rc = nee_material_evaluate_pdf(&scene->impl, material, light, pos_normal_view, u, n, out, err);
+    return rc == RRS_OK ? rc : fail(rc, err);
+}
+
 int rrs_background(RrsScene* scene, const double* dirs, size_t n, float* out) {
     if (!scene || (n && (!dirs || !out))) return fail(RRS_ERR_INVALID, "null argument");
     std::string err;

@@ -119,6 +119,9 @@ void wf_finish_stats(SceneImpl* s);  // waits for the last render of this scene 
 void wf_free(SceneImpl* s);
 // verify_f64.cu
 int vf_intersect64(SceneImpl* s, const RrsRay* rays, size_t n, int32_t* obj_id, double* t, std::string& err);
+// nee.cu
+int nee_material_evaluate_pdf(SceneImpl* s, uint32_t material, const RrsPrim* light, const double* pnv, const double* u,
+                              size_t n, double* out, std::string& err);
 
 // Scratch device allocation of one entry point: freed on every return path, including the early returns of
 // RRS_CUDA_CHECK.

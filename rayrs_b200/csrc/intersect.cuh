@@ -11,13 +11,21 @@
 namespace rrs {
 
 // 256-bit read-only loads (LDG.E.ENL2.256.CONSTANT on sm_100a): one instruction per node / primitive half.
+// RRS_NODE_LD_HINT / RRS_PRIM_LD_HINT: L1 eviction priority of the node / primitive fetches (measurement switches:
+// ".L1::evict_last", ".L1::evict_first", ".L1::no_allocate"; empty = evict_normal).
+#ifndef RRS_NODE_LD_HINT
+#define RRS_NODE_LD_HINT ""
+#endif
+#ifndef RRS_PRIM_LD_HINT
+#define RRS_PRIM_LD_HINT ""
+#endif
 __device__ __forceinline__ void ldg256(const void* p, uint32_t (&v)[8]) {
-    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc" RRS_NODE_LD_HINT ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "l"(p));
 }
 __device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc" RRS_PRIM_LD_HINT ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                  : "l"(p));
 }

@@ -308,6 +308,12 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
     // inner-node steps a lane takes per ballot round (round 1 swept 1..8: 3-4 best, profiles/ab_logs/sweep_tune*.log;
     // round 2, after the register diet: 2 / 3 / 4 / 6 within +-0.5 %, ab_r02n_sweep.log)
     constexpr uint32_t kNodeSteps = 4;
+    // the node rounds go on while want * RRS_LEAF_NUM >= parked * RRS_LEAF_DEN lanes ask for one (1 / 1: as many lanes on
+    // inner nodes as are parked on a leaf); 2 / 1 = leaves later with fuller warps, 1 / 2 = leaves sooner — measurement switch
+#ifndef RRS_LEAF_NUM
+#define RRS_LEAF_NUM 1
+#define RRS_LEAF_DEN 1
+#endif
     SStack stack;
     stack.init(s_stack + threadIdx.x, blockDim.x);
     TravCounters cnt{0, 0};
@@ -345,7 +351,7 @@ __device__ __forceinline__ void phase_extend(const DScene& sc, DCounters* __rest
             const bool inner = trav_on_inner(tv);
             const uint32_t want = __ballot_sync(FULL, inner);
             const uint32_t parked = __ballot_sync(FULL, !inner && tv.cur != TRAV_DONE);
-            if (want == 0u || __popc(want) < __popc(parked)) break;
+            if (want == 0u || __popc(want) * RRS_LEAF_NUM < __popc(parked) * RRS_LEAF_DEN) break;
             if (inner) {
                 trav_node_step<COUNT>(sc, r, tv, stack, cnt);
 #pragma unroll 1

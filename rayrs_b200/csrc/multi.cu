@@ -43,7 +43,8 @@ NcclApi& nccl() {
             if (api.lib) break;
         }
         if (!api.lib) {
-            api.error = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "not found");
+            const char* why = dlerror();  // one call: dlerror() clears the message it returns
+            api.error = std::string("cannot load libnccl.so.2: ") + (why ? why : "not found");
             return;
         }
         bool ok = true;
@@ -70,8 +71,6 @@ NcclApi& nccl() {
     });
     return api;
 }
-
-thread_local std::string g_multi_error;
 
 }  // namespace
 

@@ -372,6 +372,12 @@ def run_ours(args):
     first, count = api.sample_range(rank, world, spp_total)
     specs = cfg.specs()
     hdri = scenes.synthetic_hdri(2048, 1024)
+    # the process's CUDA start-up (context creation on this device) is paid once per process whatever the scene: timed on
+    # its own so that scene_setup_s below is the scene's setup, not the driver's
+    t_cuda = time.time()
+    torch.zeros(1, device=dev)
+    torch.cuda.synchronize(dev)
+    t_cuda = time.time() - t_cuda
     t_setup = time.time()
     built = [(spec, spec.scene(hdri, device=local, with_f64=False, device_build=True, topology=False), spec.camera()) for spec in specs]
     t_setup = time.time() - t_setup
@@ -562,7 +568,7 @@ def run_ours(args):
                        "max_bounces": cfg.max_bounces, "hdri": "synthetic 2048x1024",
                        "parallelism": f"sample-split x{world} inside rrs_render_multi, one ncclReduce(sum) of the fp32 radiance buffer",
                        "l2": "256 MB L2 flush between steps (inside the timed region)",
-                       "rays_per_step": rays_all / args.steps, "scene_setup_s": t_setup, "bvh_build_s": build_s,
+                       "rays_per_step": rays_all / args.steps, "scene_setup_s": t_setup, "cuda_startup_s": t_cuda, "bvh_build_s": build_s,
                        "bvh_build": "same-tree build on the device (rrs_bvh_build), numbering + flattening on the host", "bvh_build_timing_s": build_timing},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cam_bytes,
                     "d2h_bytes_per_step": W * H * 3 * 4 * len(built), "steps": e2e_steps, "ms_per_step": e2e_step_ms,

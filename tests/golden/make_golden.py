@@ -5,7 +5,8 @@
 The reference itself cannot run here (Rust, no toolchain), so these are outputs of the pinned restatement
 (oracle/oracle.cpp, checked against the reference's own KATs in tests/test_oracle_kat.py) on seeded inputs.
 They freeze the oracle against silent drift and give the GPU tests a checker that does not depend on
-rebuilding it: closest hits on fixed ray sets, one sample-matched render, one output-stage byte image.
+rebuilding it: closest hits on fixed ray sets, one sample-matched render, one output-stage byte image, and the
+Pdf::Hittable hook (pdf_hook_golden.npz; `--pdf-hook-only` regenerates that file alone).
 """
 import sys
 from pathlib import Path
@@ -63,5 +64,24 @@ def main():
     print("wrote", OUT / "oracle_golden.npz", sum(v.nbytes for v in out.values()), "bytes uncompressed")
 
 
+def pdf_hook():
+    """tests/golden/pdf_hook_golden.npz: Material::evaluate with Some(Pdf::Hittable(light)) (the dormant next-event-estimation
+    hook, tests/test_pdf_hook.py) on a seeded input set, for every light kind, Lambertian and Plastic."""
+    from test_pdf_hook import LIGHTS, MATS, _inputs, _tables
+    from rayrs_b200.api import build_tables
+    objs, light_obj = _tables()
+    mats = build_tables(objs).mats
+    q, u = _inputs(512, 5)
+    out = {"q": q, "u": u}
+    for kind in sorted(LIGHTS):
+        row = objs[light_obj[kind]].rows[0]
+        for mname in ("lambertian", "plastic"):
+            out[f"{kind}/{mname}"] = oracle.material_evaluate_pdf(mats[list(MATS).index(mname)], row, q, u)
+    np.savez_compressed(OUT / "pdf_hook_golden.npz", **out)
+    print("wrote", OUT / "pdf_hook_golden.npz")
+
+
 if __name__ == "__main__":
-    main()
+    if "--pdf-hook-only" not in sys.argv:
+        main()
+    pdf_hook()

@@ -198,6 +198,20 @@ def test_oracle_lambertian_with_pdf_matches_numpy_restatement(native_built, kind
     assert lit.sum() > 1000 and np.all(o[lit, 1] < 2.0 * ALBEDO[0])
 
 
+def test_oracle_reproduces_pdf_hook_golden(native_built):
+    """tests/golden/pdf_hook_golden.npz (tests/golden/make_golden.py): the restatement frozen against silent drift"""
+    from pathlib import Path
+    g = np.load(Path(__file__).resolve().parent / "golden" / "pdf_hook_golden.npz")
+    objs, light_obj = _tables()
+    mats = Scene_tables(objs).mats
+    q, u = _inputs(512, 5)
+    assert np.array_equal(q, g["q"]) and np.array_equal(u, g["u"])
+    for kind in sorted(LIGHTS):
+        for mname in ("lambertian", "plastic"):
+            got = oracle.material_evaluate_pdf(mats[list(MATS).index(mname)], objs[light_obj[kind]].rows[0], q, u)
+            assert np.array_equal(got, g[f"{kind}/{mname}"], equal_nan=True), (kind, mname)
+
+
 def Scene_tables(objs):
     from rayrs_b200.api import build_tables
     return build_tables(objs)

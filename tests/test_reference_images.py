@@ -1,0 +1,148 @@
+"""A pin on the reference's OWN OUTPUT: the six renders rayrs ships (examples/*.png, rendered by the reference itself).
+
+Their colours pin nothing (unshipped HDRI, unknown spp) — their geometry does.  Where the spheres' silhouettes fall in the
+image depends only on Camera::new (lib.rs:99-133: the F9 field-of-view quirk `z = width / tan(fov / 2)`, the ppc rounding),
+Camera::x_pixels / y_pixels, generate_primary_ray (lib.rs:202-210), the mirrored pixel mapping of the tile loop
+(main.rs:71-76, F8), the constants of test_scenes.rs:14-44,163-256 and Sphere::intersect — the part of the path SURVEY.md 8c
+lists as pinned by no reference test.  tests/golden/reference_image_pins.npz holds the edge maps measured from the PNGs
+(tests/golden/make_reference_image_pins.py; the images themselves are not in the repository).
+
+Held to them: the oracle's primary-ray hit mask (CPU) and the CUDA path's (rrs_intersect, GPU), with the reference's exact
+camera arguments.  Each test also shows its own power: the same mask shifted by 3 pixels, or built with the textbook
+field of view instead of the reference's quirk, or with the sphere row mirrored, does NOT fit.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+from scipy.ndimage import binary_erosion, distance_transform_edt
+
+import oracle
+from rayrs_b200 import scenes
+from rayrs_b200.api import Camera
+
+PINS = np.load(Path(__file__).resolve().parent / "golden" / "reference_image_pins.npz")
+
+# Camera::new arguments exactly as test_scenes.rs:27-35 (single sphere) and :194-202 (sphere rows) write them
+SINGLE = dict(origin=(0.0, 5.0, 10.0), up=(0.0, 1.0, 0.0), lookat=(0.0, 1.0, 0.0), fov=50.0, width=1920.0 / 500.0,
+              height=1080.0 / 500.0, ppi=100)
+ROW = dict(origin=(0.0, 10.0, 20.0), up=(0.0, 1.0, 0.0), lookat=(0.0, 1.0, 0.0), fov=72.0, width=1920.0 / 500.0,
+           height=400.0 / 500.0, ppi=125)
+CASES = {
+    "diffuse_single_sphere": (scenes.diffuse_single_sphere, SINGLE),
+    "copper_sphere": (scenes.copper_single_sphere, SINGLE),
+    "cook_torrance_glass_sphere": (scenes.cook_torrance_glass_single_sphere, SINGLE),
+    "spheres_metallic": (scenes.cook_torrance_spheres_metallic, ROW),
+    "spheres_plastic": (scenes.cook_torrance_spheres_plastic, ROW),
+    "cook_torrance_spheres_frosted_glass": (scenes.cook_torrance_spheres_frosted_glass, ROW),
+}
+NEAR = 1.5  # pixels
+
+
+def _primary_rays(cam17, W, H):
+    rows, cols = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    return oracle.primary_rays(cam17, W, H, rows.ravel(), cols.ravel(), np.zeros(rows.size))
+
+
+def _edge_distance(name):
+    W, H = (int(v) for v in PINS[f"{name}/size"])
+    e = np.zeros((H, W), dtype=bool)
+    xy = PINS[f"{name}/edge_xy"].astype(np.int64)
+    e[xy[:, 1], xy[:, 0]] = True
+    return distance_transform_edt(~e), W, H
+
+
+def _fit(dist, mask, shift=(0, 0)):
+    """fraction of the silhouette's pixels that lie within NEAR pixels of an edge of the reference image"""
+    b = mask & ~binary_erosion(mask)
+    b = np.roll(np.roll(b, shift[0], 0), shift[1], 1)
+    return float((dist[b] <= NEAR).mean())
+
+
+def _check_silhouettes(name, ids_of):
+    builder, cam_args = CASES[name]
+    dist, W, H = _edge_distance(name)
+    cam = Camera(**cam_args)
+    # Camera::x_pixels / y_pixels with the reference's film constants give the size of the shipped render
+    assert (cam.x_pixels(), cam.y_pixels()) == (W, H)
+    ids = ids_of(builder(W, H), cam.derived17(), W, H)
+    spheres = ids >= 1  # object 0 is the floor (test_scenes.rs:22-24,190-191)
+    assert 0.05 < spheres.mean() < 0.6
+    fit = _fit(dist, spheres)
+    assert fit >= 0.80, (name, fit)
+    for shift in ((0, 3), (0, -3), (3, 0), (-3, 0), (3, 3), (-3, -3)):
+        other = _fit(dist, spheres, shift)
+        assert other <= fit - 0.08, (name, shift, other, fit)
+    return ids, fit, dist, cam
+
+
+def _oracle_ids(spec, cam17, W, H):
+    osc = oracle.OracleScene(spec.tables(), scenes.synthetic_hdri(64, 32).pixels)
+    ids, _ = osc.intersect(_primary_rays(cam17, W, H))
+    osc.close()
+    return ids.reshape(H, W)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_silhouettes_fit_the_reference_renders(native_built, name):
+    ids, fit, dist, cam = _check_silhouettes(name, _oracle_ids)
+    # the textbook field of view, z = (width / 2) / tan(fov / 2), instead of the reference's z = width / tan(fov / 2)
+    # (lib.rs:131): the silhouettes land elsewhere
+    builder, cam_args = CASES[name]
+    W, H = cam.x_pixels(), cam.y_pixels()
+    c17 = cam.derived17().copy()
+    c17[9:12] *= 0.5  # z_scaled
+    wrong = _oracle_ids(builder(W, H), c17, W, H) >= 1
+    assert _fit(dist, wrong) <= fit - 0.25, (name, _fit(dist, wrong), fit)
+    print(f"[{name}] {fit * 100:.1f} % of the silhouette within {NEAR} px of an edge of the reference render; "
+          f"textbook fov {_fit(dist, wrong) * 100:.1f} %")
+
+
+def _sharpness_per_sphere(name, ids):
+    sh = PINS[f"{name}/sharpness_4x4"].astype(np.float64)
+    hb, wb = sh.shape
+    out = []
+    for k in range(1, 8):
+        inner = binary_erosion(ids == k, iterations=10)
+        blocks = inner[:hb * 4, :wb * 4].reshape(hb, 4, wb, 4).all(axis=(1, 3))
+        assert blocks.sum() > 300
+        out.append(float(sh[blocks].mean()))
+    return out
+
+
+def test_sphere_row_orientation_and_roughness_order(native_built):
+    """test_scenes.rs:178-189,213-224: sphere i sits at x = 2.2 (i - 3) with alpha = 0.01 (4 i + 1).  In the reference's
+    render the mirror-like end is on the LEFT; the interior of each sphere is less sharp than its smoother neighbour's.
+    A mapping mirrored about the vertical axis (a `width - j` dropped from main.rs:75, or e_x flipped) reverses it."""
+    cam = Camera(**ROW)
+    W, H = cam.x_pixels(), cam.y_pixels()
+    ids = _oracle_ids(scenes.cook_torrance_spheres_metallic(W, H), cam.derived17(), W, H)
+    centres = [float(np.nonzero((ids == k).any(axis=0))[0].mean()) for k in range(1, 8)]
+    assert centres == sorted(centres) and centres[0] < W / 4 and centres[-1] > 3 * W / 4  # sphere 0 (alpha 0.01) on the left
+    sharp = _sharpness_per_sphere("spheres_metallic", ids)
+    assert all(a > b for a, b in zip(sharp, sharp[1:])), sharp          # strictly decreasing with alpha
+    assert sharp[0] > 1.8 * sharp[-1]
+    mirrored = _sharpness_per_sphere("spheres_metallic", ids[:, ::-1])
+    assert all(a < b for a, b in zip(mirrored, mirrored[1:]))           # the mirrored hypothesis contradicts the image
+    plastic = _sharpness_per_sphere("spheres_plastic", _oracle_ids(scenes.cook_torrance_spheres_plastic(W, H), cam.derived17(), W, H))
+    assert plastic[0] == max(plastic) and plastic[0] > 1.15 * plastic[-1], plastic
+    print("[spheres_metallic] interior sharpness, sphere 0..6:", [round(s, 2) for s in sharp])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["diffuse_single_sphere", "spheres_metallic"])
+def test_gpu_silhouettes_fit_the_reference_renders(hdri_small, name):
+    """the production fp32 traversal on the same primary rays (rounded to fp32, as the device consumes them)"""
+    def gpu_ids(spec, cam17, W, H):
+        sc = spec.scene(hdri_small)
+        rays = _primary_rays(cam17, W, H).astype(np.float32).astype(np.float64)
+        ids, _ = sc.intersect(rays, 32)
+        sc.close()
+        return ids.reshape(H, W)
+
+    ids, fit, _, cam = _check_silhouettes(name, gpu_ids)
+    builder, _ = CASES[name]
+    W, H = cam.x_pixels(), cam.y_pixels()
+    same = (ids == _oracle_ids(builder(W, H), cam.derived17(), W, H)).mean()
+    assert same > 0.999, same  # a handful of silhouette pixels may flip under the fp32 rounding of the ray
+    print(f"[{name}] GPU mask: {fit * 100:.1f} % of the silhouette on an edge of the reference render; == oracle on {same * 100:.3f} % of the pixels")

@@ -129,6 +129,133 @@ def test_sphere_row_orientation_and_roughness_order(native_built):
     print("[spheres_metallic] interior sharpness, sphere 0..6:", [round(s, 2) for s in sharp])
 
 
+def test_mirror_reflections_inside_the_smoothest_sphere(native_built):
+    """The leftmost sphere of the metallic row is almost a mirror (alpha = 0.01, test_scenes.rs:213-224): what it shows —
+    its neighbour, the floor's horizon, the sky — is drawn by Sphere::normal (geometry.rs:134-136), CookTorrance::scatter at
+    the centre of its lobe (half vector = normal: material.rs:403-424,1006-1020 -> reflect, :1492-1496) and the second
+    closest-hit query.  The contours of the oracle's second-hit mask INSIDE that sphere (4 px away from its own silhouette)
+    coincide with edges of the reference's render; shifted by 2 or 3 pixels they do not."""
+    name = "spheres_metallic"
+    dist, W, H = _edge_distance(name)
+    cam = Camera(**ROW)
+    spec = scenes.cook_torrance_spheres_metallic(W, H)
+    tables = spec.tables()
+    osc = oracle.OracleScene(tables, scenes.synthetic_hdri(64, 32).pixels)
+    rays = _primary_rays(cam.derived17(), W, H)
+    ids, t = osc.intersect(rays)
+    first = np.nonzero(ids == 1)[0]                      # object 1 = sphere 0 at x = -6.6
+    o, d = rays[first, :3], rays[first, 3:]
+    p = o + d * t[first, None]                           # Ray::point lib.rs:41-43
+    c = tables.objs[1, 4:7]
+    n = (p - c) / np.linalg.norm(p - c, axis=1, keepdims=True)
+    v = -d / np.linalg.norm(d, axis=1, keepdims=True)
+    # the oracle's own CookTorrance::scatter with the half-vector draw at the centre of the lobe (tan^2 = -alpha^2 ln(1 - 0) = 0)
+    u = np.tile(np.array([0.3, 0.0, 0.5]), (first.size, 1))
+    ev = oracle.material_evaluate(tables.mats[int(tables.objs[1, 1])], np.concatenate([n, v], axis=1), u)
+    assert (ev[:, 0] == 1).all()
+    l = ev[:, 4:7]
+    assert np.abs(l - (2 * np.sum(v * n, 1, keepdims=True) * n - v)).max() < 1e-9   # = reflect(n, v)
+    second, _ = osc.intersect(np.concatenate([p + 1e-9 * l, l], axis=1))
+    osc.close()
+    seen = np.full(H * W, -2)
+    seen[first] = second
+    seen = seen.reshape(H, W)
+    assert (seen == 2).sum() > 1000 and (seen == 0).sum() > 5000 and (seen == -1).sum() > 5000  # neighbour, floor, sky
+    inner = binary_erosion(ids.reshape(H, W) == 1, iterations=4)
+    contour = np.zeros((H, W), dtype=bool)
+    for what in (2, 0, -1):
+        m = seen == what
+        contour |= m & ~binary_erosion(m)
+    contour &= inner
+    assert contour.sum() > 400
+
+    def fit(shift):
+        b = np.roll(np.roll(contour, shift[0], 0), shift[1], 1)
+        return float((dist[b] <= NEAR).mean())
+    aligned = fit((0, 0))
+    assert aligned >= 0.82, aligned
+    worst = max(fit(s) for s in ((0, 2), (0, -2), (2, 0), (-2, 0), (0, 3), (0, -3), (3, 0), (-3, 0), (3, 3), (-3, -3), (3, -3), (-3, 3)))
+    assert worst <= aligned - 0.08, (aligned, worst)
+    print(f"[spheres_metallic, reflections in sphere 0] {aligned * 100:.1f} % of {int(contour.sum())} contour pixels on an edge of the "
+          f"reference render; best shifted hypothesis {worst * 100:.1f} %")
+
+
+def _through_the_glass_sphere(osc, tables, mat_row, rays, ids, t, W, H, straight_through):
+    """contours of what the leftmost glass sphere (object 1) shows by transmission, 4 px inside its own silhouette.
+    Both refractions are the oracle's own CookTorranceGlass::scatter (material.rs:469-565) evaluated at the centre of its
+    lobe (half vector = normal) with the Fresnel draw on the refraction side — i.e. `refract` (material.rs:1502-1518) with
+    the direction / ior bookkeeping of :1191-1231.  straight_through: the far hit of the sphere is lost and the ray goes
+    on in the ONCE-refracted direction — what the reference's re-entry quirk (geometry.rs:106-132 +
+    bvh.rs:404-413) does to part of the rays."""
+    first = np.nonzero(ids == 1)[0]
+    o, d = rays[first, :3], rays[first, 3:]
+    p = o + d * t[first, None]
+    c = tables.objs[1, 4:7]
+    n = (p - c) / np.linalg.norm(p - c, axis=1, keepdims=True)
+    v = -d / np.linalg.norm(d, axis=1, keepdims=True)
+    u = np.tile(np.array([0.3, 0.0, 0.999999]), (first.size, 1))
+    l1 = oracle.material_evaluate(mat_row, np.concatenate([n, v], axis=1), u)[:, 4:7]
+    assert np.all(np.sum(l1 * n, 1) < 0)                        # refracted into the sphere
+    t2 = -2 * np.sum(l1 * (p - c), 1) / np.sum(l1 * l1, 1)      # far root from a point on the sphere
+    p2 = p + l1 * t2[:, None]
+    if straight_through:
+        second, _ = osc.intersect(np.concatenate([p2 + 1e-6 * l1, l1], axis=1))
+    else:
+        n2 = (p2 - c) / np.linalg.norm(p2 - c, axis=1, keepdims=True)
+        v2 = -l1 / np.linalg.norm(l1, axis=1, keepdims=True)
+        l2 = oracle.material_evaluate(mat_row, np.concatenate([n2, v2], axis=1), u)[:, 4:7]
+        assert np.all(np.sum(l2 * n2, 1) > 0)                   # and out again
+        second, _ = osc.intersect(np.concatenate([p2 + 1e-9 * l2, l2], axis=1))
+    seen = np.full(H * W, -2)
+    seen[first] = second
+    seen = seen.reshape(H, W)
+    contour = np.zeros((H, W), dtype=bool)
+    for what in np.unique(second):
+        m = seen == what
+        contour |= m & ~binary_erosion(m)
+    return contour & binary_erosion(ids.reshape(H, W) == 1, iterations=4)
+
+
+def test_refraction_contours_inside_the_clearest_glass_sphere(native_built):
+    """The leftmost sphere of the frosted-glass row is almost clear (alpha = 0.01, ior 1.45, test_scenes.rs:241-256): through
+    it the floor's horizon appears upside down.  Where that contour lies is decided by two refractions at ior 1.45 — and the
+    reference's render shows a SECOND horizon 26 rows lower: the rays whose far hit the reference loses (F7) and which go on
+    once-refracted.  Both contours of the oracle lie on edges of the reference's render; moved vertically by 2-4 pixels, or
+    computed with another index of refraction, they do not."""
+    from rayrs_b200.api import Material, Object, build_tables
+    name = "cook_torrance_spheres_frosted_glass"
+    dist, W, H = _edge_distance(name)
+    cam = Camera(**ROW)
+    spec = scenes.cook_torrance_spheres_frosted_glass(W, H)
+    tables = spec.tables()
+    osc = oracle.OracleScene(tables, scenes.synthetic_hdri(64, 32).pixels)
+    rays = _primary_rays(cam.derived17(), W, H)
+    ids, t = osc.intersect(rays)
+    mat = tables.mats[int(tables.objs[1, 1])]
+    rows_of = {}
+    for through in (False, True):
+        contour = _through_the_glass_sphere(osc, tables, mat, rays, ids, t, W, H, through)
+        assert contour.sum() > 150
+
+        def fit(dy, ct=contour):
+            return float((dist[np.roll(ct, dy, 0)] <= NEAR).mean())
+        aligned = fit(0)
+        assert aligned >= 0.90, (through, aligned)
+        moved = max(fit(dy) for dy in (2, -2, 3, -3, 4, -4))
+        assert moved <= aligned - 0.25, (through, aligned, moved)
+        rows_of[through] = float(np.nonzero(contour)[0].mean())
+        # another glass: the same construction with a different index of refraction misses the reference's edges
+        for ior in (1.33, 1.6):
+            other = build_tables([Object.sphere(1.0, (0, 0, 0), Material.cook_torrance_glass((1, 1, 1), 0.01, ior))]).mats[0]
+            wrong = _through_the_glass_sphere(osc, tables, other, rays, ids, t, W, H, through)
+            assert float((dist[wrong] <= NEAR).mean()) <= aligned - 0.4, (through, ior)
+        print(f"[frosted glass row, sphere 0, {'once-refracted (F7)' if through else 'twice refracted'}] {aligned * 100:.1f} % of "
+              f"{int(contour.sum())} contour pixels on an edge of the reference render (mean row {rows_of[through]:.1f}); "
+              f"moved 2-4 px vertically: at most {moved * 100:.1f} %")
+    osc.close()
+    assert rows_of[True] - rows_of[False] > 15   # two distinct horizons
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["diffuse_single_sphere", "spheres_metallic"])
 def test_gpu_silhouettes_fit_the_reference_renders(hdri_small, name):

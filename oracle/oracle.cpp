@@ -20,9 +20,11 @@
 // pinned against every numeric known-answer test the reference holds for this path
 // (tests/test_oracle_kat.py lists them with file:line), and its camera / primary rays /
 // pixel mapping / sphere-scene constants against the geometry of the six renders the
-// reference ships (examples/*.png; tests/test_reference_images.py).  Triangle intersection,
-// BSDF values, radiance(), background() and tree shape are NOT pinned by any reference
-// test or output ("parity unpinned" for those).
+// reference ships (examples/*.png; tests/test_reference_images.py); its Midpoint build
+// reproduces the expected dumps of the construction tests the reference carries commented
+// out (bvh.rs:436-541).  Triangle intersection, BSDF values, radiance(), background() and the
+// SAH tree shape are NOT pinned by any reference test or output ("parity unpinned" for
+// those).
 //
 // One deliberate deviation: rand::random::<f64>() (thread_rng, OS seeded, not
 // reproducible; lib.rs:206-207,539 and material.rs call sites) is replaced by a

@@ -173,3 +173,64 @@ def test_intersect_sensitivity_is_the_stability_probe_plus_conditioning():
     # a head-on hit of the floor moves by about the perturbation itself; the probe must see that scale
     floor = hit & (oid == 0)
     assert floor.any() and np.median(tchange[floor]) < 1e-4
+
+
+# ---- bvh.rs:436-541: four construction tests the reference carries COMMENTED OUT.  Their expected values are the author's
+# own `{:?}` dumps of `Bvh::build(BvhHeuristic::Midpoint, ..)`; they are not run by `cargo test`, but they are the only
+# statement of a tree SHAPE the reference makes — and the code as it stands still produces them: the oracle's build (both
+# of its build modes), the fast host build of the C++ mirror and its flattening reproduce every one.
+def _dump(objects, mode):
+    from rayrs_b200.api import build_tables
+    s = oracle.OracleScene(build_tables(objects), np.ones((2, 2, 3)), heuristic=(0, 0), build_mode=mode)
+    topo, boxes = s.tree_dump()
+    s.close()
+    return topo.tolist(), boxes
+
+
+def _host_dump(objects):
+    from rayrs_b200.api import BvhHeuristic, Image, Scene
+    sc = Scene(objects, 1e-6, 1e6, BvhHeuristic.Midpoint(), Image(2, 2, np.ones((2, 2, 3))), upload=False)
+    flat = sc.flat()
+    topo, boxes = flat[3].tolist(), flat[4].copy()
+    sc.close()
+    return topo, boxes
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2], ids=["x", "y", "z"])
+def test_commented_out_midpoint_construction_along_an_axis(axis):
+    """bvh.rs:435-487: 8 unit spheres at -10.5 + 3 i along one axis -> Node(all, [Node(left four), Node(right four)]),
+    boxes -11.5..11.5, -11.5..-0.5 and 0.5..11.5 on that axis, -1..1 on the others"""
+    from rayrs_b200.api import Material, Object
+    objects = []
+    for i in range(8):
+        c = [0.0, 0.0, 0.0]
+        c[axis] = -10.5 + 3.0 * i
+        objects.append(Object.sphere(1.0, tuple(c), Material.no_reflect()))
+    want_topo = [-2, -4, 0, 1, 2, 3, -4, 4, 5, 6, 7]
+    want_boxes = np.tile(np.array([-1.0, 1.0] * 3), (3, 1))
+    want_boxes[:, 2 * axis:2 * axis + 2] = [[-11.5, 11.5], [-11.5, -0.5], [0.5, 11.5]]
+    for topo, boxes in (_dump(objects, 0), _dump(objects, 1), _host_dump(objects)):
+        assert topo == want_topo
+        assert np.array_equal(boxes, want_boxes)
+
+
+def test_commented_out_midpoint_construction_sphere_in_center():
+    """bvh.rs:489-541: three walls, a light and a triangle inside a 5 x 5 x 5 box (all three extents tie: the x axis is
+    taken) -> Node(box, [Node(box, [top, bottom]), Node(z -2.5..0.8, [back, light, triangle])]); the dump also spells out
+    Triangle::new's derived fields: e1 (0.5, 0, -0.5), e2 (2, 2, -1), unit normal (2/3, -1/3, 2/3), area 0.75"""
+    from rayrs_b200.api import Axis, Emission, Material, Object
+    nr = Material.no_reflect()
+    top = Object.plane(Axis.YRev, -2.5, 2.5, -2.5, 2.5, 2.5, nr)
+    bottom = Object.plane(Axis.Y, -2.5, 2.5, -2.5, 2.5, -2.5, nr)
+    back = Object.plane(Axis.Z, -2.5, 2.5, -2.5, 2.5, -2.5, nr)
+    light = Object.plane(Axis.YRev, -0.8, 0.8, -0.8, 0.8, 2.4999, nr, Emission.new(5.0, (1, 1, 1)))
+    tri = Object.triangle((-1, -1, -0.5), (-0.5, -1, -1), (1, 1, -1.5), nr)
+    objects = [top, bottom, back, light, tri]
+    want_boxes = np.array([[-2.5, 2.5, -2.5, 2.5, -2.5, 2.5], [-2.5, 2.5, -2.5, 2.5, -2.5, 2.5], [-2.5, 2.5, -2.5, 2.5, -2.5, 0.8]])
+    for topo, boxes in (_dump(objects, 0), _dump(objects, 1), _host_dump(objects)):
+        assert topo == [-2, -2, 0, 1, -3, 2, 3, 4]
+        assert np.array_equal(boxes, want_boxes)
+    _, normal = oracle.triangle_intersect([-1, -1, -0.5, -0.5, -1, -1, 1, 1, -1.5], [0, 0, 5, 0, 0, -1])
+    assert list(normal) == [0.6666666666666666, -0.3333333333333333, 0.6666666666666666]  # the dump's digits
+    area, _ = oracle.hittable_area_sample(tri.rows[0], [0.0, 0.0])
+    assert area == 0.75

@@ -57,6 +57,7 @@ def lib() -> C.CDLL:
         L.orc_aabb_intersect.argtypes = [vp, vp, dbl, dbl]
         L.orc_scene_bbox.argtypes = [vp, vp]
         L.orc_orthonormal_basis.argtypes = [vp, vp]
+        L.orc_vecmath_ops.argtypes = [vp, vp, dbl, vp]
         L.orc_philox.argtypes = [vp, vp, vp, i32]
         L.orc_rng_uniforms.argtypes = [u64, u32, u32, u32, i32, vp]
         L.orc_traversal_counts.argtypes = [vp, vp, u64, vp, vp, vp]
@@ -240,6 +241,15 @@ def triangle_intersect(p9, ray6):
 def aabb_intersect(box6, ray6, tmin, tmax) -> bool:
     b, r = _d(box6), _d(ray6)
     return bool(lib().orc_aabb_intersect(b.ctypes.data, r.ctypes.data, tmin, tmax))
+
+
+def vecmath_ops(a, b, s) -> dict:
+    """the oracle's Vec3 operators on (a, b, s): add, sub, mul, scalar_mul (s * a), mul_scalar (a * s), dot, cross, mag2 (of a)"""
+    out = np.zeros(20)
+    aa, bb = _d(a), _d(b)
+    lib().orc_vecmath_ops(aa.ctypes.data, bb.ctypes.data, float(s), out.ctypes.data)
+    return {"add": out[0:3], "sub": out[3:6], "mul": out[6:9], "scalar_mul": out[9:12], "mul_scalar": out[12:15],
+            "dot": float(out[15]), "cross": out[16:19], "mag2": float(out[19])}
 
 
 def orthonormal_basis(n3):

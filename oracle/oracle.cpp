@@ -1390,6 +1390,17 @@ void orc_scene_bbox(const OrcScene* h, double* out11) {
     double v[11] = {b.xmin, b.xmax, b.ymin, b.ymax, b.zmin, b.zmax, c.x, c.y, c.z, b.volume(), b.surface_area()};
     std::memcpy(out11, v, sizeof(v));
 }
+// The Vec3 operators as the restatement uses them, for the reference's own unit tests (vecmath.rs:816-881):
+// out = [a + b, a - b, a * b, s * a, a * s, a . b, a x b, |a|^2] = 3 + 3 + 3 + 3 + 3 + 1 + 3 + 1 doubles
+void orc_vecmath_ops(const double* a3, const double* b3, double s, double* out20) {
+    V3 a = v3(a3[0], a3[1], a3[2]), b = v3(b3[0], b3[1], b3[2]);
+    V3 r[5] = {a + b, a - b, a * b, s * a, a * s};
+    for (int k = 0; k < 5; ++k) { out20[3 * k] = r[k].x; out20[3 * k + 1] = r[k].y; out20[3 * k + 2] = r[k].z; }
+    out20[15] = dot(a, b);
+    V3 c = cross(a, b);
+    out20[16] = c.x; out20[17] = c.y; out20[18] = c.z;
+    out20[19] = mag2(a);
+}
 void orc_orthonormal_basis(const double* n3, double* e1e2) {
     V3 e1, e2;
     orthonormal_basis(v3(n3[0], n3[1], n3[2]), e1, e2);

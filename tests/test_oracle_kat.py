@@ -234,3 +234,35 @@ def test_commented_out_midpoint_construction_sphere_in_center():
     assert list(normal) == [0.6666666666666666, -0.3333333333333333, 0.6666666666666666]  # the dump's digits
     area, _ = oracle.hittable_area_sample(tri.rows[0], [0.0, 0.0])
     assert area == 0.75
+
+
+# ---- geometry.rs:829-845 test_plane_area / test_plane_sample (the two live reference tests of Hittable::area / sample,
+# restated with the dormant next-event-estimation hook: tests/test_pdf_hook.py)
+def test_plane_area_and_sample():
+    from rayrs_b200.api import Axis, Material, Object
+    row = Object.plane(Axis.Z, -1.0, 1.0, -1.0, 1.0, 0.0, Material.no_reflect()).rows[0]
+    rng = np.random.default_rng(3)
+    for u in rng.random((200, 2)):
+        area, s = oracle.hittable_area_sample(row, u)
+        assert area == 4.0
+        assert -1.0 <= s[0] < 1.0 and -1.0 <= s[1] < 1.0 and s[2] == 0.0   # Range::contains is half-open
+
+
+# ---- vecmath.rs:816-893: the reference's unit tests of the Vec3 operators (cross1 / cross2 fix the handedness everything
+# from orthonormal_basis to the camera frame relies on); powf and clip are the two operators of the output stage
+def test_vecmath_unit_tests():
+    ops = oracle.vecmath_ops([1, 2, 3], [2, 4, 6], 3.0)
+    assert list(ops["add"]) == [3, 6, 9]                                  # test_add
+    assert list(oracle.vecmath_ops([4, 3, 2], [1, 1, 1], 1.0)["sub"]) == [3, 2, 1]      # test_sub
+    assert list(oracle.vecmath_ops([1, 4, 8], [2, 2, 2], 1.0)["mul"]) == [2, 8, 16]     # test_mul
+    assert list(ops["scalar_mul"]) == [3, 6, 9] and list(ops["mul_scalar"]) == [3, 6, 9]  # test_scalar_mul, test_mul_scalar
+    assert oracle.vecmath_ops([1, 2, 3], [1, 2, 3], 1.0)["dot"] == 14.0     # test_dot
+    assert list(oracle.vecmath_ops([1, 0, 0], [0, 1, 0], 1.0)["cross"]) == [0, 0, 1]    # test_cross1
+    assert list(oracle.vecmath_ops([1, 0, 0], [0, 0, 1], 1.0)["cross"]) == [0, -1, 0]   # test_cross2
+    assert ops["mag2"] == 14.0                                             # test_mag2
+    # test_pow (1, 2, 3).powf(2) == (1, 4, 9) and test_clip (-1, 2, 0.5).clip(0, 1) == (0, 1, 0.5), through the restated
+    # output stage that applies them (image.rs:193-222): clip then powf(gamma) then (255.99 x) as u8
+    by, census = oracle.to_raw_bytes(np.array([[[-1.0, 2.0, 0.5]]]), gamma=1.0)
+    assert by[0, 0].tolist() == [0, 255, 127] and census == {"clamped": 1, "nan": 0, "negative": 1}
+    by2, _ = oracle.to_raw_bytes(np.array([[[0.1, 0.2, 0.3]]]), gamma=2.0)
+    assert by2[0, 0].tolist() == [int(255.99 * 0.1 ** 2), int(255.99 * 0.2 ** 2), int(255.99 * 0.3 ** 2)]

@@ -286,6 +286,16 @@ def test_device_f64_code_on_the_host_matches_oracle(host_check, host_scene, kind
     host_check.nee_host_area_sample(C.byref(light), u2.ctypes.data, a4.ctypes.data)
     area, point = oracle.hittable_area_sample(row, u2)
     assert a4[0] == area and np.array_equal(a4[1:], point)
+    if kind == "plane":
+        # the reference's own two tests of this code, geometry.rs:829-845 (test_plane_area, test_plane_sample), on the device's
+        # functions: Plane::new(Axis::Z, -1, 1, -1, 1, 0) has area 4 and samples inside its ranges at z = 0
+        from rayrs_b200 import _ffi
+        kat = _ffi.RrsPrim()
+        kat.type = 1
+        kat.v[0], kat.v[1], kat.v[2], kat.v[3], kat.v[4], kat.v[5] = 4.0, -1.0, 1.0, -1.0, 1.0, 0.0   # RrsAxis Z = 4
+        for uu in np.random.default_rng(3).random((100, 2)):
+            host_check.nee_host_area_sample(C.byref(kat), uu.ctypes.data, a4.ctypes.data)
+            assert a4[0] == 4.0 and -1.0 <= a4[1] < 1.0 and -1.0 <= a4[2] < 1.0 and a4[3] == 0.0
     q, u = _inputs(100_000, 21)
     u3 = np.ascontiguousarray(u[:, :3])
     got = np.zeros((q.shape[0], 7))

@@ -256,6 +256,26 @@ def test_refraction_contours_inside_the_clearest_glass_sphere(native_built):
     assert rows_of[True] - rows_of[False] > 15   # two distinct horizons
 
 
+def test_refracted_horizon_in_the_single_glass_sphere(native_built):
+    """cook_torrance_glass_single_sphere (test_scenes.rs:65-68: alpha 0.05, ior 1.45) with the single-sphere camera: the lobe
+    is five times wider and the sphere 2.5 times larger on screen than in the row, so the refracted horizon is a soft edge — the
+    fit is lower, but it still peaks where the oracle puts the contour and falls off within 4 rows either way."""
+    name = "cook_torrance_glass_sphere"
+    dist, W, H = _edge_distance(name)
+    cam = Camera(**SINGLE)
+    tables = scenes.cook_torrance_glass_single_sphere(W, H).tables()
+    osc = oracle.OracleScene(tables, scenes.synthetic_hdri(64, 32).pixels)
+    rays = _primary_rays(cam.derived17(), W, H)
+    ids, t = osc.intersect(rays)
+    contour = _through_the_glass_sphere(osc, tables, tables.mats[int(tables.objs[1, 1])], rays, ids, t, W, H, False)
+    osc.close()
+    assert contour.sum() > 500
+    fit = {dy: float((dist[np.roll(contour, dy, 0)] <= NEAR).mean()) for dy in (0, 2, -2, 4, -4, 8, -8)}
+    assert fit[0] == max(fit.values()) and fit[0] >= 0.45, fit
+    assert max(fit[4], fit[-4]) <= fit[0] - 0.2 and max(fit[8], fit[-8]) <= fit[0] - 0.3, fit
+    print("[cook_torrance_glass_sphere, twice-refracted horizon] fit by vertical offset:", {k: round(v, 3) for k, v in fit.items()})
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["diffuse_single_sphere", "spheres_metallic"])
 def test_gpu_silhouettes_fit_the_reference_renders(hdri_small, name):

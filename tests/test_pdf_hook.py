@@ -173,7 +173,7 @@ def test_hittable_area_and_sample_closed_forms(native_built):
 def test_oracle_lambertian_with_pdf_matches_numpy_restatement(native_built, kind):
     objs, light_obj = _tables()
     row = objs[light_obj[kind]].rows[0]
-    mat_row = Scene_tables(objs).mats[list(MATS).index("lambertian")]
+    mat_row = _tables_of(objs).mats[list(MATS).index("lambertian")]
     q, u = _inputs(50_000, 7)
     o = oracle.material_evaluate_pdf(mat_row, row, q, u)
     l, color, pdf, hit, side = _np_lambert_with_pdf(ALBEDO, kind, row, q, u[:, :3])
@@ -203,7 +203,7 @@ def test_oracle_reproduces_pdf_hook_golden(native_built):
     from pathlib import Path
     g = np.load(Path(__file__).resolve().parent / "golden" / "pdf_hook_golden.npz")
     objs, light_obj = _tables()
-    mats = Scene_tables(objs).mats
+    mats = _tables_of(objs).mats
     q, u = _inputs(512, 5)
     assert np.array_equal(q, g["q"]) and np.array_equal(u, g["u"])
     for kind in sorted(LIGHTS):
@@ -212,7 +212,7 @@ def test_oracle_reproduces_pdf_hook_golden(native_built):
             assert np.array_equal(got, g[f"{kind}/{mname}"], equal_nan=True), (kind, mname)
 
 
-def Scene_tables(objs):
+def _tables_of(objs):
     from rayrs_b200.api import build_tables
     return build_tables(objs)
 
@@ -220,7 +220,7 @@ def Scene_tables(objs):
 def test_oracle_materials_that_ignore_the_pdf(native_built):
     """every arm but the diffuse lobe names its parameter `_pdf`: same event as evaluate(..., None)"""
     objs, light_obj = _tables()
-    t = Scene_tables(objs)
+    t = _tables_of(objs)
     q, u = _inputs(20_000, 11)
     row = objs[light_obj["sphere"]].rows[0]
     for name in ("ct_copper", "glass"):
